@@ -1,0 +1,213 @@
+/* nasb200.h -- C ABI of libnasb200.so: the B200 (sm_100a) kernels behind the NAS inner-loop hot path of
+ * DrSleep/nas-segm-pytorch (reference paths below are relative to the reference repo root).
+ *
+ * The reference has no FFI: its "plugin API" is the Python op/cell registry (src/nn/layer_factory.py:27-91),
+ * the decoder/encoder modules (src/nn/micro_decoders.py, src/nn/encoders.py), the engine functions
+ * (src/engine/trainer.py:17,78,179; src/engine/inference.py:18) and the Cython metric
+ * (src/helpers/miou_utils.pyx:7,32,59).  The host mirror of those (nas-segm-pytorch_b200/{nn,engine,helpers})
+ * crosses exactly this boundary; every entry point says which reference code it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless marked host.  Pointers are borrowed; nothing is allocated.
+ *  - Activations are NHWC ("channels-last"): element (n,y,x,c) of tensor t is at
+ *    t.ptr[((n*h + y)*w + x)*cstride + c]; cstride >= c lets a tensor be a channel slice of a wider buffer
+ *    (this is how torch.cat along channels is realised without a copy).
+ *  - dtype: NASB_F32 or NASB_BF16 (fp32 accumulation everywhere).  NASB_F32_NCHW marks the planar fp32 image
+ *    handed to the encoder stem (the layout the reference's DataLoader produces).
+ *  - Parameters (conv weights, BN vectors, biases) are always fp32 in the reference's own layouts
+ *    (conv weight [C_out][C_in/groups][kH][kW]); gradients are fp32 and are ACCUMULATED (+=) into the buffer.
+ *  - `stream` is a cudaStream_t passed as void*.
+ *  - Return value: 0 on success, otherwise a cudaError_t value or NASB_ERR_*.  The Python shim raises
+ *    RuntimeError for any non-zero value (reference error convention: src/helpers/utils.py:172-187).
+ */
+#ifndef NASB200_H_
+#define NASB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NASB_F32 0
+#define NASB_BF16 1
+#define NASB_F32_NCHW 2
+
+#define NASB_ACT_NONE 0
+#define NASB_ACT_RELU 1
+#define NASB_ACT_RELU6 2
+
+#define NASB_POOL_MAX 0
+#define NASB_POOL_AVG 1
+
+#define NASB_ERR_UNSUPPORTED 10001
+#define NASB_ERR_BAD_ARG 10002
+
+typedef struct NasbTensor {
+    void *ptr;
+    int32_t n, h, w, c;
+    int32_t cstride;
+    int32_t dtype;
+} NasbTensor;
+
+/* library / build identification: returns a static string "nasb200 <version> sm_100a" */
+const char *nasb_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM (dense k x k, k in {1,3}; any stride / dilation / padding).
+ * Replaces nn.Conv2d(+BatchNorm2d eval +ReLU/ReLU6 +residual) chains: layer_factory.py:7-24 (conv3x3/conv1x1),
+ * :56-75 (registry conv ops), :94-114 (conv_bn, conv_bn_relu, conv_bn_relu6), :125-158 (InvertedResidual
+ * pointwise convs), :316-335 (Adapt), :369-382 (ConcatReduce: BN->ReLU->1x1 over a channel concat),
+ * micro_decoders.py:44-45,218-224 (adapt / pre_clf / conv_clf / aux_clf).
+ *
+ *   out = act( out_scale[co] * sum_{tap,ci} pro(x)[.., ci] * W[co][ci][tap] + out_shift[co] ) (+ res)
+ *   pro(x) = in_relu ? relu(x*in_scale[ci]+in_shift[ci]) : x*in_scale+in_shift      (only if in_scale != NULL)
+ * x is the channel concatenation of x0 and (optional) x1, which share n,h,w.
+ * out_scale / out_shift may be NULL (identity / zero); a conv bias is passed as out_shift with out_scale NULL.
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_conv_fwd(const NasbTensor *x0, const NasbTensor *x1, const float *weight, int ks, int stride, int dil,
+                  int pad, const float *in_scale, const float *in_shift, int in_relu, const float *out_scale,
+                  const float *out_shift, int act, const NasbTensor *res, const NasbTensor *out, void *stream);
+
+/* dx = conv^T(dz): gradient w.r.t. the (concatenated) conv input; dx1 may be NULL.  dx0/dx1 are fully written. */
+int nasb_conv_dgrad(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
+                    const NasbTensor *dx0, const NasbTensor *dx1, void *stream);
+
+/* dweight[co][ci][tap] += sum_pixels dz[.., co] * pro(x)[.., ci];  dweight is fp32 in the reference layout. */
+int nasb_conv_wgrad(const NasbTensor *x0, const NasbTensor *x1, const float *in_scale, const float *in_shift,
+                    int in_relu, const NasbTensor *dz, int ks, int stride, int dil, int pad, float *dweight,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Depthwise k x k convolution (groups == channels), k in {3,5,7}, any stride/dilation/padding, with optional
+ * folded BN + activation epilogue.  Replaces the depthwise nn.Conv2d of SepConv / DilConv
+ * (layer_factory.py:198-265) and of InvertedResidual (:141-151).   weight: [C][1][k][k].
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_dwconv_fwd(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int in_relu,
+                    const float *out_scale, const float *out_shift, int act, const NasbTensor *out, void *stream);
+int nasb_dwconv_dgrad(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
+                      const NasbTensor *dx, void *stream);
+int nasb_dwconv_wgrad(const NasbTensor *x, int in_relu, const NasbTensor *dz, int ks, int stride, int dil, int pad,
+                      float *dweight, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BatchNorm2d pieces (eps 1e-5, momentum 0.1 in the reference; both are arguments here).
+ * nasb_bn_fold      : running stats -> per-channel (scale, shift) for the fused eval-mode epilogues.
+ * nasb_bn_stats     : training mode: batch mean / biased var of z over (n,h,w); updates running stats
+ *                     (unbiased var, momentum) exactly like nn.BatchNorm2d.train(); also emits (scale, shift).
+ *                     workspace: >= nasb_bn_stats_workspace(C) bytes.
+ * nasb_affine_act   : y = act(z*scale[c]+shift[c])                       (in place allowed)
+ * nasb_bn_act_bwd   : backward of y = act(gamma*xhat+beta):
+ *                       g = dy * act'(y); dbeta += sum g; dgamma += sum g*xhat
+ *                       xhat = (z-save_mean)*save_rstd in training (z = saved conv output), and is rebuilt from
+ *                       y as (y-beta)/gamma in eval mode (only unmasked pixels matter there).  dz may alias dy.
+ *                       eval : dz = g * scale
+ *                       train: dz = scale * (g - mean(g) - xhat*mean(g*xhat))
+ *                     workspace: >= nasb_bn_stats_workspace(C) bytes.
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_bn_fold(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int C,
+                 float *scale, float *shift, void *stream);
+long long nasb_bn_stats_workspace(int C);
+int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
+                  float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
+                  float *shift, void *workspace, void *stream);
+int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift, int act, const NasbTensor *y,
+                    void *stream);
+int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,
+                    const float *beta, const float *scale, const float *save_mean, const float *save_rstd,
+                    int training, float *dgamma, float *dbeta, const NasbTensor *dz, void *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 3x3 pooling, padding 1 (layer_factory.py:161-178).  Max pooling optionally records the arg-max tap
+ * (uint8, same NHW C layout, dense) for the backward pass; avg pooling is count_include_pad=False.
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_pool3x3_fwd(const NasbTensor *x, int mode, int stride, const NasbTensor *out, uint8_t *argmax,
+                     void *stream);
+int nasb_pool3x3_bwd(const NasbTensor *dy, int mode, int stride, const uint8_t *argmax, const NasbTensor *dx,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Bilinear resize, align_corners=False, up or down (layer_factory.py:338-350, micro_decoders.py:11-25,47-50,
+ * trainer.py:141-143,153-155, inference.py:58-60), fused with the aggregation that follows it:
+ *    out = sa[c] * resize(x) + sb[c] * y        (sa, sb NULL = 1;  y NULL = no second operand)
+ * When x already has out's size the resize is the identity.  Covers AggregateCell's sum
+ * (micro_decoders.py:51), ParamSum (layer_factory.py:353-366) and writing resized maps into concat slices.
+ * nasb_resize_bwd : dx = resize^T(sa * dz)   (deterministic gather form)
+ * nasb_axpby_bwd_params : dsa[c] += sum dz*resize(x), dsb[c] += sum dz*y  (ParamSum's a / b gradients)
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_resize_axpby(const NasbTensor *x, const float *sa, const NasbTensor *y, const float *sb,
+                      const NasbTensor *out, void *stream);
+int nasb_resize_bwd(const NasbTensor *dz, const float *sa, const NasbTensor *dx, void *stream);
+int nasb_axpby_bwd_params(const NasbTensor *dz, const NasbTensor *x, const NasbTensor *y, float *dsa, float *dsb,
+                          void *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Small data-movement ops.
+ * nasb_scale_copy   : out = s[c] * x (s NULL = 1), dtype conversion allowed (concat-slice writes, dY = b*dz)
+ * nasb_channel_tile : Skip / Zero (layer_factory.py:268-297): out[.., r*C+c] = scale * x[.., c] with spatial
+ *                     subsampling by `stride` (Zero honours stride, Skip passes 1); scale 0 gives exact zeros.
+ * nasb_channel_tile_bwd : dx[.., c] = scale * sum_r dz[.., r*C+c] scattered to the strided positions.
+ * nasb_spatial_mean : GAPConv1x1's mean over H then W (layer_factory.py:189): out[n,c] fp32.
+ * nasb_spatial_bcast: out[n,y,x,c] = s * v[n,c]  (bilinear resize from a 1x1 map is a broadcast; also GAP bwd)
+ * nasb_spatial_sum  : out[n,c] = sum_{y,x} x[n,y,x,c]   (fp32; backward of the broadcast)
+ * nasb_channel_sum  : out[c] += sum over all pixels x[..,c]  (conv bias gradient)
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_scale_copy(const NasbTensor *x, const float *s, int relu, const NasbTensor *out, void *stream);
+int nasb_channel_tile(const NasbTensor *x, int stride, float scale, const NasbTensor *out, void *stream);
+int nasb_channel_tile_bwd(const NasbTensor *dz, int stride, float scale, const NasbTensor *dx, void *stream);
+int nasb_spatial_mean(const NasbTensor *x, float *out_nc, void *stream);
+int nasb_spatial_bcast(const NasbTensor *v_nc, float s, const NasbTensor *out, void *stream);
+int nasb_spatial_sum(const NasbTensor *x, float *out_nc, void *stream);
+int nasb_channel_sum(const NasbTensor *x, float *out_c, void *workspace, void *stream);
+int nasb_relu_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *dx, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Losses (trainer.py:144-158, main_search.py:435,458).
+ * nasb_ce_fwd : LogSoftmax(dim=C) + NLLLoss2d(ignore_index, mean over non-ignored pixels).
+ *               target: int64 [n,h,w].  out2[0] = loss (fp32), out2[1] = number of valid pixels (fp32).
+ *               workspace >= nasb_loss_workspace() bytes.
+ * nasb_ce_bwd : dlogits = gscale * (softmax - onehot) / n_valid   (0 at ignored pixels); n_valid read from out2[1].
+ * nasb_mse_*  : nn.MSELoss() (mean over all elements) between x and y.
+ * nasb_berhu_*: reverse Huber (defined by this repo): valid = target > valid_min.
+ * -------------------------------------------------------------------------------------------------------*/
+long long nasb_loss_workspace(void);
+int nasb_ce_fwd(const NasbTensor *logits, const int64_t *target, int ignore_index, float *out2, void *workspace,
+                void *stream);
+int nasb_ce_bwd(const NasbTensor *logits, const int64_t *target, int ignore_index, const float *out2,
+                const float *gscale_dev, const NasbTensor *dlogits, void *stream);
+int nasb_mse_fwd(const NasbTensor *x, const NasbTensor *y, float *out1, void *workspace, void *stream);
+int nasb_mse_bwd(const NasbTensor *x, const NasbTensor *y, const float *gscale_dev, const NasbTensor *dx,
+                 void *stream);
+int nasb_berhu_fwd(const NasbTensor *pred, const NasbTensor *target, float valid_min, float *out3, void *workspace,
+                   void *stream);
+int nasb_berhu_bwd(const NasbTensor *pred, const NasbTensor *target, float valid_min, const float *out3,
+                   const float *gscale_dev, const NasbTensor *dpred, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Metric: the CUDA replacement of the Cython module src/helpers/miou_utils.pyx.
+ * nasb_confmat_labels : fast_cm (:7-30): cm[gt[i]][pred[i]] += 1 for i < n (rows = ground truth), int64,
+ *                       ACCUMULATES into cm (caller zeroes).  Entries with gt >= n_classes or
+ *                       pred >= n_classes are skipped (the reference caller pre-masks gt < n_classes,
+ *                       inference.py:65, so the mask can be fused here).
+ * nasb_confmat_logits : inference.py:58-66 fused: bilinear-upsample logits [n,h,w,C] to the label size,
+ *                       arg-max over classes (first maximal index), uint8 labels gt [n,H,W], mask
+ *                       gt < n_classes, accumulate.  Removes the full-logits device->host copy.
+ * nasb_ius_accs       : compute_iu / compute_ius_accs (:32-90): float64 IoU, int64 n_pixels, float64 acc;
+ *                       32-bit unsigned accumulators exactly like the reference; default value 2.
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_confmat_labels(const uint8_t *pred, const uint8_t *gt, long long n, int n_classes, long long *cm,
+                        void *stream);
+int nasb_confmat_logits(const NasbTensor *logits, const uint8_t *gt, int H, int W, int n_classes, long long *cm,
+                        void *stream);
+int nasb_ius_accs(const long long *cm, int n_classes, double *iu, long long *n_pixels, double *accs, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimiser-side fused passes over a flat fp32 buffer (trainer.py:163-169; "next" row f2 of the scope table).
+ * nasb_sumsq : out[0] += sum x^2   (global grad-norm for clip_grad_norm_)
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_sumsq(const float *x, long long n, float *out1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NASB200_H_ */

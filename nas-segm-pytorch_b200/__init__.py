@@ -1,0 +1,49 @@
+"""nas-segm-pytorch_b200 -- B200-native (sm_100a) implementation of the NAS inner-loop hot path of
+DrSleep/nas-segm-pytorch behind the reference's own registry / module / engine API.
+
+Host code is Python/PyTorch (device memory, streams, autograd glue); every arithmetic step on the path runs in the
+hand-written CUDA kernels of ``libnasb200.so`` (C ABI: ``include/nasb200.h``).  There is no CPU or eager fallback:
+importing the compute modules without the built library, or running them without a CUDA device, raises.
+
+Sub-packages mirror the reference's ``src/`` layout: ``nn`` (op/cell registry, decoders, encoder), ``rl.genotypes``
+(name tables), ``engine`` (populate_task0 / train_task0 / train_segmenter / validate), ``helpers.miou_utils``
+(fast_cm / compute_iu / compute_ius_accs).  ``dropin()`` registers them under the reference's top-level module names.
+"""
+import sys as _sys
+
+__version__ = "0.1.0"
+
+
+class _Config:
+    """Process-wide numeric mode.  ``act_dtype`` is the storage type of activations inside the network:
+    torch.float32 = parity mode (matches the reference within 1e-3 on logits), torch.bfloat16 = speed mode."""
+
+    def __init__(self):
+        import torch
+        self.act_dtype = torch.float32
+        self.use_tcgen05 = True  # bf16 pointwise convolutions on the tensor cores when shapes allow
+
+
+_config = None
+
+
+def config():
+    global _config
+    if _config is None:
+        _config = _Config()
+    return _config
+
+
+def set_act_dtype(dtype):
+    config().act_dtype = dtype
+
+
+def dropin():
+    """Register this package's sub-packages under the reference's import names (``nn``, ``rl``, ``engine``,
+    ``helpers``) so reference-side code such as ``from nn.micro_decoders import MicroDecoder`` or
+    ``from helpers.miou_utils import fast_cm`` binds to the B200 implementation unchanged."""
+    import importlib
+    me = __name__
+    for sub in ("rl", "rl.genotypes", "nn", "nn.layer_factory", "nn.micro_decoders", "nn.encoders", "helpers",
+                "helpers.utils", "helpers.miou_utils", "engine", "engine.trainer", "engine.inference"):
+        _sys.modules[sub] = importlib.import_module(me + "." + sub)

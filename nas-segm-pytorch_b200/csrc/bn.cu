@@ -1,0 +1,314 @@
+// bn.cu -- BatchNorm2d pieces: eval-mode folding, training-mode batch statistics (+ running-stat update), the
+// affine+activation pass, and the backward of y = act(gamma*xhat + beta).  All reductions accumulate in fp64
+// (per-thread and across CTAs through fp64 atomics), so the fp32 results do not depend on summation order.
+#include "common.cuh"
+
+namespace nasb {
+
+__global__ void bn_fold_kernel(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int C,
+                               float *scale, float *shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    float s = g / sqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = b - mean[c] * s;
+}
+
+// ws[0..C) += sum z ; ws[C..2C) += sum z^2        block (32 channel lanes x 8 pixel lanes), one pixel slab per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) bn_sums_kernel(const T *z, int cs, long long P, int C, double *ws,
+                                                      long long rows_per_cta) {
+    __shared__ double r1[256], r2[256];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta, rend = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
+    double a = 0.0, b = 0.0;
+    if (c < C)
+        for (long long m = r0 + threadIdx.y; m < rend; m += 8) {
+            double v = (double)to_f(z[m * cs + c]);
+            a += v;
+            b += v * v;
+        }
+    const int lin = threadIdx.y * 32 + threadIdx.x;
+    r1[lin] = a;
+    r2[lin] = b;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < 8; ++i) {
+            s1 += r1[i * 32 + threadIdx.x];
+            s2 += r2[i * 32 + threadIdx.x];
+        }
+        atomicAdd(&ws[c], s1);
+        atomicAdd(&ws[C + c], s2);
+    }
+}
+
+__global__ void bn_stats_finalize_kernel(const double *ws, long long P, int C, const float *gamma, const float *beta,
+                                         float eps, float momentum, float *running_mean, float *running_var,
+                                         float *save_mean, float *save_rstd, float *scale, float *shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean = ws[c] / (double)P;
+    double var = ws[C + c] / (double)P - mean * mean;  // biased
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_rstd) save_rstd[c] = rstd;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) {
+        double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    float s = g * rstd;
+    scale[c] = s;
+    shift[c] = b - (float)mean * s;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) affine_act_kernel(const T *z, int z_cs, const float *scale, const float *shift, int act,
+                                                         T *y, int y_cs, long long P, int C) {
+    const int CV = C / V;
+    const long long total = P * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        float v[V];
+        load_vec<T, V>(z + pix * z_cs + cv * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float s = scale ? scale[cv * V + j] : 1.f, b = shift ? shift[cv * V + j] : 0.f;
+            v[j] = apply_act(v[j] * s + b, act);
+        }
+        store_vec<T, V>(y + pix * y_cs + cv * V, v);
+    }
+}
+
+__device__ __forceinline__ float xhat_from_y(float y, float gamma, float beta) {
+    return gamma != 0.f ? (y - beta) / gamma : 0.f;
+}
+
+// ws[0..C) += sum g ; ws[C..2C) += sum g*xhat   with g = dy * act'(y)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs, const T *y, int y_cs, const T *z, int z_cs,
+                                                          const float *mean, const float *rstd, int act,
+                                                          const float *gamma, const float *beta, long long P, int C,
+                                                          double *ws, long long rows_per_cta) {
+    __shared__ double r1[256], r2[256];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta, rend = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+        float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+        float mu = z ? mean[c] : 0.f, rs = z ? rstd[c] : 0.f;
+        for (long long m = r0 + threadIdx.y; m < rend; m += 8) {
+            float yy = to_f(y[m * y_cs + c]);
+            float g = to_f(dy[m * dy_cs + c]) * act_mask(yy, act);
+            float xh = z ? (to_f(z[m * z_cs + c]) - mu) * rs : xhat_from_y(yy, ga, be);
+            a += (double)g;
+            b += (double)(g * xh);
+        }
+    }
+    const int lin = threadIdx.y * 32 + threadIdx.x;
+    r1[lin] = a;
+    r2[lin] = b;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < 8; ++i) {
+            s1 += r1[i * 32 + threadIdx.x];
+            s2 += r2[i * 32 + threadIdx.x];
+        }
+        atomicAdd(&ws[c], s1);
+        atomicAdd(&ws[C + c], s2);
+    }
+}
+
+// dgamma += sum g*xhat ; dbeta += sum g ; coef[0..C) = mean g ; coef[C..2C) = mean g*xhat  (fp32, aliased after ws)
+__global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, float *dgamma, float *dbeta, float *coef) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = ws[c], s2 = ws[C + c];
+    if (dbeta) dbeta[c] += (float)s1;
+    if (dgamma) dgamma[c] += (float)s2;
+    coef[c] = (float)(s1 / (double)P);
+    coef[C + c] = (float)(s2 / (double)P);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, const T *y, int y_cs, const T *z, int z_cs,
+                                                        const float *mean, const float *rstd, int act,
+                                                        const float *scale,
+                                                        const float *coef, int training, T *dz, int dz_cs, long long P,
+                                                        int C) {
+    const int CV = C / V;
+    const long long total = P * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        float g[V], yy[V], zz[V];
+        load_vec<T, V>(dy + pix * dy_cs + cv * V, g);
+        load_vec<T, V>(y + pix * y_cs + cv * V, yy);
+        if (training) load_vec<T, V>(z + pix * z_cs + cv * V, zz);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            int c = cv * V + j;
+            float gm = g[j] * act_mask(yy[j], act);
+            float s = scale ? scale[c] : 1.f;
+            if (training) {
+                float xh = (zz[j] - mean[c]) * rstd[c];
+                g[j] = s * (gm - coef[c] - xh * coef[C + c]);
+            } else {
+                g[j] = s * gm;
+            }
+        }
+        store_vec<T, V>(dz + pix * dz_cs + cv * V, g);
+    }
+}
+
+static inline void slab_grid(long long P, int C, dim3 &grid, long long &rows) {
+    int cblocks = cdiv(C, 32);
+    long long want = (long long)NASB_SM_COUNT * 8 / cblocks;
+    if (want < 1) want = 1;
+    rows = (P + want - 1) / want;
+    if (rows < 64) rows = 64;
+    grid = dim3(cblocks, cdiv(P, rows));
+}
+
+static inline int ew_grid(long long total) {
+    long long b = (total + 255) / 256, cap = (long long)NASB_SM_COUNT * 32;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace nasb
+
+using namespace nasb;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int nasb_bn_fold(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int C,
+                            float *scale, float *shift, void *stream) {
+    if (!mean || !var || !scale || !shift || C <= 0) return NASB_ERR_BAD_ARG;
+    bn_fold_kernel<<<cdiv(C, 128), 128, 0, ST>>>(gamma, beta, mean, var, eps, C, scale, shift);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// 2*C doubles for the sums, then 2*C floats for the backward coefficients
+extern "C" long long nasb_bn_stats_workspace(int C) { return (long long)C * (2 * 8 + 2 * 4); }
+
+extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
+                             float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
+                             float *shift, void *workspace, void *stream) {
+    if (!z || !scale || !shift || !workspace || (z->dtype != NASB_F32 && z->dtype != NASB_BF16)) return NASB_ERR_BAD_ARG;
+    long long P = npix(*z);
+    int C = z->c;
+    if (P == 0) return NASB_ERR_BAD_ARG;
+    double *ws = (double *)workspace;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid;
+    long long rows;
+    slab_grid(P, C, grid, rows);
+    if (z->dtype == NASB_BF16)
+        bn_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
+    else
+        bn_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)z->ptr, z->cstride, P, C, ws, rows);
+    NASB_CHECK_LAUNCH();
+    bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                           save_mean, save_rstd, scale, shift);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift, int act, const NasbTensor *y,
+                               void *stream) {
+    if (!z || !y || z->dtype != y->dtype || (z->dtype != NASB_F32 && z->dtype != NASB_BF16) || z->c != y->c ||
+        npix(*z) != npix(*y))
+        return NASB_ERR_BAD_ARG;
+    long long P = npix(*z);
+    if (P == 0) return 0;
+    int C = z->c;
+    if (z->dtype == NASB_BF16) {
+        if (vec_ok(*z, 8) && vec_ok(*y, 8))
+            affine_act_kernel<bf16, 8><<<ew_grid(P * (C / 8)), 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+                                                                             (bf16 *)y->ptr, y->cstride, P, C);
+        else
+            affine_act_kernel<bf16, 1><<<ew_grid(P * C), 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+                                                                       (bf16 *)y->ptr, y->cstride, P, C);
+    } else {
+        if (vec_ok(*z, 4) && vec_ok(*y, 4))
+            affine_act_kernel<float, 4><<<ew_grid(P * (C / 4)), 256, 0, ST>>>((const float *)z->ptr, z->cstride, scale, shift, act,
+                                                                              (float *)y->ptr, y->cstride, P, C);
+        else
+            affine_act_kernel<float, 1><<<ew_grid(P * C), 256, 0, ST>>>((const float *)z->ptr, z->cstride, scale, shift, act,
+                                                                        (float *)y->ptr, y->cstride, P, C);
+    }
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,
+                               const float *beta, const float *scale, const float *save_mean, const float *save_rstd,
+                               int training, float *dgamma, float *dbeta, const NasbTensor *dz, void *workspace,
+                               void *stream) {
+    if (!dy || !y || !dz || !workspace) return NASB_ERR_BAD_ARG;
+    if (training && (!z || !save_mean || !save_rstd || z->dtype != dy->dtype || z->c != dy->c || npix(*z) != npix(*dy)))
+        return NASB_ERR_BAD_ARG;
+    if (!training) z = nullptr;
+    const void *zp = z ? z->ptr : nullptr;
+    const int zcs = z ? z->cstride : 0;
+    if (dy->dtype != y->dtype || dy->dtype != dz->dtype || (dy->dtype != NASB_F32 && dy->dtype != NASB_BF16))
+        return NASB_ERR_BAD_ARG;
+    if (dy->c != y->c || dy->c != dz->c || npix(*dy) != npix(*y) || npix(*dy) != npix(*dz)) return NASB_ERR_BAD_ARG;
+    long long P = npix(*dy);
+    if (P == 0) return 0;
+    int C = dy->c;
+    double *ws = (double *)workspace;
+    float *coef = (float *)(ws + 2 * C);
+    bool need_sums = training || dgamma || dbeta;
+    if (need_sums) {
+        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST);
+        if (e != cudaSuccess) return (int)e;
+        dim3 grid;
+        long long rows;
+        slab_grid(P, C, grid, rows);
+        if (dy->dtype == NASB_BF16)
+            bn_bwd_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
+                                                                   y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act,
+                                                                   gamma, beta, P, C, ws, rows);
+        else
+            bn_bwd_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
+                                                                    y->cstride, (const float *)zp, zcs, save_mean, save_rstd, act,
+                                                                    gamma, beta, P, C, ws, rows);
+        NASB_CHECK_LAUNCH();
+        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef);
+        NASB_CHECK_LAUNCH();
+    }
+    if (dy->dtype == NASB_BF16) {
+        if (vec_ok(*dy, 8) && vec_ok(*y, 8) && vec_ok(*dz, 8) && (!z || vec_ok(*z, 8)))
+            bn_bwd_dz_kernel<bf16, 8><<<ew_grid(P * (C / 8)), 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
+                                                                            y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, coef,
+                                                                            training, (bf16 *)dz->ptr, dz->cstride, P, C);
+        else
+            bn_bwd_dz_kernel<bf16, 1><<<ew_grid(P * C), 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
+                                                                      y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, coef,
+                                                                      training, (bf16 *)dz->ptr, dz->cstride, P, C);
+    } else {
+        if (vec_ok(*dy, 4) && vec_ok(*y, 4) && vec_ok(*dz, 4) && (!z || vec_ok(*z, 4)))
+            bn_bwd_dz_kernel<float, 4><<<ew_grid(P * (C / 4)), 256, 0, ST>>>((const float *)dy->ptr, dy->cstride,
+                                                                             (const float *)y->ptr, y->cstride, (const float *)zp, zcs, save_mean,
+                                                                             save_rstd, act, scale, coef, training, (float *)dz->ptr,
+                                                                             dz->cstride, P, C);
+        else
+            bn_bwd_dz_kernel<float, 1><<<ew_grid(P * C), 256, 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
+                                                                       y->cstride, (const float *)zp, zcs, save_mean, save_rstd, act, scale, coef,
+                                                                       training, (float *)dz->ptr, dz->cstride, P, C);
+    }
+    NASB_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,184 @@
+"""Training functions with the reference's signatures (src/engine/trainer.py) on the fused kernel path.
+
+  populate_task0(segmenter, train_loader, kd_net, n_train, do_kd=False) -> dict            (trainer.py:17-74)
+  train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch_size, freeze_bn, do_kd, kd_coeff,
+              dec_grad_clip, do_polyak, avg_param=None, polyak_decay=0.9, aux_weight=0) -> None   (trainer.py:78-175)
+  train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_crit, freeze_bn, enc_grad_clip,
+              dec_grad_clip, do_polyak, print_every=10, aux_weight=-1, avg_param=None, polyak_decay=0.99) -> None
+                                                                                                 (trainer.py:179-283)
+``segmenter`` is the DataParallel-style wrapper: ``segmenter.module.{encoder,decoder}``.  All four engine functions
+are wrapped by ``try_except``: RuntimeError -> return 0.
+
+Differences that do not change results: the loss (bilinear resize + LogSoftmax + NLL(ignore) [+ KD-MSE] [+ aux]) runs in
+the fused loss kernels instead of four torch passes, and the per-iteration ``loss.item()`` device sync of the reference
+(trainer.py:165) is replaced by one sync per epoch for the logged average.
+"""
+import logging
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import functional as Fn
+from ..helpers.utils import try_except
+
+logger = logging.getLogger(__name__)
+
+
+def _ignore_index(crit):
+    return int(getattr(crit, "ignore_index", 255))
+
+
+def _segm_loss(crit, logits, target, size=None):
+    """segm_crit(LogSoftmax(resize(logits)), target) -- fused when crit is the reference's NLL criterion."""
+    if size is not None:
+        logits = Fn.resize(Fn.lib.to_nhwc(logits), size)
+    if crit is None or isinstance(crit, (nn.NLLLoss,)) or hasattr(crit, "ignore_index"):
+        return Fn.cross_entropy2d(logits, target, _ignore_index(crit) if crit is not None else 255)
+    return crit(nn.functional.log_softmax(logits.float(), dim=1), target)
+
+
+def _set_stage(loader, stage):
+    try:
+        loader.dataset.set_stage(stage)
+    except AttributeError:
+        try:
+            loader.dataset.dataset.set_stage(stage)
+        except AttributeError:
+            pass
+
+
+@try_except
+def populate_task0(segmenter, train_loader, kd_net, n_train, do_kd=False):
+    """Cache the encoder's outputs (NHWC, activation dtype), nearest-resized int64 labels and optional KD targets."""
+    Xy_train = defaultdict(list)
+    segmenter.eval()
+    _set_stage(train_loader, "train")
+    try:
+        train_loader.batch_sampler.batch_size = 1  # reference: batch 1 "to not run out of memory"
+    except AttributeError:
+        pass
+    with torch.no_grad():
+        n_curr = 0
+        for sample in train_loader:
+            image = sample["image"].float().cuda()
+            target = sample["mask"].float()
+            enc_outputs = segmenter.module.encoder(image)
+            size = enc_outputs[0].size()[2:]
+            for i, enc_output in enumerate(enc_outputs):
+                Xy_train[i].append(enc_output.permute(0, 2, 3, 1))
+            Xy_train["y"].append(nn.functional.interpolate(target[:, None], size=size, mode="nearest").long()
+                                 .squeeze(dim=1).cuda())
+            if do_kd:
+                kd_y = kd_net(image)
+                Xy_train["kd_y"].append(Fn.resize(Fn.lib.to_nhwc(kd_y.float()), size).permute(0, 2, 3, 1))
+            n_curr += image.size(0)
+            if n_curr >= n_train:
+                Xy_train["out_size"] = size
+                logger.info(" Populated Xy_train, N = {}".format(n_curr))
+                break
+        for k, v in list(Xy_train.items()):
+            if k == "out_size":
+                continue
+            cat = torch.cat(v, 0)
+            Xy_train[k] = cat if k == "y" else cat.permute(0, 3, 1, 2)  # logical NCHW over NHWC storage
+    return Xy_train
+
+
+def _gather(t, idx):
+    """Rows `idx` of a cached tensor, NHWC storage (GPU-side gather; trainer.py:131-136)."""
+    if t.dim() == 4:
+        return torch.index_select(t.permute(0, 2, 3, 1), 0, idx).permute(0, 3, 1, 2)
+    return torch.index_select(t, 0, idx)
+
+
+@try_except
+def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch_size, freeze_bn, do_kd, kd_coeff,
+                dec_grad_clip, do_polyak, avg_param=None, polyak_decay=0.9, aux_weight=0):
+    """Decoder-only training on cached encoder features."""
+    decoder = segmenter.module.decoder
+    n_examples = Xy_train[0].size(0)
+    batch_size = min(batch_size, n_examples)
+    n_passes = n_examples // batch_size
+    indices = np.arange(n_examples)
+    decoder.train()
+    if freeze_bn:
+        for m in decoder.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+    np.random.shuffle(indices)
+    dev = Xy_train[0].device
+    feat_keys = [k for k in Xy_train.keys() if k not in ("y", "kd_y", "out_size")]
+    out_size = tuple(Xy_train["out_size"])
+    loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+    start = time.time()
+    for i in range(n_passes):
+        idx = torch.from_numpy(indices[i * batch_size:(i + 1) * batch_size]).to(dev)
+        encoder_outputs = [_gather(Xy_train[k], idx) for k in feat_keys]
+        y = _gather(Xy_train["y"], idx)
+        output = decoder(encoder_outputs)
+        aux_outs = []
+        if isinstance(output, tuple):
+            output, aux_outs = output
+        output = Fn.resize(output, out_size)  # NOTE (reference): output size can change with the connectivity
+        loss = _segm_loss(segm_crit, output, y)
+        if do_kd:
+            loss = loss + kd_coeff * Fn.mse_loss(output, _gather(Xy_train["kd_y"], idx))
+        if aux_weight > 0:
+            for aux_out in aux_outs:
+                loss = loss + _segm_loss(segm_crit, aux_out, y, out_size) * aux_weight
+        optim_dec.zero_grad()
+        loss.backward()
+        nn.utils.clip_grad_norm_(decoder.parameters(), dec_grad_clip)
+        optim_dec.step()
+        loss_sum += loss.detach()
+        if do_polyak:
+            for p, avg_p in zip(decoder.parameters(), avg_param):
+                avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+    avg_loss = float(loss_sum.item()) / max(n_passes, 1)
+    logger.info(" Train epoch: {}\tAvg. Loss: {:.3f}\tAvg. Time: {:.3f}".format(
+        epoch, avg_loss, (time.time() - start) / max(n_passes, 1)))
+
+
+@try_except
+def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_crit, freeze_bn, enc_grad_clip,
+                    dec_grad_clip, do_polyak, print_every=10, aux_weight=-1, avg_param=None, polyak_decay=0.99):
+    """End-to-end training (encoder + decoder)."""
+    _set_stage(train_loader, "train")
+    segmenter.train()
+    if freeze_bn:
+        for m in segmenter.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+    loss_sum, n_it, start = None, 0, time.time()
+    for i, sample in enumerate(train_loader):
+        image = sample["image"].float().cuda(non_blocking=True)
+        target = sample["mask"].cuda(non_blocking=True)
+        output = segmenter(image)
+        aux_outs = []
+        if isinstance(output, tuple):
+            output, aux_outs = output
+        target_var = nn.functional.interpolate(target[:, None].float(), size=output.size()[2:], mode="nearest").long()[:, 0]
+        loss = _segm_loss(segm_crit, output, target_var)
+        if aux_weight > 0:
+            for aux_out in aux_outs:
+                loss = loss + _segm_loss(segm_crit, aux_out, target_var, tuple(target_var.size()[1:])) * aux_weight
+        optim_enc.zero_grad()
+        optim_dec.zero_grad()
+        loss.backward()
+        if enc_grad_clip > 0:
+            nn.utils.clip_grad_norm_(segmenter.module.encoder.parameters(), enc_grad_clip)
+        if dec_grad_clip > 0:
+            nn.utils.clip_grad_norm_(segmenter.module.decoder.parameters(), dec_grad_clip)
+        optim_enc.step()
+        optim_dec.step()
+        if do_polyak:
+            for p, avg_p in zip(segmenter.parameters(), avg_param):
+                avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+        loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
+        n_it += 1
+        if i % print_every == 0:
+            logger.info(" Train epoch: {} [{}/{}]\tAvg. Loss: {:.3f}\tAvg. Time: {:.3f}".format(
+                epoch, i, len(train_loader), float(loss_sum.item()) / n_it, (time.time() - start) / n_it))

@@ -1,0 +1,538 @@
+"""Autograd glue between torch tensors and the C-ABI kernels (include/nasb200.h).
+
+Every function here is a thin ``torch.autograd.Function``: ``forward`` / ``backward`` only allocate outputs and call
+the library; there is no torch arithmetic on activations.  Tensors are logical NCHW views over dense NHWC storage
+(``lib.new_act``); parameters stay fp32 in the reference's layouts.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+from .lib import ACT_NONE, ACT_RELU, ACT_RELU6, POOL_AVG, POOL_MAX, call, desc, ptr, ref  # noqa: F401
+
+
+def act_dtype():
+    from . import config
+    return config().act_dtype
+
+
+def conv_out_hw(h, w, ks, stride, dil, pad):
+    return ((h + 2 * pad - dil * (ks - 1) - 1) // stride + 1, (w + 2 * pad - dil * (ks - 1) - 1) // stride + 1)
+
+
+def _ws(dev, c=0):
+    return lib.workspace(dev, max(1 << 20, 24 * c + 256))
+
+
+def _grad_in(dy, like_dtype):
+    """Incoming gradient -> NHWC storage of the expected dtype (a no-op when it comes from our own kernels)."""
+    return lib.to_nhwc(dy, like_dtype)
+
+
+class _ConvUnit(torch.autograd.Function):
+    """conv (dense 1x1/3x3 or depthwise kxk) [+ BatchNorm2d train/eval] [+ bias] [+ ReLU/ReLU6] [+ residual].
+
+    One fused unit of the reference graph: nn.Conv2d -> nn.BatchNorm2d -> nn.ReLU(6) chains
+    (layer_factory.py:56-75,94-114,125-158,225-265; micro_decoders.py adapt/pre_clf/conv_clf)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, gamma, beta, bias, res, bn, cfg):
+        lib.require_cuda(x0)
+        dev = x0.device
+        ks, stride, dil, pad = cfg["ks"], cfg["stride"], cfg["dil"], cfg["pad"]
+        act, dw, in_relu, image = cfg["act"], cfg.get("dw", False), cfg.get("in_relu", 0), cfg.get("image", False)
+        n, _, h, w = x0.shape
+        cout = weight.shape[0]
+        oh, ow = conv_out_hw(h, w, ks, stride, dil, pad)
+        out_dtype = cfg.get("out_dtype") or (act_dtype() if image else x0.dtype)
+        training = bn is not None and bn.training
+        dx0 = lib.desc_nchw_f32(x0) if image else desc(x0)
+        dx1 = desc(x1) if x1 is not None else None
+        if bn is not None and bn.running_mean is None:
+            raise RuntimeError("BatchNorm2d without running statistics is not supported")
+
+        def run_conv(out, scale, shift, a, r):
+            if dw:
+                call("nasb_dwconv_fwd", ref(dx0), ptr(weight), ks, stride, dil, pad, in_relu, ptr(scale), ptr(shift), a,
+                     ref(desc(out)))
+                assert r is None
+            else:
+                call("nasb_conv_fwd", ref(dx0), ref(dx1), ptr(weight), ks, stride, dil, pad, None, None, in_relu,
+                     ptr(scale), ptr(shift), a, ref(desc(r)) if r is not None else None, ref(desc(out)))
+
+        z = ss = sv = None
+        y = lib.new_act(n, cout, oh, ow, out_dtype, dev)
+        # The residual add is fused into the conv epilogue only when no gradient is needed: the backward pass
+        # rebuilds xhat / the activation mask from the unit's own output, which must then exclude the residual.
+        late_res = res is not None and any(ctx.needs_input_grad)
+        fused_res = None if late_res else res
+        if bn is None:
+            run_conv(y, None, bias, act, fused_res)
+        elif not training:
+            ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
+            call("nasb_bn_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), cout,
+                 ptr(ss[0]), ptr(ss[1]))
+            run_conv(y, ss[0], ss[1], act, fused_res)
+        else:
+            if n * oh * ow == 1:  # same guard (and exception type) as torch.nn.functional.batch_norm
+                raise ValueError("Expected more than 1 value per channel when training, got input size {}".format(
+                    [n, cout, oh, ow]))
+            z = lib.new_act(n, cout, oh, ow, out_dtype, dev)
+            run_conv(z, None, None, ACT_NONE, None)
+            ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
+            sv = torch.empty((2, cout), dtype=torch.float32, device=dev)
+            mom = 0.1 if bn.momentum is None else float(bn.momentum)
+            call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
+                 ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, cout)))
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
+            if res is not None and not late_res:
+                call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, ref(desc(y)))
+        ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
+        ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
+        ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
+        if late_res:
+            out = lib.new_act(n, cout, oh, ow, out_dtype, dev)
+            call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, ref(desc(out)))
+            return out
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x0, x1, weight, gamma, beta, y, z, ss, sv = ctx.saved_tensors
+        cfg = ctx.cfg
+        ks, stride, dil, pad = cfg["ks"], cfg["stride"], cfg["dil"], cfg["pad"]
+        act, dw, in_relu, image = cfg["act"], cfg.get("dw", False), cfg.get("in_relu", 0), cfg.get("image", False)
+        has_x1, has_g, has_b, has_bias, has_res = ctx.has
+        dev = y.device
+        cout = weight.shape[0]
+        dy = _grad_in(dy, y.dtype)
+        need = ctx.needs_input_grad
+        dgamma = torch.zeros(cout, dtype=torch.float32, device=dev) if has_g else None
+        dbeta = torch.zeros(cout, dtype=torch.float32, device=dev) if has_b else None
+        if ctx.bn_mode or act != ACT_NONE:
+            dz = lib.new_act(*y.shape, y.dtype, dev)
+            call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)), ref(desc(z)) if z is not None else None, act, ptr(gamma),
+                 ptr(beta), ptr(ss[0]) if ss is not None else None, ptr(sv[0]) if sv is not None else None,
+                 ptr(sv[1]) if sv is not None else None, 1 if ctx.bn_mode == 2 else 0, ptr(dgamma), ptr(dbeta),
+                 ref(desc(dz)), ptr(_ws(dev, cout)))
+        else:
+            dz = dy
+        dbias = None
+        if has_bias:
+            dbias = torch.zeros(cout, dtype=torch.float32, device=dev)
+            call("nasb_channel_sum", ref(desc(dz)), ptr(dbias), None)
+        dweight = None
+        ddz = desc(dz)
+        if need[2]:
+            dweight = torch.zeros_like(weight, dtype=torch.float32)
+            if dw:
+                call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
+            else:
+                dsrc0 = lib.desc_nchw_f32(x0) if image else desc(x0)
+                call("nasb_conv_wgrad", ref(dsrc0), ref(desc(x1)) if has_x1 else None, None, None, in_relu, ref(ddz), ks,
+                     stride, dil, pad, ptr(dweight))
+        dx0 = dx1 = None
+        if need[0] or (has_x1 and need[1]):
+            dx0 = lib.new_act(*x0.shape, x0.dtype, dev)
+            if has_x1:
+                dx1 = lib.new_act(*x1.shape, x1.dtype, dev)
+            if dw:
+                call("nasb_dwconv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)))
+            else:
+                call("nasb_conv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)),
+                     ref(desc(dx1)) if has_x1 else None)
+            if in_relu:
+                call("nasb_relu_bwd", ref(desc(dx0)), ref(desc(x0)), ref(desc(dx0)))
+                if has_x1:
+                    call("nasb_relu_bwd", ref(desc(dx1)), ref(desc(x1)), ref(desc(dx1)))
+        dres = dy if has_res else None
+        return dx0, dx1, dweight, dgamma, dbeta, dbias, dres, None, None
+
+
+def conv_unit(x0, weight, bn=None, *, ks, stride=1, dil=1, pad=0, act=ACT_NONE, x1=None, bias=None, res=None, dw=False,
+              in_relu=0, image=False, out_dtype=None):
+    """Fused conv unit.  ``bn`` is the nn.BatchNorm2d module holding gamma/beta/running stats (or None)."""
+    cfg = dict(ks=ks, stride=stride, dil=dil, pad=pad, act=act, dw=dw, in_relu=in_relu, image=image, out_dtype=out_dtype)
+    gamma = bn.weight if bn is not None else None
+    beta = bn.bias if bn is not None else None
+    return _ConvUnit.apply(x0, x1, weight, gamma, beta, bias, res, bn, cfg)
+
+
+class _BnAct(torch.autograd.Function):
+    """Stand-alone BatchNorm2d (+ReLU): the head of ConcatReduce (layer_factory.py:372-376)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, act):
+        lib.require_cuda(x)
+        dev, c = x.device, x.shape[1]
+        training = bn.training
+        ss = torch.empty((2, c), dtype=torch.float32, device=dev)
+        sv = None
+        if training:
+            if x.shape[0] * x.shape[2] * x.shape[3] == 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size {}".format(
+                    list(x.shape)))
+            sv = torch.empty((2, c), dtype=torch.float32, device=dev)
+            mom = 0.1 if bn.momentum is None else float(bn.momentum)
+            call("nasb_bn_stats", ref(desc(x)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
+                 ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, c)))
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+        else:
+            call("nasb_bn_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), c,
+                 ptr(ss[0]), ptr(ss[1]))
+        y = lib.new_act(*x.shape, x.dtype, dev)
+        call("nasb_affine_act", ref(desc(x)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
+        ctx.act, ctx.training = act, training
+        ctx.has = (gamma is not None, beta is not None)
+        ctx.save_for_backward(x, gamma, beta, y, ss, sv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, y, ss, sv = ctx.saved_tensors
+        dev, c = y.device, y.shape[1]
+        dy = _grad_in(dy, y.dtype)
+        dgamma = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[0] else None
+        dbeta = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[1] else None
+        dx = lib.new_act(*y.shape, y.dtype, dev)
+        call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)), ref(desc(x)) if ctx.training else None, ctx.act, ptr(gamma),
+             ptr(beta), ptr(ss[0]), ptr(sv[0]) if sv is not None else None, ptr(sv[1]) if sv is not None else None,
+             1 if ctx.training else 0, ptr(dgamma), ptr(dbeta), ref(desc(dx)), ptr(_ws(dev, c)))
+        return dx, dgamma, dbeta, None, None
+
+
+def bn_act(x, bn, act=ACT_RELU):
+    return _BnAct.apply(x, bn.weight, bn.bias, bn, act)
+
+
+class _Pool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mode, stride):
+        lib.require_cuda(x)
+        n, c, h, w = x.shape
+        oh, ow = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        y = lib.new_act(n, c, oh, ow, x.dtype, x.device)
+        arg = None
+        if mode == POOL_MAX and ctx.needs_input_grad[0]:
+            arg = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+        call("nasb_pool3x3_fwd", ref(desc(x)), mode, stride, ref(desc(y)), ptr(arg))
+        ctx.mode, ctx.stride, ctx.xshape = mode, stride, tuple(x.shape)
+        ctx.save_for_backward(arg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        dy = _grad_in(dy, dy.dtype)
+        dx = lib.new_act(*ctx.xshape, dy.dtype, dy.device)
+        call("nasb_pool3x3_bwd", ref(desc(dy)), ctx.mode, ctx.stride, ptr(arg), ref(desc(dx)))
+        return dx, None, None
+
+
+def pool3x3(x, mode, stride):
+    return _Pool.apply(x, mode, stride)
+
+
+class _ResizeAxpby(torch.autograd.Function):
+    """out = sa*resize(x) + sb*y (bilinear, align_corners=False; identity when sizes agree)."""
+
+    @staticmethod
+    def forward(ctx, x, y, sa, sb, size):
+        lib.require_cuda(x)
+        n, c = x.shape[:2]
+        oh, ow = size
+        out = lib.new_act(n, c, oh, ow, x.dtype, x.device)
+        call("nasb_resize_axpby", ref(desc(x)), ptr(sa), ref(desc(y)) if y is not None else None, ptr(sb), ref(desc(out)))
+        ctx.save_for_backward(x, y, sa, sb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y, sa, sb = ctx.saved_tensors
+        dev = x.device
+        dz = _grad_in(dz, x.dtype)
+        need = ctx.needs_input_grad
+        dx = dyy = dsa = dsb = None
+        if need[0]:
+            dx = lib.new_act(*x.shape, x.dtype, dev)
+            call("nasb_resize_bwd", ref(desc(dz)), ptr(sa), ref(desc(dx)))
+        if y is not None and need[1]:
+            if sb is None:
+                dyy = dz
+            else:
+                dyy = lib.new_act(*y.shape, y.dtype, dev)
+                call("nasb_scale_copy", ref(desc(dz)), ptr(sb), 0, ref(desc(dyy)))
+        if (sa is not None and need[2]) or (sb is not None and need[3]):
+            c = x.shape[1]
+            dsa = torch.zeros(c, dtype=torch.float32, device=dev) if sa is not None else None
+            dsb = torch.zeros(c, dtype=torch.float32, device=dev) if sb is not None else None
+            call("nasb_axpby_bwd_params", ref(desc(dz)), ref(desc(x)), ref(desc(y)) if y is not None else None, ptr(dsa),
+                 ptr(dsb), None)
+        return dx, dyy, dsa, dsb, None
+
+
+def resize(x, size):
+    size = (int(size[0]), int(size[1]))
+    if tuple(x.shape[2:]) == size:
+        return x
+    return _ResizeAxpby.apply(x, None, None, None, size)
+
+
+def resize_add(x, y, sa=None, sb=None):
+    """sa*resize(x -> y's size) + sb*y."""
+    return _ResizeAxpby.apply(x, y, sa, sb, (y.shape[2], y.shape[3]))
+
+
+class _ConcatResize(torch.autograd.Function):
+    """torch.cat([resize(t, size) for t in tensors], 1): every producer-side resize writes straight into its channel
+    slice of the concat buffer (collect_all, micro_decoders.py:11-25; ConcatReduce's cat, layer_factory.py:380)."""
+
+    @staticmethod
+    def forward(ctx, size, *tensors):
+        lib.require_cuda(tensors[0])
+        n = tensors[0].shape[0]
+        ctot = sum(t.shape[1] for t in tensors)
+        out = lib.new_act(n, ctot, size[0], size[1], tensors[0].dtype, tensors[0].device)
+        c0 = 0
+        for t in tensors:
+            c = t.shape[1]
+            call("nasb_resize_axpby", ref(desc(t)), None, None, None, ref(desc(out[:, c0:c0 + c])))
+            c0 += c
+        ctx.shapes = [tuple(t.shape) for t in tensors]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _grad_in(dout, dout.dtype)
+        grads, c0 = [], 0
+        for i, shp in enumerate(ctx.shapes):
+            c = shp[1]
+            if ctx.needs_input_grad[i + 1]:
+                dx = lib.new_act(*shp, dout.dtype, dout.device)
+                call("nasb_resize_bwd", ref(desc(dout[:, c0:c0 + c])), None, ref(desc(dx)))
+                grads.append(dx)
+            else:
+                grads.append(None)
+            c0 += c
+        return (None, *grads)
+
+
+def concat_resize(tensors, size):
+    return _ConcatResize.apply((int(size[0]), int(size[1])), *tensors)
+
+
+class _ChannelTile(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, reps, stride, scale):
+        lib.require_cuda(x)
+        n, c, h, w = x.shape
+        oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
+        out = lib.new_act(n, c * reps, oh, ow, x.dtype, x.device)
+        call("nasb_channel_tile", ref(desc(x)), stride, float(scale), ref(desc(out)))
+        ctx.args = (reps, stride, scale, tuple(x.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        reps, stride, scale, xshape = ctx.args
+        dz = _grad_in(dz, dz.dtype)
+        dx = lib.new_act(*xshape, dz.dtype, dz.device)
+        call("nasb_channel_tile_bwd", ref(desc(dz)), stride, float(scale), ref(desc(dx)))
+        return dx, None, None, None
+
+
+def channel_tile(x, reps, stride=1, scale=1.0):
+    return _ChannelTile.apply(x, reps, stride, scale)
+
+
+class _SpatialMean(torch.autograd.Function):
+    """x.mean(2).mean(3) -> fp32 [N,C,1,1] (GAPConv1x1, layer_factory.py:189)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib.require_cuda(x)
+        n, c, h, w = x.shape
+        out = lib.new_act(n, c, 1, 1, torch.float32, x.device)
+        call("nasb_spatial_mean", ref(desc(x)), ptr(out))
+        ctx.xshape, ctx.xdtype = tuple(x.shape), x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dv):
+        dv = lib.to_nhwc(dv, torch.float32)
+        n, c, h, w = ctx.xshape
+        dx = lib.new_act(n, c, h, w, ctx.xdtype, dv.device)
+        call("nasb_spatial_bcast", ref(desc(dv)), 1.0 / float(h * w), ref(desc(dx)))
+        return dx
+
+
+class _SpatialBcast(torch.autograd.Function):
+    """Bilinear interpolation of a 1x1 map to HxW == broadcast (layer_factory.py:191-194)."""
+
+    @staticmethod
+    def forward(ctx, v, h, w, dtype):
+        lib.require_cuda(v)
+        n, c = v.shape[:2]
+        out = lib.new_act(n, c, h, w, dtype, v.device)
+        call("nasb_spatial_bcast", ref(desc(v)), 1.0, ref(desc(out)))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _grad_in(dout, dout.dtype)
+        n, c = dout.shape[:2]
+        dv = lib.new_act(n, c, 1, 1, torch.float32, dout.device)
+        call("nasb_spatial_sum", ref(desc(dout)), ptr(dv))
+        return dv, None, None, None
+
+
+def spatial_mean(x):
+    return _SpatialMean.apply(x)
+
+
+def spatial_bcast(v, h, w, dtype):
+    return _SpatialBcast.apply(v, h, w, dtype)
+
+
+class _Cast(torch.autograd.Function):
+    """dtype conversion at the fp32 <-> bf16 boundary of the network (nasb_scale_copy)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        out = lib.new_act(*x.shape, dtype, x.device)
+        call("nasb_scale_copy", ref(desc(x)), None, 0, ref(desc(out)))
+        ctx.src = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _grad_in(dy, dy.dtype)
+        dx = lib.new_act(*dy.shape, ctx.src, dy.device)
+        call("nasb_scale_copy", ref(desc(dy)), None, 0, ref(desc(dx)))
+        return dx, None
+
+
+def as_act(x, dtype=None):
+    """User tensor -> NHWC storage in the activation dtype."""
+    dtype = dtype or act_dtype()
+    lib.require_cuda(x)
+    if x.dtype == dtype:
+        return lib.to_nhwc(x)
+    x = lib.to_nhwc(x, None if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+    return _Cast.apply(x, dtype)
+
+
+# ------------------------------------------------------------------------------------------------------- losses
+class _CrossEntropy2d(torch.autograd.Function):
+    """nn.NLLLoss2d(ignore_index)(nn.LogSoftmax()(logits), target), trainer.py:144-146 / main_search.py:435."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        lib.require_cuda(logits)
+        if target.dtype != torch.int64:
+            target = target.long()
+        target = target.contiguous()
+        assert tuple(target.shape) == (logits.shape[0], logits.shape[2], logits.shape[3])
+        out2 = torch.empty(2, dtype=torch.float32, device=logits.device)
+        call("nasb_ce_fwd", ref(desc(logits)), ptr(target), int(ignore_index), ptr(out2), ptr(_ws(logits.device)))
+        ctx.ignore = int(ignore_index)
+        ctx.save_for_backward(logits, target, out2)
+        return out2[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, out2 = ctx.saved_tensors
+        g = g.to(torch.float32).contiguous()
+        dl = lib.new_act(*logits.shape, logits.dtype, logits.device)
+        call("nasb_ce_bwd", ref(desc(logits)), ptr(target), ctx.ignore, ptr(out2), ptr(g), ref(desc(dl)))
+        return dl, None, None
+
+
+def cross_entropy2d(logits, target, ignore_index=255):
+    return _CrossEntropy2d.apply(lib.to_nhwc(logits), target, ignore_index)
+
+
+class _MSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        lib.require_cuda(x)
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        call("nasb_mse_fwd", ref(desc(x)), ref(desc(y)), ptr(out), ptr(_ws(x.device)))
+        ctx.save_for_backward(x, y)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        g = g.to(torch.float32).contiguous()
+        dx = lib.new_act(*x.shape, x.dtype, x.device)
+        call("nasb_mse_bwd", ref(desc(x)), ref(desc(y)), ptr(g), ref(desc(dx)))
+        return dx, None
+
+
+def mse_loss(x, y):
+    """nn.MSELoss()(x, y) (knowledge-distillation term, trainer.py:147-149)."""
+    return _MSE.apply(lib.to_nhwc(x), lib.to_nhwc(y))
+
+
+class _BerHu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, valid_min):
+        lib.require_cuda(x)
+        out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+        call("nasb_berhu_fwd", ref(desc(x)), ref(desc(y)), float(valid_min), ptr(out3), ptr(_ws(x.device)))
+        ctx.vmin = float(valid_min)
+        ctx.save_for_backward(x, y, out3)
+        return out3[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, out3 = ctx.saved_tensors
+        g = g.to(torch.float32).contiguous()
+        dx = lib.new_act(*x.shape, x.dtype, x.device)
+        call("nasb_berhu_bwd", ref(desc(x)), ref(desc(y)), ctx.vmin, ptr(out3), ptr(g), ref(desc(dx)))
+        return dx, None, None
+
+
+def berhu_loss(pred, target, valid_min=0.0):
+    """Reverse Huber depth loss (defined by this repo; the reference ships depth inference only)."""
+    return _BerHu.apply(lib.to_nhwc(pred), lib.to_nhwc(target), valid_min)
+
+
+# ------------------------------------------------------------------------------------------------------- metric
+def confmat_labels(pred_u8, gt_u8, n_classes, cm=None):
+    lib.require_cuda(pred_u8)
+    assert pred_u8.dtype == torch.uint8 and gt_u8.dtype == torch.uint8
+    pred_u8, gt_u8 = pred_u8.contiguous().view(-1), gt_u8.contiguous().view(-1)
+    assert pred_u8.numel() == gt_u8.numel()
+    if cm is None:
+        cm = torch.zeros((n_classes, n_classes), dtype=torch.int64, device=pred_u8.device)
+    call("nasb_confmat_labels", ptr(pred_u8), ptr(gt_u8), C.c_longlong(pred_u8.numel()), int(n_classes), ptr(cm))
+    return cm
+
+
+def confmat_logits(logits, gt_u8, n_classes, cm=None):
+    """Fused upsample(bilinear, align_corners=False) + argmax + (gt < C) mask + histogram; accumulates into cm."""
+    lib.require_cuda(logits)
+    logits = lib.to_nhwc(logits.detach())
+    assert gt_u8.dtype == torch.uint8 and gt_u8.dim() == 3 and gt_u8.shape[0] == logits.shape[0]
+    gt_u8 = gt_u8.contiguous()
+    if cm is None:
+        cm = torch.zeros((n_classes, n_classes), dtype=torch.int64, device=logits.device)
+    call("nasb_confmat_logits", ref(desc(logits)), ptr(gt_u8), int(gt_u8.shape[1]), int(gt_u8.shape[2]), int(n_classes),
+         ptr(cm))
+    return cm
+
+
+def ius_accs(cm):
+    lib.require_cuda(cm)
+    c = cm.shape[0]
+    iu = torch.empty(c, dtype=torch.float64, device=cm.device)
+    acc = torch.empty(c, dtype=torch.float64, device=cm.device)
+    npx = torch.empty(c, dtype=torch.int64, device=cm.device)
+    call("nasb_ius_accs", ptr(cm.contiguous()), int(c), ptr(iu), ptr(npx), ptr(acc))
+    return iu, npx, acc

@@ -1,0 +1,202 @@
+"""ctypes binding of libnasb200.so (C ABI declared in include/nasb200.h).
+
+Fails loudly: a missing library is an ImportError at first use, any non-zero return code is a RuntimeError
+(the reference's engine wrappers turn RuntimeError into "reward 0", src/helpers/utils.py:172-187)."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnasb200.so")
+
+F32, BF16, F32_NCHW = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+POOL_MAX, POOL_AVG = 0, 1
+
+
+class NasbTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("cstride", C.c_int32), ("dtype", C.c_int32)]
+
+
+_TP = C.POINTER(NasbTensor)
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes (return type int unless listed in _RET)
+_SIG = {
+    "nasb_conv_fwd": [_TP, _TP, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _TP, _TP, _P],
+    "nasb_conv_dgrad": [_TP, _P, _I, _I, _I, _I, _TP, _TP, _P],
+    "nasb_conv_wgrad": [_TP, _TP, _P, _P, _I, _TP, _I, _I, _I, _I, _P, _P],
+    "nasb_dwconv_fwd": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
+    "nasb_dwconv_dgrad": [_TP, _P, _I, _I, _I, _I, _TP, _P],
+    "nasb_dwconv_wgrad": [_TP, _I, _TP, _I, _I, _I, _I, _P, _P],
+    "nasb_bn_fold": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
+    "nasb_bn_stats_workspace": [_I],
+    "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
+    "nasb_affine_act": [_TP, _P, _P, _I, _TP, _P],
+    "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
+    "nasb_pool3x3_fwd": [_TP, _I, _I, _TP, _P, _P],
+    "nasb_pool3x3_bwd": [_TP, _I, _I, _P, _TP, _P],
+    "nasb_resize_axpby": [_TP, _P, _TP, _P, _TP, _P],
+    "nasb_resize_bwd": [_TP, _P, _TP, _P],
+    "nasb_axpby_bwd_params": [_TP, _TP, _TP, _P, _P, _P, _P],
+    "nasb_scale_copy": [_TP, _P, _I, _TP, _P],
+    "nasb_channel_tile": [_TP, _I, _F, _TP, _P],
+    "nasb_channel_tile_bwd": [_TP, _I, _F, _TP, _P],
+    "nasb_spatial_mean": [_TP, _P, _P],
+    "nasb_spatial_bcast": [_TP, _F, _TP, _P],
+    "nasb_spatial_sum": [_TP, _P, _P],
+    "nasb_channel_sum": [_TP, _P, _P, _P],
+    "nasb_relu_bwd": [_TP, _TP, _TP, _P],
+    "nasb_loss_workspace": [],
+    "nasb_ce_fwd": [_TP, _P, _I, _P, _P, _P],
+    "nasb_ce_bwd": [_TP, _P, _I, _P, _P, _TP, _P],
+    "nasb_mse_fwd": [_TP, _TP, _P, _P, _P],
+    "nasb_mse_bwd": [_TP, _TP, _P, _TP, _P],
+    "nasb_berhu_fwd": [_TP, _TP, _F, _P, _P, _P],
+    "nasb_berhu_bwd": [_TP, _TP, _F, _P, _P, _TP, _P],
+    "nasb_confmat_labels": [_P, _P, _L, _I, _P, _P],
+    "nasb_confmat_logits": [_TP, _P, _I, _I, _I, _P, _P],
+    "nasb_ius_accs": [_P, _I, _P, _P, _P, _P],
+    "nasb_sumsq": [_P, _L, _P, _P],
+    "nasb_version": [],
+}
+_RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L}
+EXPORTS = tuple(sorted(_SIG))
+
+_lib = None
+launches = 0  # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def load():
+    """dlopen the library (once) and attach signatures.  No compute, no GPU needed."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libnasb200.so is not built: run `python nas-segm-pytorch_b200/build.py` "
+                              "(there is no CPU / eager fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in _SIG.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = _RET.get(name, C.c_int)
+        _lib = lib
+    return _lib
+
+
+def version():
+    return load().nasb_version().decode()
+
+
+def require_cuda(t):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("nas-segm-pytorch_b200 kernels run on a CUDA device only (no CPU fallback); got %s"
+                           % (t.device if isinstance(t, torch.Tensor) else type(t)))
+
+
+def call(name, *args):
+    """Invoke an entry point on torch's current stream; raise RuntimeError on failure."""
+    global launches
+    fn = getattr(load(), name)
+    rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    launches += 1
+    if rc != 0:
+        raise RuntimeError("%s failed with code %d%s" % (name, rc, _explain(rc)))
+
+
+def _explain(rc):
+    if rc == 10001:
+        return " (unsupported configuration)"
+    if rc == 10002:
+        return " (bad argument)"
+    try:
+        return " (cudaError %d)" % rc
+    except Exception:
+        return ""
+
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def new_act(n, c, h, w, dtype, device):
+    """Allocate an activation: logical NCHW view over dense NHWC memory."""
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def zeros_act(n, c, h, w, dtype, device):
+    return torch.zeros((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def is_nhwc(t):
+    """True if logical-NCHW tensor t is addressable as NHWC with a constant pixel stride (channel slices allowed)."""
+    if t.dim() != 4:
+        return False
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if c > 1 and sc != 1:
+        return False
+    cs = sw if w > 1 else (sh // max(w, 1) if h > 1 else (sn // max(h * w, 1) if n > 1 else c))
+    if cs < c:
+        return False
+    if w > 1 and sw != cs:
+        return False
+    if h > 1 and sh != w * cs:
+        return False
+    if n > 1 and sn != h * w * cs:
+        return False
+    return True
+
+
+def to_nhwc(t, dtype=None):
+    """Boundary conversion of a user tensor to dense NHWC storage (torch copy; not on the hot path)."""
+    require_cuda(t)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if is_nhwc(t) and t.dtype in _DT:
+        return t
+    return t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def desc(t):
+    """NasbTensor for a logical-NCHW torch tensor with NHWC storage."""
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if w > 1:
+        cs = sw
+    elif h > 1:
+        cs = sh
+    elif n > 1:
+        cs = sn
+    else:
+        cs = c
+    d = NasbTensor(t.data_ptr(), n, h, w, c, cs, _DT[t.dtype])
+    return d
+
+
+def desc_nchw_f32(t):
+    """Planar fp32 image (contiguous NCHW) for the encoder stem."""
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    n, c, h, w = t.shape
+    return NasbTensor(t.data_ptr(), n, h, w, c, c, F32_NCHW)
+
+
+def ref(d):
+    return C.byref(d) if d is not None else None
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+_ws = {}
+
+
+def workspace(device, nbytes=1 << 20):
+    """Per-device scratch for the reductions (BN statistics, loss sums); calls on one stream are serialised."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
