@@ -142,6 +142,34 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
         epoch, avg_loss, (time.time() - start) / max(n_passes, 1)))
 
 
+def segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip, do_polyak,
+                   aux_weight=-1, avg_param=None, polyak_decay=0.99):
+    """One end-to-end iteration on device-resident tensors (the body of trainer.py:226-272): forward, nearest-resized
+    target, CE (+ aux), backward, the two grad-norm clips, the two optimiser steps, Polyak.  Returns the loss tensor."""
+    output = segmenter(image)
+    aux_outs = []
+    if isinstance(output, tuple):
+        output, aux_outs = output
+    target_var = nn.functional.interpolate(target[:, None].float(), size=output.size()[2:], mode="nearest").long()[:, 0]
+    loss = _segm_loss(segm_crit, output, target_var)
+    if aux_weight > 0:
+        for aux_out in aux_outs:
+            loss = loss + _segm_loss(segm_crit, aux_out, target_var, tuple(target_var.size()[1:])) * aux_weight
+    optim_enc.zero_grad()
+    optim_dec.zero_grad()
+    loss.backward()
+    if enc_grad_clip > 0:
+        nn.utils.clip_grad_norm_(segmenter.module.encoder.parameters(), enc_grad_clip)
+    if dec_grad_clip > 0:
+        nn.utils.clip_grad_norm_(segmenter.module.decoder.parameters(), dec_grad_clip)
+    optim_enc.step()
+    optim_dec.step()
+    if do_polyak:
+        for p, avg_p in zip(segmenter.parameters(), avg_param):
+            avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+    return loss
+
+
 @try_except
 def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_crit, freeze_bn, enc_grad_clip,
                     dec_grad_clip, do_polyak, print_every=10, aux_weight=-1, avg_param=None, polyak_decay=0.99):
@@ -156,27 +184,8 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
     for i, sample in enumerate(train_loader):
         image = sample["image"].float().cuda(non_blocking=True)
         target = sample["mask"].cuda(non_blocking=True)
-        output = segmenter(image)
-        aux_outs = []
-        if isinstance(output, tuple):
-            output, aux_outs = output
-        target_var = nn.functional.interpolate(target[:, None].float(), size=output.size()[2:], mode="nearest").long()[:, 0]
-        loss = _segm_loss(segm_crit, output, target_var)
-        if aux_weight > 0:
-            for aux_out in aux_outs:
-                loss = loss + _segm_loss(segm_crit, aux_out, target_var, tuple(target_var.size()[1:])) * aux_weight
-        optim_enc.zero_grad()
-        optim_dec.zero_grad()
-        loss.backward()
-        if enc_grad_clip > 0:
-            nn.utils.clip_grad_norm_(segmenter.module.encoder.parameters(), enc_grad_clip)
-        if dec_grad_clip > 0:
-            nn.utils.clip_grad_norm_(segmenter.module.decoder.parameters(), dec_grad_clip)
-        optim_enc.step()
-        optim_dec.step()
-        if do_polyak:
-            for p, avg_p in zip(segmenter.parameters(), avg_param):
-                avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+        loss = segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
+                              do_polyak, aux_weight, avg_param, polyak_decay)
         loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
         n_it += 1
         if i % print_every == 0:

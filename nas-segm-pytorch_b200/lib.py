@@ -66,7 +66,11 @@ _RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_wo
 EXPORTS = tuple(sorted(_SIG))
 
 _lib = None
-launches = 0  # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+launches = 0  # kernels launched through the C ABI by this process (bench.py reports the delta over its timed region)
+# kernels (and async memsets) behind one call of each entry point; everything not listed launches exactly one
+_KERNELS_PER_CALL = {"nasb_bn_stats": 3, "nasb_bn_act_bwd": 4, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
+                     "nasb_spatial_mean": 2, "nasb_spatial_sum": 2}
+_prof = None  # list of (key, bytes, ev0, ev1) while profiling
 
 
 def load():
@@ -99,10 +103,49 @@ def call(name, *args):
     """Invoke an entry point on torch's current stream; raise RuntimeError on failure."""
     global launches
     fn = getattr(load(), name)
-    rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    launches += 1
+    if _prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        ev1.record()
+        key, nbytes = _describe(name, args)
+        _prof.append((key, nbytes, ev0, ev1))
+    else:
+        rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    launches += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError("%s failed with code %d%s" % (name, rc, _explain(rc)))
+
+
+def _describe(name, args):
+    """(key, algorithmic bytes) of one call: every NasbTensor argument counted once (reads + writes), the unit-level
+    definition of SURVEY 8(d): numel(inputs) + numel(outputs), parameters being negligible."""
+    shapes, nbytes = [], 0
+    for a in args:
+        t = getattr(a, "_obj", None)
+        if isinstance(t, NasbTensor):
+            esz = 2 if t.dtype == BF16 else 4
+            nbytes += t.n * t.h * t.w * t.c * esz
+            shapes.append("%dx%dx%dx%d%s" % (t.n, t.h, t.w, t.c, "b" if t.dtype == BF16 else "f"))
+    ints = [str(a) for a in args if isinstance(a, int) and not isinstance(a, bool)][:4]
+    return name + "[" + ",".join(shapes) + "|" + ",".join(ints) + "]", nbytes
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {key: (calls, total_ms, algorithmic_bytes_per_call)} with CUDA-event durations on the launching stream."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for key, nbytes, e0, e1 in rec:
+        c, ms, b = out.get(key, (0, 0.0, nbytes))
+        out[key] = (c + 1, ms + e0.elapsed_time(e1), b)
+    return out
 
 
 def _explain(rc):

@@ -54,8 +54,36 @@ def test_network_eval_logits(golden, tag):
         assert agree > 0.999
 
 
+def _oracle_train(tag, fx, dtype):
+    """fp64 / fp32 evaluation of the same training step in the CPU oracle."""
+    from oracle import nas_oracle as O
+    paper, cfg, ncls, agg, rep, aux = NETS[tag]
+    sd = det_state_dict(keys_shapes(fx), seed=7)
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    Pe, Pd = O.Params(sub_state(sd, "encoder."), dtype=dtype), O.Params(sub_state(sd, "decoder."), dtype=dtype)
+    rl = (1, 2) if paper == "wacv" else (1, 2, 4, 6)
+    feats = O.mbv2_encoder(t(fx["x"]).to(dtype), Pe, rl, True)
+    if paper == "wacv":
+        out, auxs = O.template_decoder(feats, Pd, cfg, O.encoder_out_sizes(rl), ncls, agg, rep, training=True), []
+    else:
+        out, auxs = O.micro_decoder(feats, Pd, cfg, O.encoder_out_sizes(rl), ncls, agg, aux, rep, training=True)
+    y = t(fx["train_y"])
+    loss = O.segm_loss(out, y)
+    for a in auxs:
+        loss = loss + 0.15 * O.segm_loss(a, y, y.shape[1:])
+    loss.backward()
+    return sd
+
+
 @pytest.mark.parametrize("tag", ["W0cv", "C0search", "C1search"])
 def test_network_train_step(golden, tag):
+    """One training step (BN in training mode): logits and loss against the real reference's fixture; gradients against
+    an fp64 evaluation of the oracle.  The 65x65 CVPR fixtures put 18 samples per channel through the deepest
+    BatchNorms, which makes the encoder gradients ill-conditioned: the reference's own fp32 gradients are 1-2 % away from
+    fp64 there (tools/diag_grads.py), so each parameter is held to max(5e-3, 3 x the fp32 CPU error)."""
     from nas_segm_b200 import functional as Fn
     nas_segm_b200.set_act_dtype(torch.float32)
     fx = golden("net_" + tag)
@@ -71,24 +99,33 @@ def test_network_train_step(golden, tag):
     for a in auxs:
         loss = loss + 0.15 * Fn.cross_entropy2d(Fn.resize(a, tuple(y.shape[1:])), y, 255)
     assert rel_err(_np(out), fx["train_out"]) < 1e-3
-    assert abs(float(loss) - float(fx["train_loss"])) < 1e-4 * max(1.0, abs(float(fx["train_loss"])))
+    assert abs(float(loss.detach()) - float(fx["train_loss"])) < 1e-4 * max(1.0, abs(float(fx["train_loss"])))
     loss.backward()
     named = {("encoder." + k): p for k, p in enc.named_parameters()}
     named.update({("decoder." + k): p for k, p in dec.named_parameters()})
-    bad = []
+    sd64, sd32 = _oracle_train(tag, fx, torch.float64), _oracle_train(tag, fx, torch.float32)
+    bad, checked = [], 0
+    for k, p in named.items():
+        g64 = sd64[k].grad
+        if g64 is None:
+            if p.grad is not None and float(p.grad.abs().max()) != 0.0:
+                bad.append((k, "expected no gradient"))
+            continue
+        scale = float(g64.abs().max())
+        if scale < 1e-4:  # analytically-zero gradients (e.g. a bias in front of a training-mode BatchNorm): noise only
+            if float(p.grad.abs().max()) > 1e-3:
+                bad.append((k, "expected ~0", float(p.grad.abs().max())))
+            continue
+        e_cuda = rel_err(_np(p.grad), g64.numpy())
+        e_cpu = rel_err(sd32[k].grad.numpy(), g64.numpy())
+        checked += 1
+        if e_cuda > max(5e-3, 3.0 * e_cpu):
+            bad.append((k, e_cuda, e_cpu))
+    assert checked > 100 and not bad, bad[:20]
+    # the real reference's fixture gradients (fp32) must sit in the same error band around fp64
     for k in [k for k in fx.files if k.startswith("grad/")]:
-        e = rel_err(_np(named[k[5:]].grad), fx[k])
-        if e > 5e-3:
-            bad.append((k, e))
-    for k in [k for k in fx.files if k.startswith("gnorm/")]:
-        ref = float(fx[k])
-        g = named[k[6:]].grad
-        if ref < 0:
-            if g is not None and float(g.abs().max()) != 0.0:
-                bad.append((k, "expected no grad"))
-        elif abs(float(g.norm()) - ref) > 5e-3 * ref + 2e-4:
-            bad.append((k, float(g.norm()), ref))
-    assert not bad, bad[:20]
+        g64 = sd64[k[5:]].grad.numpy()
+        assert rel_err(_np(named[k[5:]].grad), g64) <= max(5e-3, 3.0 * rel_err(fx[k], g64)), k
 
 
 @pytest.mark.parametrize("tag", ["W0", "C0search"])
