@@ -79,6 +79,22 @@ int nasb_conv_wgrad(const NasbTensor *x0, const NasbTensor *x1, const float *in_
                     void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Tensor-core path of the pointwise (1x1, stride 1) convolution: bf16 activations, TMA-staged 128-byte-swizzled
+ * operands, tcgen05.mma (kind::f16, M=128) with the fp32 accumulator in TMEM, fused epilogue, TMA store.
+ * nasb_pack_weight_bf16 : fp32 [rows][cols] -> bf16 [R][Kp] (K padded to 8): transpose=0 for the forward
+ *                         (R=C_out, K=C_in), transpose=1 for the data gradient (R=C_in, K=C_out).
+ * nasb_pw_tc_supported  : 1 if a (K=C_in, N=C_out) pair fits the kernel (8-aligned, N <= 256, smem budget).
+ * nasb_pw_tc_fwd        : out = act(scale*x.W^T + shift) (+res); x/out/res bf16.  stats (optional) -> fp64
+ *                         [2][N] sum / sum-of-squares of the stored output, ACCUMULATED (training-mode BN fused
+ *                         into the epilogue; finish with nasb_bn_finalize).  The data gradient is the same call
+ *                         with x = dz and the transposed pack.
+ * -------------------------------------------------------------------------------------------------------*/
+int nasb_pack_weight_bf16(const float *w, int rows, int cols, int transpose, void *out, void *stream);
+int nasb_pw_tc_supported(int K, int N);
+int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
+                   const NasbTensor *res, const NasbTensor *out, double *stats, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Depthwise k x k convolution (groups == channels), k in {3,5,7}, any stride/dilation/padding, with optional
  * folded BN + activation epilogue.  Replaces the depthwise nn.Conv2d of SepConv / DilConv
  * (layer_factory.py:198-265) and of InvertedResidual (:141-151).   weight: [C][1][k][k].
@@ -111,6 +127,9 @@ long long nasb_bn_stats_workspace(int C);
 int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
                   float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
                   float *shift, void *workspace, void *stream);
+int nasb_bn_finalize(const double *sums, long long P, int C, const float *gamma, const float *beta, float eps,
+                     float momentum, float *running_mean, float *running_var, float *save_mean, float *save_rstd,
+                     float *scale, float *shift, void *stream);
 int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift, int act, const NasbTensor *y,
                     void *stream);
 int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,

@@ -225,6 +225,17 @@ extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const floa
     return 0;
 }
 
+// finalize from externally accumulated fp64 sums (the tcgen05 pointwise kernel fuses the statistics into its epilogue)
+extern "C" int nasb_bn_finalize(const double *sums, long long P, int C, const float *gamma, const float *beta, float eps,
+                                float momentum, float *running_mean, float *running_var, float *save_mean, float *save_rstd,
+                                float *scale, float *shift, void *stream) {
+    if (!sums || !scale || !shift || P <= 0 || C <= 0) return NASB_ERR_BAD_ARG;
+    bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(sums, P, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                           save_mean, save_rstd, scale, shift);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift, int act, const NasbTensor *y,
                                void *stream) {
     if (!z || !y || z->dtype != y->dtype || (z->dtype != NASB_F32 && z->dtype != NASB_BF16) || z->c != y->c ||

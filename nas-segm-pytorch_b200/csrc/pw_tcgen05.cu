@@ -1,0 +1,395 @@
+// pw_tcgen05.cu -- pointwise (1x1) convolution as a bf16 GEMM on the 5th-generation tensor cores (sm_100a):
+//
+//     out[m, n] = act( scale[n] * sum_k A[m, k] * B[n, k] + shift[n] ) (+ res[m, n])          m = pixel, n = C_out
+//
+//  * A ([pixels, C_in] NHWC activations, K-major) and B (bf16-packed weights [C_out, C_in], K-major) are staged into
+//    128-byte-swizzled shared memory by TMA (cp.async.bulk.tensor, zero fill for the K / N / M tails);
+//  * tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = C_out rounded to 16, K = 16 per instruction) issued by one
+//    thread, fp32 accumulator in TMEM;
+//  * the four warps read the accumulator with tcgen05.ld (one TMEM lane = one pixel row per thread), apply the folded
+//    BN / bias / activation / residual epilogue, write the bf16 tile to swizzled shared memory and one thread stores it
+//    with TMA (tails clipped by the hardware);
+//  * optional fused training-mode BatchNorm statistics: per-channel sum / sum-of-squares of the stored tile are
+//    accumulated per CTA and flushed once with fp64 atomics (removes the separate statistics pass over z).
+//
+// The path is HBM-bound (C_in, C_out <= 256): the kernel is deliberately simple -- every CTA loops over its 128-pixel
+// tiles (load -> mma -> epilogue, serial per CTA) and latency is hidden by 2-5 co-resident CTAs per SM, each with its
+// own TMEM columns.  The same kernel computes the data gradient (A = dz, B = W^T packed by nasb_pack_weight_bf16).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace nasb {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address [0,14)
+    d |= (uint64_t)1 << 16;                   // leading byte offset (ignored for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                   // descriptor version [46,48)
+    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // c_format = F32
+    d |= 1u << 7;                    // a_format = BF16
+    d |= 1u << 10;                   // b_format = BF16
+    d |= (uint32_t)(n >> 3) << 17;   // n_dim
+    d |= (uint32_t)(128 >> 4) << 24; // m_dim
+    return d;
+}
+
+struct PwParams {
+    int M, K, N;          // pixels, C_in, C_out
+    int nkb, nnb, npad;   // K blocks of 64, N blocks of 64, N rounded up to 16
+    int tmem_cols;
+    const float *scale, *shift;
+    int act;
+    const bf16 *res;
+    int res_cs;
+    double *stats;  // [2][N] (sum, sumsq) or null
+};
+
+constexpr int TC_THREADS = 128;
+constexpr int TILE_M = 128;
+
+__global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                           const __grid_constant__ CUtensorMap map_b,
+                                                           const __grid_constant__ CUtensorMap map_o, const PwParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (all tile regions are multiples of 1024 B)
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;                                   // nkb x [npad x 128 B]
+    uint8_t *sA = sB + (size_t)p.nkb * p.npad * 128;      // nkb x [128 x 128 B]
+    uint8_t *sO = sA + (size_t)p.nkb * TILE_M * 128;      // nnb x [128 x 128 B]
+    float *s_scale = (float *)(sO + (size_t)p.nnb * TILE_M * 128);
+    float *s_shift = s_scale + p.npad;
+    float *s_sum = s_shift + p.npad;
+    float *s_sq = s_sum + p.npad;
+    uint64_t *bar_b = (uint64_t *)(s_sq + p.npad);
+    uint64_t *bar_a = bar_b + 1;
+    uint64_t *bar_mma = bar_a + 1;
+    uint32_t *s_tmem = (uint32_t *)(bar_mma + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (p.M + TILE_M - 1) / TILE_M;
+
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_a, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < p.npad; i += TC_THREADS) {
+        s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
+        s_shift[i] = (p.shift && i < p.N) ? p.shift[i] : 0.f;
+        s_sum[i] = 0.f;
+        s_sq[i] = 0.f;
+    }
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (tid == 0) {  // weights: once per CTA
+        mbar_expect_tx(bar_b, (uint32_t)(p.nkb * p.npad * 128));
+        for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.npad * 128, &map_b, bar_b, kb * 64, 0);
+    }
+    const uint32_t idesc = make_idesc_bf16(p.npad);
+    const int row = warp * 32 + lane;  // TMEM lane == row of the tile owned by this thread
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t parity = it & 1;
+        const int m0 = tile * TILE_M;
+        if (tid == 0) {
+            mbar_expect_tx(bar_a, (uint32_t)(p.nkb * TILE_M * 128));
+            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sA + (size_t)kb * TILE_M * 128, &map_a, bar_a, kb * 64, m0);
+            if (it == 0) mbar_wait(bar_b, 0);
+            mbar_wait(bar_a, parity);
+            tc_fence_after();
+            const int ksteps = (p.K + 15) / 16;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int kb = ks >> 2, kin = ks & 3;  // 4 K-steps of 16 elements (32 B) per 128-byte swizzle row
+                uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)kb * TILE_M * 128) + kin * 32);
+                uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * p.npad * 128) + kin * 32);
+                umma_f16(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, parity);
+        tc_fence_after();
+
+        // ---- epilogue: TMEM -> registers -> (BN fold / bias, activation, residual) -> bf16 -> swizzled smem
+        const long long m = (long long)m0 + row;
+        const bool row_ok = m < p.M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+            if (p.res && row_ok) {
+                const bf16 *rp = p.res + m * p.res_cs + c0;
+                if (c0 + 16 <= p.N) {
+                    float r[8];
+                    load_vec<bf16, 8>(rp, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += r[j];
+                    load_vec<bf16, 8>(rp + 8, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[8 + j] += r[j];
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+                }
+            }
+            const int nb = c0 >> 6, ch = (c0 & 63) >> 3;  // 64-column block, first 16-byte chunk inside the 128-byte row
+            uint8_t *orow = sO + (size_t)nb * TILE_M * 128 + (size_t)row * 128;
+            uint4 q0, q1;
+            bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                e0[j] = __float2bfloat16_rn(v[j]);
+                e1[j] = __float2bfloat16_rn(v[8 + j]);
+            }
+            *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
+            *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();  // tile complete in smem; every thread is done with TMEM and with A
+        if (tid == 0) {
+            for (int nb = 0; nb < p.nnb; ++nb) tma_store_2d(&map_o, sO + (size_t)nb * TILE_M * 128, nb * 64, m0);
+            tma_store_commit();
+        }
+        if (p.stats) {
+            // column statistics of the tile as stored (bf16-rounded): thread -> column tid % npad, rows strided
+            const int rows_valid = min(TILE_M, p.M - m0);
+            const int cw = p.npad < TC_THREADS ? p.npad : TC_THREADS;  // columns covered per pass
+            const int groups = TC_THREADS / cw, g = tid / cw;
+            if (g < groups) {
+                for (int c = tid % cw; c < p.N; c += cw) {
+                    const int nb = c >> 6, ch = (c & 63) >> 3, e = c & 7;
+                    const uint8_t *blk = sO + (size_t)nb * TILE_M * 128;
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int r = g; r < rows_valid; r += groups) {
+                        float x = __bfloat162float(
+                            *reinterpret_cast<const bf16 *>(blk + (size_t)r * 128 + ((ch ^ (r & 7)) << 4) + e * 2));
+                        s1 += x;
+                        s2 = fmaf(x, x, s2);
+                    }
+                    atomicAdd(&s_sum[c], s1);
+                    atomicAdd(&s_sq[c], s2);
+                }
+            }
+        }
+        if (tid == 0) tma_store_wait_read();  // smem tile may be overwritten once the bulk store has read it
+        __syncthreads();
+    }
+    if (tid == 0) tma_store_wait_all();
+    if (p.stats) {
+        __syncthreads();
+        for (int c = tid; c < p.N; c += TC_THREADS) {
+            atomicAdd(&p.stats[c], (double)s_sum[c]);
+            atomicAdd(&p.stats[p.N + c], (double)s_sq[c]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// weight [rows][cols] fp32 (row-major) -> bf16 [R][Kp]:  transpose=0: out[r][k] = w[r][k] ; transpose=1: out[r][k] = w[k][r]
+__global__ void pack_weight_kernel(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * Kp) return;
+    int r = i / Kp, k = i - r * Kp;
+    float v = 0.f;
+    if (!transpose) {
+        if (r < rows && k < cols) v = w[(long long)r * cols + k];
+    } else {
+        if (k < rows && r < cols) v = w[(long long)k * cols + r];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 map over [rows][inner] with row pitch `pitch_elems`; box = 64 x box_rows, 128-byte swizzle
+static bool make_map(CUtensorMap *m, const void *ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace nasb
+
+using namespace nasb;
+
+extern "C" int nasb_pack_weight_bf16(const float *w, int rows, int cols, int transpose, void *out, void *stream) {
+    if (!w || !out || rows <= 0 || cols <= 0) return NASB_ERR_BAD_ARG;
+    int R = transpose ? cols : rows, K = transpose ? rows : cols;
+    int Kp = (K + 7) / 8 * 8;
+    pack_weight_kernel<<<cdiv((long long)R * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, transpose, (bf16 *)out, R, Kp);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// Shapes the tensor-core path accepts: bf16 in/out, 8-aligned channels and pitches, C_in / C_out small enough for the
+// whole weight matrix plus one A tile and one output tile to fit in shared memory.
+extern "C" int nasb_pw_tc_supported(int K, int N) {
+    if (K < 8 || N < 8 || (K % 8) || (N % 8) || N > 256) return 0;
+    int nkb = (K + 63) / 64, nnb = (N + 63) / 64, npad = (N + 15) / 16 * 16;
+    size_t smem = (size_t)nkb * npad * 128 + (size_t)nkb * 128 * 128 + (size_t)nnb * 128 * 128 + 4 * npad * 4 + 64 + 1024;
+    return smem <= 200 * 1024 ? 1 : 0;
+}
+
+extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
+                              const NasbTensor *res, const NasbTensor *out, double *stats, void *stream) {
+    if (!x || !out || !wpack) return NASB_ERR_BAD_ARG;
+    if (x->dtype != NASB_BF16 || out->dtype != NASB_BF16 || out->c != N || npix(*x) != npix(*out)) return NASB_ERR_BAD_ARG;
+    if (!vec_ok(*x, 8) || !vec_ok(*out, 8) || !nasb_pw_tc_supported(x->c, N)) return NASB_ERR_UNSUPPORTED;
+    if (res && (res->dtype != NASB_BF16 || res->c != N || npix(*res) != npix(*out) || !vec_ok(*res, 8))) return NASB_ERR_BAD_ARG;
+    long long M = npix(*x);
+    if (M == 0) return 0;
+    if (M > 0x7fffffffLL) return NASB_ERR_UNSUPPORTED;
+    PwParams p{};
+    p.M = (int)M;
+    p.K = x->c;
+    p.N = N;
+    p.nkb = (p.K + 63) / 64;
+    p.nnb = (N + 63) / 64;
+    p.npad = (N + 15) / 16 * 16;
+    int cols = 32;
+    while (cols < p.npad) cols <<= 1;
+    p.tmem_cols = cols;
+    p.scale = scale;
+    p.shift = shift;
+    p.act = act;
+    p.res = res ? (const bf16 *)res->ptr : nullptr;
+    p.res_cs = res ? res->cstride : 0;
+    p.stats = stats;
+    int Kp = (p.K + 7) / 8 * 8;
+    CUtensorMap ma, mb, mo;
+    if (!make_map(&ma, x->ptr, (uint64_t)p.K, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    if (!make_map(&mb, wpack, (uint64_t)Kp, (uint64_t)N, (uint64_t)Kp, (uint32_t)p.npad)) return NASB_ERR_UNSUPPORTED;
+    if (!make_map(&mo, out->ptr, (uint64_t)N, (uint64_t)M, (uint64_t)out->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    size_t smem = (size_t)p.nkb * p.npad * 128 + (size_t)p.nkb * TILE_M * 128 + (size_t)p.nnb * TILE_M * 128 + 4 * p.npad * 4 + 64 + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
+        if (e != cudaSuccess) return (int)e;
+        configured = 200 * 1024 + 2048;
+    }
+    int ntiles = (int)((M + TILE_M - 1) / TILE_M);
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
+    if (per_sm < 1) per_sm = 1;
+    int grid = NASB_SM_COUNT * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    pw_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, p);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
