@@ -30,6 +30,26 @@ def _grad_in(dy, like_dtype):
     return lib.to_nhwc(dy, like_dtype)
 
 
+def _tc_ok(x, cin, cout, out_dtype):
+    """Can this pointwise GEMM (K=cin -> N=cout) run on the tcgen05 kernel?  bf16 in/out, 8-aligned channels/pitches."""
+    from . import config
+    if not config().use_tcgen05 or x.dtype != torch.bfloat16 or out_dtype != torch.bfloat16:
+        return False
+    if x.data_ptr() % 16 or lib.desc(x).cstride % 8:
+        return False
+    return bool(lib.load().nasb_pw_tc_supported(int(cin), int(cout)))
+
+
+def _pack_weight(weight, transpose):
+    """fp32 [C_out, C_in, 1, 1] -> bf16 [R][Kp] operand of the tensor-core kernel (a few KB; repacked per call because the
+    optimiser rewrites the fp32 master weights every step)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    r, k = (cin, cout) if transpose else (cout, cin)
+    wp = torch.empty(r * ((k + 7) // 8 * 8), dtype=torch.bfloat16, device=weight.device)
+    call("nasb_pack_weight_bf16", ptr(weight), cout, cin, 1 if transpose else 0, ptr(wp))
+    return wp
+
+
 class _ConvUnit(torch.autograd.Function):
     """conv (dense 1x1/3x3 or depthwise kxk) [+ BatchNorm2d train/eval] [+ bias] [+ ReLU/ReLU6] [+ residual].
 
@@ -52,7 +72,15 @@ class _ConvUnit(torch.autograd.Function):
         if bn is not None and bn.running_mean is None:
             raise RuntimeError("BatchNorm2d without running statistics is not supported")
 
-        def run_conv(out, scale, shift, a, r):
+        use_tc = (not dw and ks == 1 and stride == 1 and pad == 0 and x1 is None and not in_relu and not image
+                  and _tc_ok(x0, x0.shape[1], cout, out_dtype))
+        wpack = _pack_weight(weight, False) if use_tc else None
+
+        def run_conv(out, scale, shift, a, r, stats=None):
+            if use_tc:
+                call("nasb_pw_tc_fwd", ref(dx0), ptr(wpack), cout, ptr(scale), ptr(shift), a,
+                     ref(desc(r)) if r is not None else None, ref(desc(out)), ptr(stats))
+                return
             if dw:
                 call("nasb_dwconv_fwd", ref(dx0), ptr(weight), ks, stride, dil, pad, in_relu, ptr(scale), ptr(shift), a,
                      ref(desc(out)))
@@ -79,12 +107,18 @@ class _ConvUnit(torch.autograd.Function):
                 raise ValueError("Expected more than 1 value per channel when training, got input size {}".format(
                     [n, cout, oh, ow]))
             z = lib.new_act(n, cout, oh, ow, out_dtype, dev)
-            run_conv(z, None, None, ACT_NONE, None)
             ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
             sv = torch.empty((2, cout), dtype=torch.float32, device=dev)
             mom = 0.1 if bn.momentum is None else float(bn.momentum)
-            call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
-                 ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, cout)))
+            if use_tc:  # batch statistics are accumulated by the GEMM epilogue
+                sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+                run_conv(z, None, None, ACT_NONE, None, sums)
+                call("nasb_bn_finalize", ptr(sums), C.c_longlong(n * oh * ow), cout, ptr(gamma), ptr(beta), float(bn.eps),
+                     mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]))
+            else:
+                run_conv(z, None, None, ACT_NONE, None)
+                call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
+                     ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, cout)))
             if bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
             call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
@@ -139,7 +173,11 @@ class _ConvUnit(torch.autograd.Function):
             dx0 = lib.new_act(*x0.shape, x0.dtype, dev)
             if has_x1:
                 dx1 = lib.new_act(*x1.shape, x1.dtype, dev)
-            if dw:
+            if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image
+                    and _tc_ok(dz, cout, x0.shape[1], x0.dtype)):
+                call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
+                     ref(desc(dx0)), None)
+            elif dw:
                 call("nasb_dwconv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)))
             else:
                 call("nasb_conv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)),

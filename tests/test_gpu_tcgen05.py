@@ -1,0 +1,106 @@
+"""tcgen05 pointwise-GEMM kernel vs an fp32 torch matmul of the same bf16 operands and vs the CUDA-core path, over
+channel counts of the real networks, M tails, channel-slice views, every epilogue variant and the fused BN statistics."""
+import pytest
+import torch
+
+import nas_segm_b200
+from nas_segm_b200 import functional as Fn
+from nas_segm_b200 import lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, scale, shift, act, res):
+    y = x.float().reshape(-1, x.shape[-1]) @ w.to(torch.bfloat16).float().t()
+    if scale is not None:
+        y = y * scale + shift
+    if act == lib.ACT_RELU:
+        y = y.clamp_min(0)
+    elif act == lib.ACT_RELU6:
+        y = y.clamp(0, 6)
+    if res is not None:
+        y = y + res.float().reshape(-1, res.shape[-1])
+    return y
+
+
+def _run_tc(x_nhwc, w, scale, shift, act, res_nhwc, stats=False, out_buf=None):
+    """x_nhwc: [n,h,w,K] bf16 (possibly a channel slice of a wider buffer)."""
+    n, h, ww, K = x_nhwc.shape
+    N = w.shape[0]
+    x = x_nhwc.permute(0, 3, 1, 2)
+    out = lib.new_act(n, N, h, ww, torch.bfloat16, x.device) if out_buf is None else out_buf
+    wp = Fn._pack_weight(w.reshape(N, K, 1, 1).contiguous(), False)
+    st = torch.zeros(2 * N, dtype=torch.float64, device=x.device) if stats else None
+    lib.call("nasb_pw_tc_fwd", lib.ref(lib.desc(x)), lib.ptr(wp), N, lib.ptr(scale), lib.ptr(shift), act,
+             lib.ref(lib.desc(res_nhwc.permute(0, 3, 1, 2))) if res_nhwc is not None else None, lib.ref(lib.desc(out)),
+             lib.ptr(st))
+    torch.cuda.synchronize()
+    return out.permute(0, 2, 3, 1), st
+
+
+def test_tc_gemm_shapes_and_tails():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bad = []
+    for K, N in [(16, 96), (96, 24), (24, 144), (144, 24), (144, 32), (32, 192), (192, 32), (24, 48), (32, 64), (64, 64),
+                 (128, 64), (224, 64), (8, 8), (48, 48), (64, 16), (16, 256), (256, 16), (200, 72)]:
+        assert lib.load().nasb_pw_tc_supported(K, N) == 1, (K, N)
+        for M in (1, 100, 128, 129, 4099):
+            x = torch.randn(1, 1, M, K, generator=g, device="cuda").to(torch.bfloat16)
+            w = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+            y, _ = _run_tc(x, w, None, None, lib.ACT_NONE, None)
+            ref = _ref(x, w, None, None, lib.ACT_NONE, None)
+            err = float((y.float().reshape(-1, N) - ref).abs().max() / ref.abs().max().clamp_min(1e-6))
+            if not err < 1e-2:
+                bad.append((K, N, M, err))
+    assert not bad, bad
+
+
+def test_tc_epilogues_slices_and_stats():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n, h, w_, K, N = 3, 37, 41, 64, 96
+    wide = torch.randn(n, h, w_, K + 32, generator=g, device="cuda").to(torch.bfloat16)
+    x = wide[..., 16:16 + K]                       # channel slice: pixel pitch 96, 32-byte offset
+    wt = torch.randn(N, K, generator=g, device="cuda") / 8
+    scale = torch.rand(N, generator=g, device="cuda") + 0.5
+    shift = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn(n, h, w_, N, generator=g, device="cuda").to(torch.bfloat16)
+    for act in (lib.ACT_NONE, lib.ACT_RELU, lib.ACT_RELU6):
+        for r in (None, res):
+            y, _ = _run_tc(x, wt, scale, shift, act, r)
+            ref = _ref(x, wt, scale, shift, act, r)
+            err = float((y.float().reshape(-1, N) - ref).abs().max() / ref.abs().max())
+            assert err < 1e-2, (act, r is not None, err)
+    # output into a channel slice of a wider concat buffer; untouched channels stay untouched
+    buf = torch.full((n, h, w_, N + 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    out_view = buf.permute(0, 3, 1, 2)[:, 32:32 + N]
+    y, _ = _run_tc(x, wt, None, None, lib.ACT_NONE, None, out_buf=out_view)
+    ref = _ref(x, wt, None, None, lib.ACT_NONE, None)
+    assert float((buf[..., 32:32 + N].float().reshape(-1, N) - ref).abs().max() / ref.abs().max()) < 1e-2
+    assert float((buf[..., :32] - 7).abs().max()) == 0 and float((buf[..., 32 + N:] - 7).abs().max()) == 0
+    # fused statistics == sums of the stored (bf16) output
+    y, st = _run_tc(x, wt, None, None, lib.ACT_NONE, None, stats=True)
+    yd = y.double().reshape(-1, N)
+    assert torch.allclose(st[:N], yd.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[N:], (yd * yd).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_conv_unit_tc_vs_cuda_core_path():
+    """The fused conv unit (train-mode BN, backward) on the tensor-core path vs the CUDA-core path, same bf16 inputs."""
+    from nas_segm_b200.nn.layer_factory import conv_bn_relu
+    torch.manual_seed(0)
+    m = conv_bn_relu(64, 96, 1, 1, 0).cuda().train()
+    x = torch.randn(4, 64, 45, 53, device="cuda").to(torch.bfloat16)
+    outs = {}
+    for tc in (True, False):
+        nas_segm_b200.config().use_tcgen05 = tc
+        try:
+            xi = x.clone().requires_grad_(True)
+            m.zero_grad()
+            y = m(xi)
+            (y.float() * torch.linspace(-1, 1, y.numel(), device="cuda").reshape(y.shape)).sum().backward()
+            outs[tc] = (y.detach().float(), xi.grad.float(), m[0].weight.grad.clone(), m[1].weight.grad.clone(),
+                        m[1].running_var.clone())
+        finally:
+            nas_segm_b200.config().use_tcgen05 = True
+    for a, b, tol in zip(outs[True], outs[False], (3e-2, 3e-2, 2e-2, 2e-2, 1e-3)):
+        assert float((a - b).abs().max() / b.abs().max()) < tol
