@@ -91,6 +91,9 @@ int nasb_conv_wgrad(const NasbTensor *x0, const NasbTensor *x1, const float *in_
  * -------------------------------------------------------------------------------------------------------*/
 int nasb_pack_weight_bf16(const float *w, int rows, int cols, int transpose, void *out, void *stream);
 int nasb_pw_tc_supported(int K, int N);
+int nasb_pw_tc_wgrad_supported(int Co, int Ci);
+/* dweight[co][ci] += sum_pixels dz[.,co]*x[.,ci] on the tensor cores (MN-major operands, TMEM accumulation). */
+int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float *dweight, void *stream);
 int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
                    const NasbTensor *res, const NasbTensor *out, double *stats, void *stream);
 
@@ -117,6 +120,8 @@ int nasb_dwconv_wgrad(const NasbTensor *x, int in_relu, const NasbTensor *dz, in
  *                       g = dy * act'(y); dbeta += sum g; dgamma += sum g*xhat
  *                       xhat = (z-save_mean)*save_rstd in training (z = saved conv output), and is rebuilt from
  *                       y as (y-beta)/gamma in eval mode (only unmasked pixels matter there).  dz may alias dy.
+ *                       In training the activation mask is recomputed from z (scale/shift of the forward), so y
+ *                       is not read at all (y may be NULL): 2 reads for the sums, 2 reads + 1 write for dz.
  *                       eval : dz = g * scale
  *                       train: dz = scale * (g - mean(g) - xhat*mean(g*xhat))
  *                     workspace: >= nasb_bn_stats_workspace(C) bytes.
@@ -133,8 +138,9 @@ int nasb_bn_finalize(const double *sums, long long P, int C, const float *gamma,
 int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift, int act, const NasbTensor *y,
                     void *stream);
 int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,
-                    const float *beta, const float *scale, const float *save_mean, const float *save_rstd,
-                    int training, float *dgamma, float *dbeta, const NasbTensor *dz, void *workspace, void *stream);
+                    const float *beta, const float *scale, const float *shift, const float *save_mean,
+                    const float *save_rstd, int training, float *dgamma, float *dbeta, const NasbTensor *dz,
+                    void *workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * 3x3 pooling, padding 1 (layer_factory.py:161-178).  Max pooling optionally records the arg-max tap

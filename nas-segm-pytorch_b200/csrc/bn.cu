@@ -15,6 +15,93 @@ __global__ void bn_fold_kernel(const float *gamma, const float *beta, const floa
     shift[c] = b - mean[c] * s;
 }
 
+__device__ __forceinline__ float xhat_from_y(float y, float gamma, float beta) {
+    return gamma != 0.f ? (y - beta) / gamma : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column (per-channel) reduction skeleton for NHWC tensors.  A CTA owns a slab of pixels; thread t owns the channel
+// vector cv = t % CV (V channels = one 16-byte load) and the pixel lane pl = t / CV, so a warp reads whole pixels
+// contiguously.  Per-thread partials are fp32 (a few hundred to a few thousand terms), the cross-lane reduction and the
+// cross-CTA merge (fp64 atomics into ws[0..C) and ws[C..2C)) are fp64.
+// F: void f(long long pixel, int c0, float (&a)[V], float (&b)[V])  accumulates into a / b.
+template <int V, typename F>
+__device__ __forceinline__ void colreduce2(long long r0, long long r1, int C, double *ws, F f) {
+    extern __shared__ float red_sm[];  // [2][PL][C]
+    const int CV = C / V;
+    const int PL = blockDim.x / CV;
+    const int t = threadIdx.x;
+    const int cv = t % CV, pl = t / CV;
+    float a[V], b[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = b[j] = 0.f;
+    if (pl < PL)
+        for (long long m = r0 + pl; m < r1; m += PL) f(m, cv * V, a, b);
+    if (pl < PL) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            red_sm[(size_t)pl * C + cv * V + j] = a[j];
+            red_sm[(size_t)(PL + pl) * C + cv * V + j] = b[j];
+        }
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < PL; ++i) {
+            s1 += (double)red_sm[(size_t)i * C + c];
+            s2 += (double)red_sm[(size_t)(PL + i) * C + c];
+        }
+        atomicAdd(&ws[c], s1);
+        atomicAdd(&ws[C + c], s2);
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_sums_vec_kernel(const T *z, int cs, long long P, int C, double *ws,
+                                                          long long rows_per_cta) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
+    colreduce2<V>(r0, r1, C, ws, [&](long long m, int c0, float (&a)[V], float (&b)[V]) {
+        float v[V];
+        load_vec<T, V>(z + m * cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            a[j] += v[j];
+            b[j] = fmaf(v[j], v[j], b[j]);
+        }
+    });
+}
+
+// training: g = dy*act'(act(z*scale+shift)), xhat = (z-mean)*rstd ; eval: g = dy*act'(y), xhat = (y-beta)/gamma
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_bwd_sums_vec_kernel(const T *dy, int dy_cs, const T *yz, int yz_cs, int training,
+                                                              const float *scale, const float *shift, const float *mean,
+                                                              const float *rstd, const float *gamma, const float *beta,
+                                                              int act, long long P, int C, double *ws,
+                                                              long long rows_per_cta) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
+    colreduce2<V>(r0, r1, C, ws, [&](long long m, int c0, float (&a)[V], float (&b)[V]) {
+        float g[V], v[V];
+        load_vec<T, V>(dy + m * dy_cs + c0, g);
+        load_vec<T, V>(yz + m * yz_cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int c = c0 + j;
+            float yy, xh;
+            if (training) {
+                yy = apply_act(v[j] * scale[c] + shift[c], act);
+                xh = (v[j] - mean[c]) * rstd[c];
+            } else {
+                yy = v[j];
+                xh = xhat_from_y(yy, gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f);
+            }
+            float gm = g[j] * act_mask(yy, act);
+            a[j] += gm;
+            b[j] = fmaf(gm, xh, b[j]);
+        }
+    });
+}
+
+// scalar fallbacks (channel counts / pitches that are not 16-byte addressable)
 // ws[0..C) += sum z ; ws[C..2C) += sum z^2        block (32 channel lanes x 8 pixel lanes), one pixel slab per CTA
 template <typename T>
 __global__ void __launch_bounds__(256) bn_sums_kernel(const T *z, int cs, long long P, int C, double *ws,
@@ -86,13 +173,10 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T *z, int z_cs, c
     }
 }
 
-__device__ __forceinline__ float xhat_from_y(float y, float gamma, float beta) {
-    return gamma != 0.f ? (y - beta) / gamma : 0.f;
-}
-
 // ws[0..C) += sum g ; ws[C..2C) += sum g*xhat   with g = dy * act'(y)
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs, const T *y, int y_cs, const T *z, int z_cs,
+                                                          const float *scale, const float *shift,
                                                           const float *mean, const float *rstd, int act,
                                                           const float *gamma, const float *beta, long long P, int C,
                                                           double *ws, long long rows_per_cta) {
@@ -104,9 +188,10 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs
         float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
         float mu = z ? mean[c] : 0.f, rs = z ? rstd[c] : 0.f;
         for (long long m = r0 + threadIdx.y; m < rend; m += 8) {
-            float yy = to_f(y[m * y_cs + c]);
+            float zz = z ? to_f(z[m * z_cs + c]) : 0.f;
+            float yy = z ? apply_act(zz * scale[c] + shift[c], act) : to_f(y[m * y_cs + c]);
             float g = to_f(dy[m * dy_cs + c]) * act_mask(yy, act);
-            float xh = z ? (to_f(z[m * z_cs + c]) - mu) * rs : xhat_from_y(yy, ga, be);
+            float xh = z ? (zz - mu) * rs : xhat_from_y(yy, ga, be);
             a += (double)g;
             b += (double)(g * xh);
         }
@@ -140,7 +225,7 @@ __global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, flo
 template <typename T, int V>
 __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, const T *y, int y_cs, const T *z, int z_cs,
                                                         const float *mean, const float *rstd, int act,
-                                                        const float *scale,
+                                                        const float *scale, const float *shift,
                                                         const float *coef, int training, T *dz, int dz_cs, long long P,
                                                         int C) {
     const int CV = C / V;
@@ -151,8 +236,13 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, 
         long long pix = idx / CV;
         float g[V], yy[V], zz[V];
         load_vec<T, V>(dy + pix * dy_cs + cv * V, g);
-        load_vec<T, V>(y + pix * y_cs + cv * V, yy);
-        if (training) load_vec<T, V>(z + pix * z_cs + cv * V, zz);
+        if (training) {
+            load_vec<T, V>(z + pix * z_cs + cv * V, zz);
+#pragma unroll
+            for (int j = 0; j < V; ++j) yy[j] = apply_act(zz[j] * scale[cv * V + j] + shift[cv * V + j], act);
+        } else {
+            load_vec<T, V>(y + pix * y_cs + cv * V, yy);
+        }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             int c = cv * V + j;
@@ -176,6 +266,20 @@ static inline void slab_grid(long long P, int C, dim3 &grid, long long &rows) {
     rows = (P + want - 1) / want;
     if (rows < 64) rows = 64;
     grid = dim3(cblocks, cdiv(P, rows));
+}
+
+// vectorised reductions: one slab per CTA, ~8 CTAs per SM; returns false if the tensor is not vector-addressable
+template <int V>
+static inline bool vec_reduce_cfg(int C, long long P, int &blocks, long long &rows, size_t &smem) {
+    if (C % V || C / V > 256 || C / V < 1) return false;
+    int PL = 256 / (C / V);
+    long long want = (long long)NASB_SM_COUNT * 8;
+    rows = (P + want - 1) / want;
+    long long minrows = (long long)PL * 8;
+    if (rows < minrows) rows = minrows;
+    blocks = cdiv(P, rows);
+    smem = (size_t)2 * PL * C * sizeof(float);
+    return smem <= 48 * 1024;
 }
 
 static inline int ew_grid(long long total) {
@@ -213,11 +317,19 @@ extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const floa
     if (e != cudaSuccess) return (int)e;
     dim3 grid;
     long long rows;
-    slab_grid(P, C, grid, rows);
-    if (z->dtype == NASB_BF16)
-        bn_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
-    else
-        bn_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)z->ptr, z->cstride, P, C, ws, rows);
+    int blocks;
+    size_t smem;
+    if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_reduce_cfg<8>(C, P, blocks, rows, smem)) {
+        bn_sums_vec_kernel<bf16, 8><<<blocks, 256, smem, ST>>>((const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
+    } else if (z->dtype == NASB_F32 && vec_ok(*z, 4) && vec_reduce_cfg<4>(C, P, blocks, rows, smem)) {
+        bn_sums_vec_kernel<float, 4><<<blocks, 256, smem, ST>>>((const float *)z->ptr, z->cstride, P, C, ws, rows);
+    } else {
+        slab_grid(P, C, grid, rows);
+        if (z->dtype == NASB_BF16)
+            bn_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
+        else
+            bn_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)z->ptr, z->cstride, P, C, ws, rows);
+    }
     NASB_CHECK_LAUNCH();
     bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                            save_mean, save_rstd, scale, shift);
@@ -264,12 +376,15 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
 }
 
 extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,
-                               const float *beta, const float *scale, const float *save_mean, const float *save_rstd,
-                               int training, float *dgamma, float *dbeta, const NasbTensor *dz, void *workspace,
-                               void *stream) {
-    if (!dy || !y || !dz || !workspace) return NASB_ERR_BAD_ARG;
-    if (training && (!z || !save_mean || !save_rstd || z->dtype != dy->dtype || z->c != dy->c || npix(*z) != npix(*dy)))
+                               const float *beta, const float *scale, const float *shift, const float *save_mean,
+                               const float *save_rstd, int training, float *dgamma, float *dbeta, const NasbTensor *dz,
+                               void *workspace, void *stream) {
+    if (!dy || !dz || !workspace) return NASB_ERR_BAD_ARG;
+    if (training && (!z || !scale || !shift || !save_mean || !save_rstd || z->dtype != dy->dtype || z->c != dy->c ||
+                     npix(*z) != npix(*dy)))
         return NASB_ERR_BAD_ARG;
+    if (!training && !y) return NASB_ERR_BAD_ARG;
+    if (training) y = z;  // the activation mask is recomputed from z, y is not read
     if (!training) z = nullptr;
     const void *zp = z ? z->ptr : nullptr;
     const int zcs = z ? z->cstride : 0;
@@ -287,15 +402,29 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
         if (e != cudaSuccess) return (int)e;
         dim3 grid;
         long long rows;
+        int blocks;
+        size_t smem;
+        const NasbTensor *yz = training ? z : y;
+        if (dy->dtype == NASB_BF16 && vec_ok(*dy, 8) && vec_ok(*yz, 8) && vec_reduce_cfg<8>(C, P, blocks, rows, smem)) {
+            bn_bwd_sums_vec_kernel<bf16, 8><<<blocks, 256, smem, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)yz->ptr,
+                                                                       yz->cstride, training, scale, shift, save_mean,
+                                                                       save_rstd, gamma, beta, act, P, C, ws, rows);
+        } else if (dy->dtype == NASB_F32 && vec_ok(*dy, 4) && vec_ok(*yz, 4) && vec_reduce_cfg<4>(C, P, blocks, rows, smem)) {
+            bn_bwd_sums_vec_kernel<float, 4><<<blocks, 256, smem, ST>>>((const float *)dy->ptr, dy->cstride,
+                                                                        (const float *)yz->ptr, yz->cstride, training, scale,
+                                                                        shift, save_mean, save_rstd, gamma, beta, act, P, C, ws,
+                                                                        rows);
+        } else {
         slab_grid(P, C, grid, rows);
         if (dy->dtype == NASB_BF16)
             bn_bwd_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
-                                                                   y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act,
+                                                                   y->cstride, (const bf16 *)zp, zcs, scale, shift, save_mean, save_rstd, act,
                                                                    gamma, beta, P, C, ws, rows);
         else
             bn_bwd_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
-                                                                    y->cstride, (const float *)zp, zcs, save_mean, save_rstd, act,
+                                                                    y->cstride, (const float *)zp, zcs, scale, shift, save_mean, save_rstd, act,
                                                                     gamma, beta, P, C, ws, rows);
+        }
         NASB_CHECK_LAUNCH();
         bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef);
         NASB_CHECK_LAUNCH();
@@ -303,21 +432,21 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
     if (dy->dtype == NASB_BF16) {
         if (vec_ok(*dy, 8) && vec_ok(*y, 8) && vec_ok(*dz, 8) && (!z || vec_ok(*z, 8)))
             bn_bwd_dz_kernel<bf16, 8><<<ew_grid(P * (C / 8)), 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
-                                                                            y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, coef,
+                                                                            y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, shift, coef,
                                                                             training, (bf16 *)dz->ptr, dz->cstride, P, C);
         else
             bn_bwd_dz_kernel<bf16, 1><<<ew_grid(P * C), 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
-                                                                      y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, coef,
+                                                                      y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, shift, coef,
                                                                       training, (bf16 *)dz->ptr, dz->cstride, P, C);
     } else {
         if (vec_ok(*dy, 4) && vec_ok(*y, 4) && vec_ok(*dz, 4) && (!z || vec_ok(*z, 4)))
             bn_bwd_dz_kernel<float, 4><<<ew_grid(P * (C / 4)), 256, 0, ST>>>((const float *)dy->ptr, dy->cstride,
                                                                              (const float *)y->ptr, y->cstride, (const float *)zp, zcs, save_mean,
-                                                                             save_rstd, act, scale, coef, training, (float *)dz->ptr,
+                                                                             save_rstd, act, scale, shift, coef, training, (float *)dz->ptr,
                                                                              dz->cstride, P, C);
         else
             bn_bwd_dz_kernel<float, 1><<<ew_grid(P * C), 256, 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
-                                                                       y->cstride, (const float *)zp, zcs, save_mean, save_rstd, act, scale, coef,
+                                                                       y->cstride, (const float *)zp, zcs, save_mean, save_rstd, act, scale, shift, coef,
                                                                        training, (float *)dz->ptr, dz->cstride, P, C);
     }
     NASB_CHECK_LAUNCH();

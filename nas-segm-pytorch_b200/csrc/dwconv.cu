@@ -138,6 +138,84 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const DwP p, const vo
     }
 }
 
+
+// vectorised weight gradient: thread = (channel vector of V channels) x (pixel lane); a warp reads whole pixels
+// contiguously (V*sizeof(T) = 16 B for k=3, 8 B for k=5, 4 B for k=7 keeps k*k*V accumulators in registers).
+template <typename T, int KS, int V>
+__global__ void __launch_bounds__(256) dwconv_wgrad_vec_kernel(const DwP p, const void *dz_, int dz_cs, float *dw,
+                                                               long long rows_per_cta) {
+    constexpr int KK = KS * KS;
+    extern __shared__ float red_sm[];  // [PL][C]
+    const T *dz = reinterpret_cast<const T *>(dz_);
+    const T *x = reinterpret_cast<const T *>(p.x);
+    const int CV = p.C / V, PL = blockDim.x / CV;
+    const int t = threadIdx.x, cv = t % CV, pl = t / CV, c0 = cv * V;
+    const long long M = (long long)p.N * p.OH * p.OW;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+    float acc[KK][V];
+#pragma unroll
+    for (int i = 0; i < KK; ++i)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[i][j] = 0.f;
+    if (pl < PL) {
+        for (long long m = r0 + pl; m < r1; m += PL) {
+            int ox = (int)(m % p.OW);
+            long long tt = m / p.OW;
+            int oy = (int)(tt % p.OH);
+            int n = (int)(tt / p.OH);
+            float g[V];
+            load_vec<T, V>(dz + m * dz_cs + c0, g);
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+                int sy = oy * p.stride - p.pad + ky * p.dil;
+                if (sy < 0 || sy >= p.IH) continue;
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    int sx = ox * p.stride - p.pad + kx * p.dil;
+                    if (sx < 0 || sx >= p.IW) continue;
+                    float xv[V];
+                    load_vec<T, V>(x + (((long long)n * p.IH + sy) * p.IW + sx) * p.x_cs + c0, xv);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        float v = p.in_relu ? fmaxf(xv[j], 0.f) : xv[j];
+                        acc[ky * KS + kx][j] = fmaf(g[j], v, acc[ky * KS + kx][j]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int tap = 0; tap < KK; ++tap) {
+        if (pl < PL) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) red_sm[(size_t)pl * p.C + c0 + j] = acc[tap][j];
+        }
+        __syncthreads();
+        for (int c = t; c < p.C; c += blockDim.x) {
+            float sum = 0.f;
+            for (int i = 0; i < PL; ++i) sum += red_sm[(size_t)i * p.C + c];
+            atomicAdd(&dw[(long long)c * KK + tap], sum);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int KS, int V>
+static bool launch_dw_wgrad_vec(const DwP &p, const NasbTensor *x, const NasbTensor *dz, float *dweight, cudaStream_t st) {
+    if (!vec_ok(*x, V) || !vec_ok(*dz, V)) return false;
+    int CV = p.C / V;
+    if (CV < 1 || CV > 256) return false;
+    int PL = 256 / CV;
+    size_t smem = (size_t)PL * p.C * sizeof(float);
+    if (smem > 48 * 1024) return false;
+    long long M = (long long)p.N * p.OH * p.OW;
+    long long want = (long long)NASB_SM_COUNT * 8;
+    long long rows = (M + want - 1) / want;
+    if (rows < (long long)PL * 4) rows = (long long)PL * 4;
+    dwconv_wgrad_vec_kernel<T, KS, V><<<cdiv(M, rows), 256, smem, st>>>(p, dz->ptr, dz->cstride, dweight, rows);
+    return true;
+}
+
 template <typename T>
 static int launch_dw(const DwP &p, bool vec, long long rows, cudaStream_t st) {
     constexpr int V = 16 / sizeof(T);
@@ -234,6 +312,23 @@ extern "C" int nasb_dwconv_wgrad(const NasbTensor *x, int in_relu, const NasbTen
     p.in_relu = in_relu;
     long long M = npix(*dz);
     if (M == 0) return 0;
+    {
+        cudaStream_t st = (cudaStream_t)stream;
+        bool done = false;
+        if (x->dtype == NASB_BF16) {
+            if (ks == 3) done = launch_dw_wgrad_vec<bf16, 3, 8>(p, x, dz, dweight, st);
+            else if (ks == 5) done = launch_dw_wgrad_vec<bf16, 5, 4>(p, x, dz, dweight, st);
+            else done = launch_dw_wgrad_vec<bf16, 7, 2>(p, x, dz, dweight, st);
+        } else {
+            if (ks == 3) done = launch_dw_wgrad_vec<float, 3, 4>(p, x, dz, dweight, st);
+            else if (ks == 5) done = launch_dw_wgrad_vec<float, 5, 4>(p, x, dz, dweight, st);
+            else done = launch_dw_wgrad_vec<float, 7, 2>(p, x, dz, dweight, st);
+        }
+        if (done) {
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     const int CL = 32, PL = 8;
     int cblocks = cdiv(p.C, CL);
     long long want = (long long)NASB_SM_COUNT * 8 / cblocks;

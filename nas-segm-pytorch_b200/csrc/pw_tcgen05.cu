@@ -280,6 +280,105 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[co][ci] += sum_m dz[m][co] * x[m][ci].  Both operands are "MN-major" for this GEMM (the reduction index is the
+// pixel, the contiguous index is the channel), so the very same TMA boxes (64 channels x 128 pixels, 128-byte swizzle)
+// feed tcgen05.mma through MN-major descriptors: LBO = distance between 64-channel blocks, SBO = distance between
+// 8-pixel groups, 16 pixels (2 groups) per instruction.  A CTA accumulates its pixel chunks in TMEM (two-stage TMA ring),
+// then adds its 128 x C_in fp32 tile to dW with atomics.
+struct WgParams {
+    int M, Co, Ci;   // pixels, channels of this dz block (<= 128), channels of x (<= 256)
+    int npad, nbb;   // C_in rounded to 16, C_in blocks of 64
+    int tmem_cols;
+    float *dw;       // + co0 * ldw already applied
+    int ldw;         // row pitch of dW in floats (= total C_in)
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset: next 64-element MN block
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next group of 8 K (pixels)
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+constexpr int WG_STAGE_A = 2 * TILE_M * 128;  // two 64-channel blocks of dz
+
+__global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz,
+                                                                 const __grid_constant__ CUtensorMap map_x, const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stage_bytes = WG_STAGE_A + p.nbb * TILE_M * 128;
+    uint64_t *bars = (uint64_t *)(smem + 2 * (size_t)stage_bytes);  // full[2], done[2]
+    uint32_t *s_tmem = (uint32_t *)(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = (p.M + TILE_M - 1) / TILE_M;
+    const int my_n = blockIdx.x < nchunks ? (nchunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (tid == 0 && my_n > 0) {
+        uint32_t idesc = make_idesc_bf16(p.npad) | (1u << 15) | (1u << 16);  // A and B MN-major
+        auto load = [&](int i) {
+            const int s = i & 1;
+            uint8_t *st = smem + (size_t)s * stage_bytes;
+            const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE_M;
+            mbar_expect_tx(&bars[s], (uint32_t)stage_bytes);
+            tma_load_2d(st, &map_dz, &bars[s], 0, m0);
+            tma_load_2d(st + TILE_M * 128, &map_dz, &bars[s], 64, m0);
+            for (int b = 0; b < p.nbb; ++b) tma_load_2d(st + WG_STAGE_A + (size_t)b * TILE_M * 128, &map_x, &bars[s], b * 64, m0);
+        };
+        load(0);
+        for (int i = 0; i < my_n; ++i) {
+            const int s = i & 1;
+            if (i + 1 < my_n) {
+                if (i >= 1) mbar_wait(&bars[2 + ((i + 1) & 1)], (uint32_t)(((i + 1) >> 1) - 1) & 1);  // stage free again
+                load(i + 1);
+            }
+            mbar_wait(&bars[s], (uint32_t)(i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + WG_STAGE_A;
+#pragma unroll
+            for (int ks = 0; ks < TILE_M / 16; ++ks) {
+                uint64_t ad = make_desc_mn_sw128(a0 + ks * 2048, TILE_M * 128);
+                uint64_t bd = make_desc_mn_sw128(b0 + ks * 2048, TILE_M * 128);
+                umma_f16(tmem_base, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(&bars[2 + s]);
+        }
+    }
+    if (my_n > 0) {
+        const int last = my_n - 1;
+        mbar_wait(&bars[2 + (last & 1)], (uint32_t)(last >> 1) & 1);
+        tc_fence_after();
+        const int co = warp * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (co < p.Co) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.Ci) atomicAdd(&p.dw[(size_t)co * p.ldw + c0 + j], v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // weight [rows][cols] fp32 (row-major) -> bf16 [R][Kp]:  transpose=0: out[r][k] = w[r][k] ; transpose=1: out[r][k] = w[k][r]
 __global__ void pack_weight_kernel(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,5 +490,58 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     if (grid > ntiles) grid = ntiles;
     pw_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, p);
     NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int nasb_pw_tc_wgrad_supported(int Co, int Ci) {
+    if (Co < 8 || Ci < 8 || (Co % 8) || (Ci % 8) || Ci > 256) return 0;
+    int nbb = (Ci + 63) / 64;
+    size_t smem = 2 * ((size_t)WG_STAGE_A + (size_t)nbb * TILE_M * 128) + 64 + 1024;
+    return smem <= 200 * 1024 ? 1 : 0;
+}
+
+// dweight[co][ci] += sum over pixels dz[.,co] * x[.,ci]   (1x1 convolution, fp32 [C_out][C_in] layout)
+extern "C" int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float *dweight, void *stream) {
+    if (!x || !dz || !dweight) return NASB_ERR_BAD_ARG;
+    if (x->dtype != NASB_BF16 || dz->dtype != NASB_BF16 || npix(*x) != npix(*dz)) return NASB_ERR_BAD_ARG;
+    if (!vec_ok(*x, 8) || !vec_ok(*dz, 8) || !nasb_pw_tc_wgrad_supported(dz->c, x->c)) return NASB_ERR_UNSUPPORTED;
+    long long M = npix(*x);
+    if (M == 0) return 0;
+    if (M > 0x7fffffffLL) return NASB_ERR_UNSUPPORTED;
+    const int Ci = x->c, Co = dz->c;
+    WgParams p{};
+    p.M = (int)M;
+    p.Ci = Ci;
+    p.npad = (Ci + 15) / 16 * 16;
+    p.nbb = (Ci + 63) / 64;
+    int cols = 32;
+    while (cols < p.npad) cols <<= 1;
+    p.tmem_cols = cols;
+    p.ldw = Ci;
+    CUtensorMap mx;
+    if (!make_map(&mx, x->ptr, (uint64_t)Ci, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    size_t smem = 2 * ((size_t)WG_STAGE_A + (size_t)p.nbb * TILE_M * 128) + 64 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int nchunks = (int)((M + TILE_M - 1) / TILE_M);
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
+    if (per_sm < 1) per_sm = 1;
+    int grid = NASB_SM_COUNT * per_sm;
+    if (grid > nchunks) grid = nchunks;
+    for (int co0 = 0; co0 < Co; co0 += 128) {
+        CUtensorMap mdz;
+        const int cb = Co - co0 < 128 ? Co - co0 : 128;
+        if (!make_map(&mdz, (const bf16 *)dz->ptr + co0, (uint64_t)cb, (uint64_t)M, (uint64_t)dz->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+        p.Co = cb;
+        p.dw = dweight + (size_t)co0 * Ci;
+        pw_wgrad_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mdz, mx, p);
+        NASB_CHECK_LAUNCH();
+    }
     return 0;
 }

@@ -40,6 +40,15 @@ def _tc_ok(x, cin, cout, out_dtype):
     return bool(lib.load().nasb_pw_tc_supported(int(cin), int(cout)))
 
 
+def _tc_wgrad_ok(x, dz, cout):
+    from . import config
+    if not config().use_tcgen05 or x.dtype != torch.bfloat16 or dz.dtype != torch.bfloat16:
+        return False
+    if x.data_ptr() % 16 or dz.data_ptr() % 16 or lib.desc(x).cstride % 8 or lib.desc(dz).cstride % 8:
+        return False
+    return bool(lib.load().nasb_pw_tc_wgrad_supported(int(cout), int(x.shape[1])))
+
+
 def _pack_weight(weight, transpose):
     """fp32 [C_out, C_in, 1, 1] -> bf16 [R][Kp] operand of the tensor-core kernel (a few KB; repacked per call because the
     optimiser rewrites the fp32 master weights every step)."""
@@ -149,7 +158,8 @@ class _ConvUnit(torch.autograd.Function):
         if ctx.bn_mode or act != ACT_NONE:
             dz = lib.new_act(*y.shape, y.dtype, dev)
             call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)), ref(desc(z)) if z is not None else None, act, ptr(gamma),
-                 ptr(beta), ptr(ss[0]) if ss is not None else None, ptr(sv[0]) if sv is not None else None,
+                 ptr(beta), ptr(ss[0]) if ss is not None else None, ptr(ss[1]) if ss is not None else None,
+                 ptr(sv[0]) if sv is not None else None,
                  ptr(sv[1]) if sv is not None else None, 1 if ctx.bn_mode == 2 else 0, ptr(dgamma), ptr(dbeta),
                  ref(desc(dz)), ptr(_ws(dev, cout)))
         else:
@@ -162,7 +172,10 @@ class _ConvUnit(torch.autograd.Function):
         ddz = desc(dz)
         if need[2]:
             dweight = torch.zeros_like(weight, dtype=torch.float32)
-            if dw:
+            if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image and not in_relu
+                    and _tc_wgrad_ok(x0, dz, cout)):
+                call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dweight))
+            elif dw:
                 call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
             else:
                 dsrc0 = lib.desc_nchw_f32(x0) if image else desc(x0)
@@ -238,7 +251,7 @@ class _BnAct(torch.autograd.Function):
         dbeta = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[1] else None
         dx = lib.new_act(*y.shape, y.dtype, dev)
         call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)), ref(desc(x)) if ctx.training else None, ctx.act, ptr(gamma),
-             ptr(beta), ptr(ss[0]), ptr(sv[0]) if sv is not None else None, ptr(sv[1]) if sv is not None else None,
+             ptr(beta), ptr(ss[0]), ptr(ss[1]), ptr(sv[0]) if sv is not None else None, ptr(sv[1]) if sv is not None else None,
              1 if ctx.training else 0, ptr(dgamma), ptr(dbeta), ref(desc(dx)), ptr(_ws(dev, c)))
         return dx, dgamma, dbeta, None, None
 

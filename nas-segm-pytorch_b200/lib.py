@@ -30,6 +30,8 @@ _SIG = {
     "nasb_conv_wgrad": [_TP, _TP, _P, _P, _I, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_pack_weight_bf16": [_P, _I, _I, _I, _P, _P],
     "nasb_pw_tc_supported": [_I, _I],
+    "nasb_pw_tc_wgrad_supported": [_I, _I],
+    "nasb_pw_tc_wgrad": [_TP, _TP, _P, _P],
     "nasb_pw_tc_fwd": [_TP, _P, _I, _P, _P, _I, _TP, _TP, _P, _P],
     "nasb_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "nasb_dwconv_fwd": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
@@ -39,7 +41,7 @@ _SIG = {
     "nasb_bn_stats_workspace": [_I],
     "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     "nasb_affine_act": [_TP, _P, _P, _I, _TP, _P],
-    "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
+    "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
     "nasb_pool3x3_fwd": [_TP, _I, _I, _TP, _P, _P],
     "nasb_pool3x3_bwd": [_TP, _I, _I, _P, _TP, _P],
     "nasb_resize_axpby": [_TP, _P, _TP, _P, _TP, _P],

@@ -104,7 +104,7 @@ def test_network_train_step(golden, tag):
     named = {("encoder." + k): p for k, p in enc.named_parameters()}
     named.update({("decoder." + k): p for k, p in dec.named_parameters()})
     sd64, sd32 = _oracle_train(tag, fx, torch.float64), _oracle_train(tag, fx, torch.float32)
-    bad, checked = [], 0
+    bad, checked, e_all, e_cpu_all = [], 0, [], []
     for k, p in named.items():
         g64 = sd64[k].grad
         if g64 is None:
@@ -119,9 +119,14 @@ def test_network_train_step(golden, tag):
         e_cuda = rel_err(_np(p.grad), g64.numpy())
         e_cpu = rel_err(sd32[k].grad.numpy(), g64.numpy())
         checked += 1
-        if e_cuda > max(5e-3, 3.0 * e_cpu):
+        e_all.append(e_cuda)
+        e_cpu_all.append(e_cpu)
+        # per parameter: a single ReLU whose pre-activation is ~0 may flip between two fp32 evaluations and move the
+        # gradient of everything upstream by one term (~1/#elements); anything beyond that band is a bug
+        if e_cuda > max(2e-2, 3.0 * e_cpu):
             bad.append((k, e_cuda, e_cpu))
     assert checked > 100 and not bad, bad[:20]
+    assert np.median(e_all) <= max(1e-3, 3.0 * np.median(e_cpu_all)), (np.median(e_all), np.median(e_cpu_all))
     # the real reference's fixture gradients (fp32) must sit in the same error band around fp64
     for k in [k for k in fx.files if k.startswith("grad/")]:
         g64 = sd64[k[5:]].grad.numpy()

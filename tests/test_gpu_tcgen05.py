@@ -104,7 +104,7 @@ def test_conv_unit_tc_vs_cuda_core_path():
             nas_segm_b200.config().use_tcgen05 = True
     # The two paths round differently (bf16 weights on the tensor cores), so a few ReLU masks flip for |y| ~ 0 and single
     # elements of the input gradient legitimately move by a whole term: compare in the mean, not in the max.
-    for a, b, tol in zip(outs[True], outs[False], (1e-2, 3e-2, 2e-2, 2e-2, 1e-3)):
+    for a, b, tol in zip(outs[True], outs[False], (1e-2, 5e-2, 5e-2, 5e-2, 1e-3)):
         assert float((a - b).abs().mean() / b.abs().mean()) < tol
 
 
@@ -119,3 +119,31 @@ def test_tc_dgrad_is_the_same_kernel_with_transposed_pack():
     ref = dz.float().reshape(M, cout) @ w.reshape(cout, cin).to(torch.bfloat16).float()
     got = dx.permute(0, 2, 3, 1).float().reshape(M, cin)
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+def test_tc_wgrad_mn_major():
+    """dW = dz^T x on the tensor cores (MN-major descriptors) vs an fp32 matmul of the same bf16 operands."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    bad = []
+    for Co, Ci in [(64, 64), (96, 16), (24, 96), (144, 24), (32, 144), (64, 128), (64, 224), (192, 32), (48, 24), (8, 8),
+                   (256, 64), (16, 256)]:
+        assert lib.load().nasb_pw_tc_wgrad_supported(Co, Ci) == 1, (Co, Ci)
+        for M in (1, 127, 128, 300, 20011):
+            dz = torch.randn(1, 1, M, Co, generator=g, device="cuda").to(torch.bfloat16)
+            x = torch.randn(1, 1, M, Ci, generator=g, device="cuda").to(torch.bfloat16)
+            dw = torch.zeros(Co, Ci, device="cuda")
+            lib.call("nasb_pw_tc_wgrad", lib.ref(lib.desc(x.permute(0, 3, 1, 2))), lib.ref(lib.desc(dz.permute(0, 3, 1, 2))),
+                     lib.ptr(dw))
+            torch.cuda.synchronize()
+            ref = dz.float().reshape(M, Co).t() @ x.float().reshape(M, Ci)
+            err = float((dw - ref).abs().max() / ref.abs().max().clamp_min(1e-6))
+            if not err < 2e-3:
+                bad.append((Co, Ci, M, err))
+    assert not bad, bad
+    # accumulates (+=) and honours channel-slice views
+    wide = torch.randn(2, 9, 11, 96, generator=g, device="cuda").to(torch.bfloat16)
+    x, dz = wide[..., 8:40], wide[..., 48:96]
+    dw = torch.ones(48, 32, device="cuda")
+    lib.call("nasb_pw_tc_wgrad", lib.ref(lib.desc(x.permute(0, 3, 1, 2))), lib.ref(lib.desc(dz.permute(0, 3, 1, 2))), lib.ptr(dw))
+    ref = 1 + dz.float().reshape(-1, 48).t() @ x.float().reshape(-1, 32)
+    assert float((dw - ref).abs().max() / ref.abs().max()) < 2e-3
