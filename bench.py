@@ -53,6 +53,7 @@ def args_():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of one instrumented step")
     return ap.parse_args()
 
 
@@ -351,6 +352,11 @@ def main():
             trainer.segmenter_step(seg, img_d, lab_d, optim_enc, optim_dec, crit, 3.0, 3.0, False)
         prof = lib.profile_end()
         tot = sum(v[1] for v in prof.values())
+        if a.profile_out:
+            with open(a.profile_out, "w") as f:
+                f.write("# ms_per_step  calls_per_step  avg_ms  GB/s(algorithmic)  key\n")
+                for k, (c, t_ms, b) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+                    f.write("%9.3f %4d %8.4f %8.1f  %s\n" % (t_ms / n_prof, c // n_prof, t_ms / c, b / (t_ms / c * 1e-3) / 1e9, k))
         by_entry = {}
         for k, (c, t_ms, b) in prof.items():
             e = by_entry.setdefault(k.split("[")[0], [0, 0.0, 0.0])

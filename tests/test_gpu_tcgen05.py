@@ -96,6 +96,7 @@ def test_conv_unit_tc_vs_cuda_core_path():
         try:
             xi = x.clone().requires_grad_(True)
             m.zero_grad()
+            m[1].reset_running_stats()
             y = m(xi)
             (y.float() * torch.linspace(-1, 1, y.numel(), device="cuda").reshape(y.shape)).sum().backward()
             outs[tc] = (y.detach().float(), xi.grad.float(), m[0].weight.grad.clone(), m[1].weight.grad.clone(),
