@@ -154,13 +154,14 @@ int nasb_pool3x3_bwd(const NasbTensor *dy, int mode, int stride, const uint8_t *
 /* ---------------------------------------------------------------------------------------------------------
  * Bilinear resize, align_corners=False, up or down (layer_factory.py:338-350, micro_decoders.py:11-25,47-50,
  * trainer.py:141-143,153-155, inference.py:58-60), fused with the aggregation that follows it:
- *    out = sa[c] * resize(x) + sb[c] * y        (sa, sb NULL = 1;  y NULL = no second operand)
+ *    out = [relu]( sa[c] * resize(x) + sb[c] * y )   (sa, sb NULL = 1;  y NULL = no second operand; relu = the F.relu
+ *    the decoders apply to the collected concat, micro_decoders.py:251,395)
  * When x already has out's size the resize is the identity.  Covers AggregateCell's sum
  * (micro_decoders.py:51), ParamSum (layer_factory.py:353-366) and writing resized maps into concat slices.
  * nasb_resize_bwd : dx = resize^T(sa * dz)   (deterministic gather form)
  * nasb_axpby_bwd_params : dsa[c] += sum dz*resize(x), dsb[c] += sum dz*y  (ParamSum's a / b gradients)
  * -------------------------------------------------------------------------------------------------------*/
-int nasb_resize_axpby(const NasbTensor *x, const float *sa, const NasbTensor *y, const float *sb,
+int nasb_resize_axpby(const NasbTensor *x, const float *sa, const NasbTensor *y, const float *sb, int relu,
                       const NasbTensor *out, void *stream);
 int nasb_resize_bwd(const NasbTensor *dz, const float *sa, const NasbTensor *dx, void *stream);
 int nasb_axpby_bwd_params(const NasbTensor *dz, const NasbTensor *x, const NasbTensor *y, float *dsa, float *dsb,

@@ -79,20 +79,37 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_vec_kernel(const T *dy, int d
                                                               int act, long long P, int C, double *ws,
                                                               long long rows_per_cta) {
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
+    // this thread's channel vector is fixed: keep its per-channel constants in registers
+    const int my_c0 = (threadIdx.x % (C / V)) * V;
+    float k_s[V], k_b[V], k_mu[V], k_rs[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = my_c0 + j;
+        if (training) {
+            k_s[j] = scale[c];
+            k_b[j] = shift[c];
+            k_mu[j] = mean[c];
+            k_rs[j] = rstd[c];
+        } else {  // eval: xhat = (y - beta) / gamma  ->  (y - k_mu) * k_rs
+            float ga = gamma ? gamma[c] : 1.f;
+            k_s[j] = k_b[j] = 0.f;
+            k_mu[j] = beta ? beta[c] : 0.f;
+            k_rs[j] = ga != 0.f ? 1.f / ga : 0.f;
+        }
+    }
     colreduce2<V>(r0, r1, C, ws, [&](long long m, int c0, float (&a)[V], float (&b)[V]) {
         float g[V], v[V];
         load_vec<T, V>(dy + m * dy_cs + c0, g);
         load_vec<T, V>(yz + m * yz_cs + c0, v);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            const int c = c0 + j;
             float yy, xh;
             if (training) {
-                yy = apply_act(v[j] * scale[c] + shift[c], act);
-                xh = (v[j] - mean[c]) * rstd[c];
+                yy = apply_act(v[j] * k_s[j] + k_b[j], act);
+                xh = (v[j] - k_mu[j]) * k_rs[j];
             } else {
                 yy = v[j];
-                xh = xhat_from_y(yy, gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f);
+                xh = (yy - k_mu[j]) * k_rs[j];
             }
             float gm = g[j] * act_mask(yy, act);
             a[j] += gm;
@@ -259,6 +276,87 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, 
     }
 }
 
+
+// Element-wise passes with a FIXED channel vector per thread: thread t owns channel vector cv = t % CV for its whole
+// life, so the per-channel constants live in registers and the inner loop is 16-byte loads / stores only.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) affine_act_fixed_kernel(const T *z, int z_cs, const float *scale, const float *shift,
+                                                               int act, T *y, int y_cs, long long P, int C) {
+    const int CV = C / V, PL = blockDim.x / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * V;
+    if (pl >= PL) return;
+    float s[V], b[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        s[j] = scale ? scale[c0 + j] : 1.f;
+        b[j] = shift ? shift[c0 + j] : 0.f;
+    }
+    const long long G = (long long)gridDim.x * PL;
+    for (long long m = (long long)blockIdx.x * PL + pl; m < P; m += 2 * G) {
+        const long long m1 = m + G;
+        float v0[V], v1[V];
+        load_vec<T, V>(z + m * z_cs + c0, v0);
+        if (m1 < P) load_vec<T, V>(z + m1 * z_cs + c0, v1);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v0[j] = apply_act(v0[j] * s[j] + b[j], act);
+        store_vec<T, V>(y + m * y_cs + c0, v0);
+        if (m1 < P) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v1[j] = apply_act(v1[j] * s[j] + b[j], act);
+            store_vec<T, V>(y + m1 * y_cs + c0, v1);
+        }
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_bwd_dz_fixed_kernel(const T *dy, int dy_cs, const T *yz, int yz_cs, int training,
+                                                              const float *scale, const float *shift, const float *mean,
+                                                              const float *rstd, const float *coef, int act, T *dz, int dz_cs,
+                                                              long long P, int C) {
+    const int CV = C / V, PL = blockDim.x / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * V;
+    if (pl >= PL) return;
+    float s[V], b[V], mu[V], rs[V], k1[V], k2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        s[j] = scale ? scale[c0 + j] : 1.f;
+        b[j] = (training && shift) ? shift[c0 + j] : 0.f;
+        mu[j] = training ? mean[c0 + j] : 0.f;
+        rs[j] = training ? rstd[c0 + j] : 0.f;
+        k1[j] = training ? coef[c0 + j] : 0.f;
+        k2[j] = training ? coef[C + c0 + j] : 0.f;
+    }
+    const long long G = (long long)gridDim.x * PL;
+    for (long long m = (long long)blockIdx.x * PL + pl; m < P; m += G) {
+        float g[V], v[V];
+        load_vec<T, V>(dy + m * dy_cs + c0, g);
+        load_vec<T, V>(yz + m * yz_cs + c0, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (training) {
+                float yy = apply_act(v[j] * s[j] + b[j], act);
+                float gm = g[j] * act_mask(yy, act);
+                float xh = (v[j] - mu[j]) * rs[j];
+                g[j] = s[j] * (gm - k1[j] - xh * k2[j]);
+            } else {
+                g[j] = s[j] * g[j] * act_mask(v[j], act);
+            }
+        }
+        store_vec<T, V>(dz + m * dz_cs + c0, g);
+    }
+}
+
+static inline bool fixed_cfg(int C, int V, long long P, int &blocks) {
+    if (C % V || C / V > 256 || C / V < 1) return false;
+    int PL = 256 / (C / V);
+    long long b = (P + (long long)PL * 4 - 1) / ((long long)PL * 4);  // >= 4 pixels per thread
+    long long cap = (long long)NASB_SM_COUNT * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    blocks = (int)b;
+    return true;
+}
+
 static inline void slab_grid(long long P, int C, dim3 &grid, long long &rows) {
     int cblocks = cdiv(C, 32);
     long long want = (long long)NASB_SM_COUNT * 8 / cblocks;
@@ -356,6 +454,21 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
     long long P = npix(*z);
     if (P == 0) return 0;
     int C = z->c;
+    {
+        int blocks;
+        if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
+            affine_act_fixed_kernel<bf16, 8><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+                                                                     (bf16 *)y->ptr, y->cstride, P, C);
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
+        if (z->dtype == NASB_F32 && vec_ok(*z, 4) && vec_ok(*y, 4) && fixed_cfg(C, 4, P, blocks)) {
+            affine_act_fixed_kernel<float, 4><<<blocks, 256, 0, ST>>>((const float *)z->ptr, z->cstride, scale, shift, act,
+                                                                      (float *)y->ptr, y->cstride, P, C);
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     if (z->dtype == NASB_BF16) {
         if (vec_ok(*z, 8) && vec_ok(*y, 8))
             affine_act_kernel<bf16, 8><<<ew_grid(P * (C / 8)), 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
@@ -428,6 +541,24 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
         NASB_CHECK_LAUNCH();
         bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef);
         NASB_CHECK_LAUNCH();
+    }
+    {
+        int blocks;
+        const NasbTensor *yz = training ? z : y;
+        if (dy->dtype == NASB_BF16 && vec_ok(*dy, 8) && vec_ok(*yz, 8) && vec_ok(*dz, 8) && fixed_cfg(C, 8, P, blocks)) {
+            bn_bwd_dz_fixed_kernel<bf16, 8><<<blocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)yz->ptr,
+                                                                    yz->cstride, training, scale, shift, save_mean, save_rstd,
+                                                                    coef, act, (bf16 *)dz->ptr, dz->cstride, P, C);
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
+        if (dy->dtype == NASB_F32 && vec_ok(*dy, 4) && vec_ok(*yz, 4) && vec_ok(*dz, 4) && fixed_cfg(C, 4, P, blocks)) {
+            bn_bwd_dz_fixed_kernel<float, 4><<<blocks, 256, 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)yz->ptr,
+                                                                     yz->cstride, training, scale, shift, save_mean, save_rstd,
+                                                                     coef, act, (float *)dz->ptr, dz->cstride, P, C);
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
     }
     if (dy->dtype == NASB_BF16) {
         if (vec_ok(*dy, 8) && vec_ok(*y, 8) && vec_ok(*dz, 8) && (!z || vec_ok(*z, 8)))

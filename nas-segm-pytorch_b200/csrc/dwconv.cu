@@ -211,7 +211,7 @@ static bool launch_dw_wgrad_vec(const DwP &p, const NasbTensor *x, const NasbTen
     long long M = (long long)p.N * p.OH * p.OW;
     long long want = (long long)NASB_SM_COUNT * 8;
     long long rows = (M + want - 1) / want;
-    if (rows < (long long)PL * 4) rows = (long long)PL * 4;
+    if (rows < (long long)PL * 48) rows = (long long)PL * 48;  // >= 48 pixels per thread before the per-tap reduction
     dwconv_wgrad_vec_kernel<T, KS, V><<<cdiv(M, rows), 256, smem, st>>>(p, dz->ptr, dz->cstride, dweight, rows);
     return true;
 }

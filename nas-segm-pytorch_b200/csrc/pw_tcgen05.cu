@@ -118,6 +118,36 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
     return d;
 }
 
+// Sum over the 32 lanes (= 32 pixel rows) of 16 per-lane column values with a transposing butterfly: 16 shuffles instead
+// of 80.  Returns, in every lane, the total of column `col` where col = 8*b4 + 4*b3 + 2*b2 + b1 of the lane index.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, int &col) {
+    float w8[8], w4[4], w2[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float send = hi ? v[j] : v[j + 8], keep = hi ? v[j + 8] : v[j];
+        w8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float send = hi ? w8[j] : w8[j + 4], keep = hi ? w8[j + 4] : w8[j];
+        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float send = hi ? w4[j] : w4[j + 2], keep = hi ? w4[j + 2] : w4[j];
+        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    hi = lane & 2;
+    float send = hi ? w2[0] : w2[1], keep = hi ? w2[1] : w2[0];
+    float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    col = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+    return w1;
+}
+
 struct PwParams {
     int M, K, N;          // pixels, C_in, C_out
     int nkb, nnb, npad;   // K blocks of 64, N blocks of 64, N rounded up to 16
@@ -178,13 +208,16 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
     const uint32_t idesc = make_idesc_bf16(p.npad);
     const int row = warp * 32 + lane;  // TMEM lane == row of the tile owned by this thread
 
+    auto load_a = [&](int tile) {
+        mbar_expect_tx(bar_a, (uint32_t)(p.nkb * TILE_M * 128));
+        for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sA + (size_t)kb * TILE_M * 128, &map_a, bar_a, kb * 64, tile * TILE_M);
+    };
+    if (tid == 0 && (int)blockIdx.x < ntiles) load_a(blockIdx.x);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t parity = it & 1;
         const int m0 = tile * TILE_M;
         if (tid == 0) {
-            mbar_expect_tx(bar_a, (uint32_t)(p.nkb * TILE_M * 128));
-            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sA + (size_t)kb * TILE_M * 128, &map_a, bar_a, kb * 64, m0);
             if (it == 0) mbar_wait(bar_b, 0);
             mbar_wait(bar_a, parity);
             tc_fence_after();
@@ -199,6 +232,8 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         }
         mbar_wait(bar_mma, parity);
         tc_fence_after();
+        // the A tile has been consumed: prefetch the next one underneath this tile's epilogue
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) load_a(tile + gridDim.x);
 
         // ---- epilogue: TMEM -> registers -> (BN fold / bias, activation, residual) -> bf16 -> swizzled smem
         const long long m = (long long)m0 + row;
@@ -224,6 +259,20 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
                         if (c0 + j < p.N) v[j] += __bfloat162float(rp[j]);
                 }
             }
+            if (p.stats) {  // statistics of the value as stored (bf16-rounded), rows beyond M excluded
+                float q[16], q2[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    q[j] = row_ok ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+                    q2[j] = q[j] * q[j];
+                }
+                int col;
+                float t1 = warp_colsum16(q, lane, col), t2 = warp_colsum16(q2, lane, col);
+                if (!(lane & 1) && c0 + col < p.N) {
+                    atomicAdd(&s_sum[c0 + col], t1);
+                    atomicAdd(&s_sq[c0 + col], t2);
+                }
+            }
             const int nb = c0 >> 6, ch = (c0 & 63) >> 3;  // 64-column block, first 16-byte chunk inside the 128-byte row
             uint8_t *orow = sO + (size_t)nb * TILE_M * 128 + (size_t)row * 128;
             uint4 q0, q1;
@@ -242,27 +291,6 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         if (tid == 0) {
             for (int nb = 0; nb < p.nnb; ++nb) tma_store_2d(&map_o, sO + (size_t)nb * TILE_M * 128, nb * 64, m0);
             tma_store_commit();
-        }
-        if (p.stats) {
-            // column statistics of the tile as stored (bf16-rounded): thread -> column tid % npad, rows strided
-            const int rows_valid = min(TILE_M, p.M - m0);
-            const int cw = p.npad < TC_THREADS ? p.npad : TC_THREADS;  // columns covered per pass
-            const int groups = TC_THREADS / cw, g = tid / cw;
-            if (g < groups) {
-                for (int c = tid % cw; c < p.N; c += cw) {
-                    const int nb = c >> 6, ch = (c & 63) >> 3, e = c & 7;
-                    const uint8_t *blk = sO + (size_t)nb * TILE_M * 128;
-                    float s1 = 0.f, s2 = 0.f;
-                    for (int r = g; r < rows_valid; r += groups) {
-                        float x = __bfloat162float(
-                            *reinterpret_cast<const bf16 *>(blk + (size_t)r * 128 + ((ch ^ (r & 7)) << 4) + e * 2));
-                        s1 += x;
-                        s2 = fmaf(x, x, s2);
-                    }
-                    atomicAdd(&s_sum[c], s1);
-                    atomicAdd(&s_sq[c], s2);
-                }
-            }
         }
         if (tid == 0) tma_store_wait_read();  // smem tile may be overwritten once the bulk store has read it
         __syncthreads();

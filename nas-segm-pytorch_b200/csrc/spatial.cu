@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T *dy, int dy_cs, T
 template <typename T, typename TY, int V>
 __global__ void __launch_bounds__(256) resize_axpby_kernel(const T *x, int x_cs, int IH, int IW, const float *sa,
                                                            const TY *y, int y_cs, const float *sb, T *out, int out_cs,
-                                                           int N, int OH, int OW, int C, float rh, float rw, int identity) {
+                                                           int N, int OH, int OW, int C, float rh, float rw, int identity,
+                                                           int relu) {
     const int CV = C / V;
     const long long total = (long long)N * OH * OW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -158,6 +159,10 @@ __global__ void __launch_bounds__(256) resize_axpby_kernel(const T *x, int x_cs,
             load_vec<TY, V>(y + pix * y_cs + c0, yv);
 #pragma unroll
             for (int j = 0; j < V; ++j) r[j] += (sb ? sb[c0 + j] : 1.f) * yv[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) r[j] = fmaxf(r[j], 0.f);
         }
         store_vec<T, V>(out + pix * out_cs + c0, r);
     }
@@ -467,7 +472,7 @@ extern "C" int nasb_pool3x3_bwd(const NasbTensor *dy, int mode, int stride, cons
     return 0;
 }
 
-extern "C" int nasb_resize_axpby(const NasbTensor *x, const float *sa, const NasbTensor *y, const float *sb,
+extern "C" int nasb_resize_axpby(const NasbTensor *x, const float *sa, const NasbTensor *y, const float *sb, int relu,
                                  const NasbTensor *out, void *stream) {
     if (!x || !out || !act_dtype(x) || x->dtype != out->dtype || x->c != out->c || x->n != out->n) return NASB_ERR_BAD_ARG;
     if (y && (!same_nhw(y, out) || y->c != out->c || !act_dtype(y))) return NASB_ERR_BAD_ARG;
@@ -481,16 +486,16 @@ extern "C" int nasb_resize_axpby(const NasbTensor *x, const float *sa, const Nas
         if (x->dtype == NASB_BF16)
             resize_axpby_kernel<bf16, float, 1><<<grid_for(rows * x->c), 256, 0, ST>>>(
                 (const bf16 *)x->ptr, x->cstride, x->h, x->w, sa, (const float *)y->ptr, y->cstride, sb, (bf16 *)out->ptr,
-                out->cstride, out->n, out->h, out->w, out->c, rh, rw, identity);
+                out->cstride, out->n, out->h, out->w, out->c, rh, rw, identity, relu);
         else
             resize_axpby_kernel<float, bf16, 1><<<grid_for(rows * x->c), 256, 0, ST>>>(
                 (const float *)x->ptr, x->cstride, x->h, x->w, sa, (const bf16 *)y->ptr, y->cstride, sb, (float *)out->ptr,
-                out->cstride, out->n, out->h, out->w, out->c, rh, rw, identity);
+                out->cstride, out->n, out->h, out->w, out->c, rh, rw, identity, relu);
     } else {
         NASB_DISPATCH(x->dtype, ok, (resize_axpby_kernel<T, T, V><<<grid_for(rows * (x->c / V)), 256, 0, ST>>>(
                                         (const T *)x->ptr, x->cstride, x->h, x->w, sa, y ? (const T *)y->ptr : nullptr,
                                         y ? y->cstride : 0, sb, (T *)out->ptr, out->cstride, out->n, out->h, out->w, out->c,
-                                        rh, rw, identity)));
+                                        rh, rw, identity, relu)));
     }
     NASB_CHECK_LAUNCH();
     return 0;

@@ -132,13 +132,13 @@ class _ConvUnit(torch.autograd.Function):
                 bn.num_batches_tracked.add_(1)
             call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
             if res is not None and not late_res:
-                call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, ref(desc(y)))
+                call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
         ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
         ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
         ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
         if late_res:
             out = lib.new_act(n, cout, oh, ow, out_dtype, dev)
-            call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, ref(desc(out)))
+            call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(out)))
             return out
         return y
 
@@ -297,7 +297,7 @@ class _ResizeAxpby(torch.autograd.Function):
         n, c = x.shape[:2]
         oh, ow = size
         out = lib.new_act(n, c, oh, ow, x.dtype, x.device)
-        call("nasb_resize_axpby", ref(desc(x)), ptr(sa), ref(desc(y)) if y is not None else None, ptr(sb), ref(desc(out)))
+        call("nasb_resize_axpby", ref(desc(x)), ptr(sa), ref(desc(y)) if y is not None else None, ptr(sb), 0, ref(desc(out)))
         ctx.save_for_backward(x, y, sa, sb)
         return out
 
@@ -339,11 +339,12 @@ def resize_add(x, y, sa=None, sb=None):
 
 
 class _ConcatResize(torch.autograd.Function):
-    """torch.cat([resize(t, size) for t in tensors], 1): every producer-side resize writes straight into its channel
-    slice of the concat buffer (collect_all, micro_decoders.py:11-25; ConcatReduce's cat, layer_factory.py:380)."""
+    """[relu](torch.cat([resize(t, size) for t in tensors], 1)): every producer-side resize writes straight into its channel
+    slice of the concat buffer (collect_all, micro_decoders.py:11-25; ConcatReduce's cat, layer_factory.py:380); the
+    optional ReLU is the F.relu the decoders apply to the collected map (micro_decoders.py:251,395)."""
 
     @staticmethod
-    def forward(ctx, size, *tensors):
+    def forward(ctx, size, relu, *tensors):
         lib.require_cuda(tensors[0])
         n = tensors[0].shape[0]
         ctot = sum(t.shape[1] for t in tensors)
@@ -351,29 +352,37 @@ class _ConcatResize(torch.autograd.Function):
         c0 = 0
         for t in tensors:
             c = t.shape[1]
-            call("nasb_resize_axpby", ref(desc(t)), None, None, None, ref(desc(out[:, c0:c0 + c])))
+            call("nasb_resize_axpby", ref(desc(t)), None, None, None, 1 if relu else 0, ref(desc(out[:, c0:c0 + c])))
             c0 += c
         ctx.shapes = [tuple(t.shape) for t in tensors]
+        ctx.relu = relu
+        if relu:
+            ctx.save_for_backward(out)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         dout = _grad_in(dout, dout.dtype)
+        if ctx.relu:
+            (out,) = ctx.saved_tensors
+            masked = lib.new_act(*out.shape, dout.dtype, dout.device)
+            call("nasb_relu_bwd", ref(desc(dout)), ref(desc(out)), ref(desc(masked)))
+            dout = masked
         grads, c0 = [], 0
         for i, shp in enumerate(ctx.shapes):
             c = shp[1]
-            if ctx.needs_input_grad[i + 1]:
+            if ctx.needs_input_grad[i + 2]:
                 dx = lib.new_act(*shp, dout.dtype, dout.device)
                 call("nasb_resize_bwd", ref(desc(dout[:, c0:c0 + c])), None, ref(desc(dx)))
                 grads.append(dx)
             else:
                 grads.append(None)
             c0 += c
-        return (None, *grads)
+        return (None, None, *grads)
 
 
-def concat_resize(tensors, size):
-    return _ConcatResize.apply((int(size[0]), int(size[1])), *tensors)
+def concat_resize(tensors, size, relu=False):
+    return _ConcatResize.apply((int(size[0]), int(size[1])), bool(relu), *tensors)
 
 
 class _ChannelTile(torch.autograd.Function):

@@ -44,7 +44,7 @@ _SIG = {
     "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
     "nasb_pool3x3_fwd": [_TP, _I, _I, _TP, _P, _P],
     "nasb_pool3x3_bwd": [_TP, _I, _I, _P, _TP, _P],
-    "nasb_resize_axpby": [_TP, _P, _TP, _P, _TP, _P],
+    "nasb_resize_axpby": [_TP, _P, _TP, _P, _I, _TP, _P],
     "nasb_resize_bwd": [_TP, _P, _TP, _P],
     "nasb_axpby_bwd_params": [_TP, _TP, _TP, _P, _P, _P, _P],
     "nasb_scale_copy": [_TP, _P, _I, _TP, _P],

@@ -14,7 +14,7 @@ from ..rl.genotypes import AGG_OP_NAMES, OP_NAMES, OP_NAMES_WACV
 from .layer_factory import AGG_OPS, OPS, conv3x3, conv_bn_relu
 
 
-def collect_all(feats, collect_indices):
+def collect_all(feats, collect_indices, relu=False):
     """Concatenate the loose-end maps at the largest height among them (micro_decoders.py:11-25): the running
     result is resized whenever a taller map arrives, i.e. every map ends up bilinearly resized (possibly in several
     hops) to the tallest size.  Hops are kept so the arithmetic matches the reference exactly."""
@@ -28,13 +28,14 @@ def collect_all(feats, collect_indices):
             size = tuple(c.shape[2:])
             out = [Fn.resize(o, size) for o in out]
         out.append(c)
-    return Fn.concat_resize(out, size)
+    return Fn.concat_resize(out, size, relu)
 
 
 def _head(module_pre, module_clf, cat):
-    """F.relu(cat) -> pre_clf (1x1 conv-BN-ReLU) -> conv_clf (3x3, bias): the ReLU rides in the 1x1's prologue."""
+    """pre_clf (1x1 conv-BN-ReLU) -> conv_clf (3x3, bias); `cat` already carries the F.relu (applied while the concat
+    slices were written)."""
     conv, bn = module_pre[0], module_pre[1]
-    x = Fn.conv_unit(cat, conv.weight, bn, ks=1, act=Fn.ACT_RELU, in_relu=1)
+    x = Fn.conv_unit(cat, conv.weight, bn, ks=1, act=Fn.ACT_RELU)
     return clf3x3(module_clf, x)
 
 
@@ -179,7 +180,7 @@ class MicroDecoder(nn.Module):
             if self.aux_cell:
                 a = head.aux_cell(a)
             aux_outs.append(clf3x3(head.aux_clf, a))
-        out = _head(self.pre_clf, self.conv_clf, collect_all(x, self.collect_inds))
+        out = _head(self.pre_clf, self.conv_clf, collect_all(x, self.collect_inds, relu=True))
         return out, aux_outs
 
 
@@ -248,4 +249,4 @@ class TemplateDecoder(nn.Module):
                 out = ops[i * 3 + 2](ops[i * 3](feat1), ops[i * 3 + 1](feat2))
                 feat1, feat2 = feat2, out
             feats.append(out)
-        return _head(self.pre_clf, self.conv_clf, collect_all(feats, self._collect_inds))
+        return _head(self.pre_clf, self.conv_clf, collect_all(feats, self._collect_inds, relu=True))
