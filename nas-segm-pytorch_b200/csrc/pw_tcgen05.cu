@@ -149,9 +149,8 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, i
 }
 
 struct PwParams {
-    int M, K, N;          // pixels, C_in, C_out
-    int nkb, nnb, npad;   // K blocks of 64, N blocks of 64, N rounded up to 16
-    int tmem_cols;
+    int M, K, N;     // pixels, C_in, C_out
+    int nkb, nnb;    // K blocks of 64, N blocks of 64 (one N block per CTA)
     const float *scale, *shift;
     int act;
     const bf16 *res;
@@ -161,27 +160,36 @@ struct PwParams {
 
 constexpr int TC_THREADS = 128;
 constexpr int TILE_M = 128;
+constexpr int TILE_N = 64;
 
+// CTA c works on output-channel block nb = c % nnb (64 channels, weights loaded once) and on the 128-pixel tiles
+// c / nnb, c / nnb + gridDim.x / nnb, ...  Splitting N keeps the per-CTA footprint small (8 KB of weights per K block,
+// a 16 KB output tile, 64 TMEM columns), so 4-5 CTAs are resident per SM and their load / MMA / epilogue / store phases
+// overlap; the A tile of a pixel block is re-read by the nnb CTAs that share it out of L2.
 __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const __grid_constant__ CUtensorMap map_o, const PwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve (all tile regions are multiples of 1024 B)
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sB = smem;                                   // nkb x [npad x 128 B]
-    uint8_t *sA = sB + (size_t)p.nkb * p.npad * 128;      // nkb x [128 x 128 B]
-    uint8_t *sO = sA + (size_t)p.nkb * TILE_M * 128;      // nnb x [128 x 128 B]
-    float *s_scale = (float *)(sO + (size_t)p.nnb * TILE_M * 128);
-    float *s_shift = s_scale + p.npad;
-    float *s_sum = s_shift + p.npad;
-    float *s_sq = s_sum + p.npad;
-    uint64_t *bar_b = (uint64_t *)(s_sq + p.npad);
+    uint8_t *sB = smem;                                    // nkb x [64 x 128 B]
+    uint8_t *sA = sB + (size_t)p.nkb * TILE_N * 128;       // nkb x [128 x 128 B]
+    uint8_t *sO = sA + (size_t)p.nkb * TILE_M * 128;       // [128 x 128 B]
+    float *s_scale = (float *)(sO + (size_t)TILE_M * 128);
+    float *s_shift = s_scale + TILE_N;
+    float *s_sum = s_shift + TILE_N;
+    float *s_sq = s_sum + TILE_N;
+    uint64_t *bar_b = (uint64_t *)(s_sq + TILE_N);
     uint64_t *bar_a = bar_b + 1;
     uint64_t *bar_mma = bar_a + 1;
     uint32_t *s_tmem = (uint32_t *)(bar_mma + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.M + TILE_M - 1) / TILE_M;
+    const int nb = (int)blockIdx.x % p.nnb, n0 = nb * TILE_N;
+    const int nblk = p.N - n0 < TILE_N ? p.N - n0 : TILE_N;   // valid channels of this block
+    const int npb = (nblk + 15) / 16 * 16;                     // MMA N
+    const int tile0 = (int)blockIdx.x / p.nnb, tstride = (int)gridDim.x / p.nnb;
+    const uint32_t tmem_cols = npb > 32 ? 64u : 32u;
 
     if (tid == 0) {
         mbar_init(bar_b, 1);
@@ -189,32 +197,32 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         mbar_init(bar_mma, 1);
         fence_barrier_init();
     }
-    for (int i = tid; i < p.npad; i += TC_THREADS) {
-        s_scale[i] = (p.scale && i < p.N) ? p.scale[i] : 1.f;
-        s_shift[i] = (p.shift && i < p.N) ? p.shift[i] : 0.f;
+    for (int i = tid; i < TILE_N; i += TC_THREADS) {
+        s_scale[i] = (p.scale && i < nblk) ? p.scale[n0 + i] : 1.f;
+        s_shift[i] = (p.shift && i < nblk) ? p.shift[n0 + i] : 0.f;
         s_sum[i] = 0.f;
         s_sq[i] = 0.f;
     }
-    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+    if (warp == 0) tmem_alloc(s_tmem, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (tid == 0) {  // weights: once per CTA
-        mbar_expect_tx(bar_b, (uint32_t)(p.nkb * p.npad * 128));
-        for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * p.npad * 128, &map_b, bar_b, kb * 64, 0);
-    }
-    const uint32_t idesc = make_idesc_bf16(p.npad);
-    const int row = warp * 32 + lane;  // TMEM lane == row of the tile owned by this thread
-
     auto load_a = [&](int tile) {
         mbar_expect_tx(bar_a, (uint32_t)(p.nkb * TILE_M * 128));
         for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sA + (size_t)kb * TILE_M * 128, &map_a, bar_a, kb * 64, tile * TILE_M);
     };
-    if (tid == 0 && (int)blockIdx.x < ntiles) load_a(blockIdx.x);
+    if (tid == 0 && tile0 < ntiles) {  // this block's weights (once) and the first pixel tile
+        mbar_expect_tx(bar_b, (uint32_t)(p.nkb * TILE_N * 128));
+        for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * TILE_N * 128, &map_b, bar_b, kb * 64, n0);
+        load_a(tile0);
+    }
+    const uint32_t idesc = make_idesc_bf16(npb);
+    const int row = warp * 32 + lane;  // TMEM lane == row of the tile owned by this thread
+
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < ntiles; tile += tstride, ++it) {
         const uint32_t parity = it & 1;
         const int m0 = tile * TILE_M;
         if (tid == 0) {
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int kb = ks >> 2, kin = ks & 3;  // 4 K-steps of 16 elements (32 B) per 128-byte swizzle row
                 uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)kb * TILE_M * 128) + kin * 32);
-                uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * p.npad * 128) + kin * 32);
+                uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * TILE_N * 128) + kin * 32);
                 umma_f16(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
             }
             umma_commit(bar_mma);
@@ -233,20 +241,20 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         mbar_wait(bar_mma, parity);
         tc_fence_after();
         // the A tile has been consumed: prefetch the next one underneath this tile's epilogue
-        if (tid == 0 && tile + (int)gridDim.x < ntiles) load_a(tile + gridDim.x);
+        if (tid == 0 && tile + tstride < ntiles) load_a(tile + tstride);
 
         // ---- epilogue: TMEM -> registers -> (BN fold / bias, activation, residual) -> bf16 -> swizzled smem
         const long long m = (long long)m0 + row;
         const bool row_ok = m < p.M;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+        for (int c0 = 0; c0 < npb; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
             if (p.res && row_ok) {
-                const bf16 *rp = p.res + m * p.res_cs + c0;
-                if (c0 + 16 <= p.N) {
+                const bf16 *rp = p.res + m * p.res_cs + n0 + c0;
+                if (c0 + 16 <= nblk) {
                     float r[8];
                     load_vec<bf16, 8>(rp, r);
 #pragma unroll
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
                     for (int j = 0; j < 8; ++j) v[8 + j] += r[j];
                 } else {
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+                        if (c0 + j < nblk) v[j] += __bfloat162float(rp[j]);
                 }
             }
             if (p.stats) {  // statistics of the value as stored (bf16-rounded), rows beyond M excluded
@@ -268,13 +276,13 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
                 }
                 int col;
                 float t1 = warp_colsum16(q, lane, col), t2 = warp_colsum16(q2, lane, col);
-                if (!(lane & 1) && c0 + col < p.N) {
+                if (!(lane & 1) && c0 + col < nblk) {
                     atomicAdd(&s_sum[c0 + col], t1);
                     atomicAdd(&s_sq[c0 + col], t2);
                 }
             }
-            const int nb = c0 >> 6, ch = (c0 & 63) >> 3;  // 64-column block, first 16-byte chunk inside the 128-byte row
-            uint8_t *orow = sO + (size_t)nb * TILE_M * 128 + (size_t)row * 128;
+            const int ch = c0 >> 3;  // first 16-byte chunk inside the 128-byte row
+            uint8_t *orow = sO + (size_t)row * 128;
             uint4 q0, q1;
             bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
 #pragma unroll
@@ -287,25 +295,25 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();  // tile complete in smem; every thread is done with TMEM and with A
+        __syncthreads();  // tile complete in smem; every thread is done with TMEM
         if (tid == 0) {
-            for (int nb = 0; nb < p.nnb; ++nb) tma_store_2d(&map_o, sO + (size_t)nb * TILE_M * 128, nb * 64, m0);
+            tma_store_2d(&map_o, sO, n0, m0);
             tma_store_commit();
+            tma_store_wait_read();  // smem tile may be overwritten once the bulk store has read it
         }
-        if (tid == 0) tma_store_wait_read();  // smem tile may be overwritten once the bulk store has read it
         __syncthreads();
     }
     if (tid == 0) tma_store_wait_all();
     if (p.stats) {
         __syncthreads();
-        for (int c = tid; c < p.N; c += TC_THREADS) {
-            atomicAdd(&p.stats[c], (double)s_sum[c]);
-            atomicAdd(&p.stats[p.N + c], (double)s_sq[c]);
+        for (int c = tid; c < nblk; c += TC_THREADS) {
+            atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
+            atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 
@@ -465,11 +473,14 @@ extern "C" int nasb_pack_weight_bf16(const float *w, int rows, int cols, int tra
 
 // Shapes the tensor-core path accepts: bf16 in/out, 8-aligned channels and pitches, C_in / C_out small enough for the
 // whole weight matrix plus one A tile and one output tile to fit in shared memory.
+static size_t pw_smem_bytes(int nkb) {
+    return (size_t)nkb * TILE_N * 128 + (size_t)nkb * TILE_M * 128 + (size_t)TILE_M * 128 + 4 * TILE_N * 4 + 64 + 1024;
+}
+
 extern "C" int nasb_pw_tc_supported(int K, int N) {
-    if (K < 8 || N < 8 || (K % 8) || (N % 8) || N > 256) return 0;
-    int nkb = (K + 63) / 64, nnb = (N + 63) / 64, npad = (N + 15) / 16 * 16;
-    size_t smem = (size_t)nkb * npad * 128 + (size_t)nkb * 128 * 128 + (size_t)nnb * 128 * 128 + 4 * npad * 4 + 64 + 1024;
-    return smem <= 200 * 1024 ? 1 : 0;
+    if (K < 8 || N < 8 || (K % 8) || (N % 8) || N > 4096) return 0;
+    int nkb = (K + 63) / 64;
+    return pw_smem_bytes(nkb) <= 200 * 1024 ? 1 : 0;
 }
 
 extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
@@ -486,11 +497,7 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     p.K = x->c;
     p.N = N;
     p.nkb = (p.K + 63) / 64;
-    p.nnb = (N + 63) / 64;
-    p.npad = (N + 15) / 16 * 16;
-    int cols = 32;
-    while (cols < p.npad) cols <<= 1;
-    p.tmem_cols = cols;
+    p.nnb = (N + TILE_N - 1) / TILE_N;
     p.scale = scale;
     p.shift = shift;
     p.act = act;
@@ -500,23 +507,23 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     int Kp = (p.K + 7) / 8 * 8;
     CUtensorMap ma, mb, mo;
     if (!make_map(&ma, x->ptr, (uint64_t)p.K, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
-    if (!make_map(&mb, wpack, (uint64_t)Kp, (uint64_t)N, (uint64_t)Kp, (uint32_t)p.npad)) return NASB_ERR_UNSUPPORTED;
+    if (!make_map(&mb, wpack, (uint64_t)Kp, (uint64_t)N, (uint64_t)Kp, TILE_N)) return NASB_ERR_UNSUPPORTED;
     if (!make_map(&mo, out->ptr, (uint64_t)N, (uint64_t)M, (uint64_t)out->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
-    size_t smem = (size_t)p.nkb * p.npad * 128 + (size_t)p.nkb * TILE_M * 128 + (size_t)p.nnb * TILE_M * 128 + 4 * p.npad * 4 + 64 + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
+    size_t smem = pw_smem_bytes(p.nkb);
+    static bool configured = false;
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
         if (e != cudaSuccess) return (int)e;
-        configured = 200 * 1024 + 2048;
+        configured = true;
     }
     int ntiles = (int)((M + TILE_M - 1) / TILE_M);
     int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
+    if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
-    int grid = NASB_SM_COUNT * per_sm;
-    if (grid > ntiles) grid = ntiles;
-    pw_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, p);
+    long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;  // a multiple of the N blocks
+    if (grid < p.nnb) grid = p.nnb;
+    if (grid > (long long)ntiles * p.nnb) grid = (long long)ntiles * p.nnb;
+    pw_tc_kernel<<<(int)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }

@@ -42,7 +42,8 @@ def test_tc_gemm_shapes_and_tails():
     g = torch.Generator(device="cuda").manual_seed(0)
     bad = []
     for K, N in [(16, 96), (96, 24), (24, 144), (144, 24), (144, 32), (32, 192), (192, 32), (24, 48), (32, 64), (64, 64),
-                 (128, 64), (224, 64), (8, 8), (48, 48), (64, 16), (16, 256), (256, 16), (200, 72)]:
+                 (128, 64), (224, 64), (8, 8), (48, 48), (64, 16), (16, 256), (256, 16), (200, 72), (96, 576), (448, 40),
+                 (64, 136)]:
         assert lib.load().nasb_pw_tc_supported(K, N) == 1, (K, N)
         for M in (1, 100, 128, 129, 4099):
             x = torch.randn(1, 1, M, K, generator=g, device="cuda").to(torch.bfloat16)
