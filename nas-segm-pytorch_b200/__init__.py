@@ -22,6 +22,7 @@ class _Config:
         import torch
         self.act_dtype = torch.float32
         self.use_tcgen05 = True  # bf16 pointwise convolutions on the tensor cores when shapes allow
+        self.use_tma_tiles = True  # bf16 depthwise convolutions on TMA-staged shared-memory tiles when shapes allow
 
 
 _config = None

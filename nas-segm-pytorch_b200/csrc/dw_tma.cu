@@ -1,0 +1,401 @@
+// dw_tma.cu -- depthwise k x k convolution on TMA-staged shared-memory tiles (bf16 activations, sm_100a).
+//
+// The gather kernels of dwconv.cu re-read every input pixel k*k times through L1 with per-tap address arithmetic and
+// bounds checks; on B200 they are instruction-bound (0.5-0.7 TB/s).  Here one CTA owns a TH x TW patch of output pixels
+// times CC channels: a single 4-D TMA box (channels, x, y, image) brings the input patch INCLUDING its halo into shared
+// memory -- out-of-image coordinates are zero-filled by the hardware, which is exactly the convolution's zero padding --
+// and the threads then work out of shared memory with no global address arithmetic at all:
+//   * forward / stride-1 data gradient: each thread produces a strip of 4 consecutive output pixels x 8 channels
+//     (16-byte LDS per tap, fp32 accumulation, fused BN-fold / activation epilogue, 16-byte coalesced stores);
+//   * weight gradient: thread = (channel vector, tap) pair walking the patch; partial sums stay in registers across the
+//     CTA's patches and are flushed once with fp32 atomics.
+// HBM traffic = input once (+ halo from L2) + output once.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace nasb {
+
+__device__ __forceinline__ uint32_t dsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dmbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsmem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void dmbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsmem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dmbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "DW_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DW_DONE;\n\t"
+        "bra DW_WAIT;\n\t"
+        "DW_DONE:\n\t"
+        "}" ::"r"(dsmem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            dsmem_u32(dst)),
+        "l"((uint64_t)map), "r"(dsmem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+struct DwT {
+    int N, IH, IW, OH, OW, C;     // forward-conv geometry of the tensor being READ (IH,IW) and WRITTEN (OH,OW)
+    int CC, nchunks;              // channels per CTA (multiple of 8, <= 64), C / CC
+    int TH, TW, ITH, ITW;         // output patch, input patch (with halo)
+    int stride, dil, pad;         // as seen by this launch (the data gradient passes pad' = dil*(k-1) - pad)
+    int flip;                     // 1: use the spatially flipped kernel (data gradient)
+    int tiles_x, tiles_y;
+    const float *w;               // [C][k*k]
+    const float *scale, *shift;
+    int act;
+    bf16 *out;
+    int out_cs;
+};
+
+constexpr int DW_P = 4;  // output pixels per strip
+
+template <int K>
+__global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const DwT p) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
+    bf16 *tile = reinterpret_cast<bf16 *>(base);                                   // [ITH][ITW][CC]
+    const size_t tile_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
+    float *wsm = reinterpret_cast<float *>(base + ((tile_bytes + 127) & ~(size_t)127));   // [K*K][CC]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + K * K * p.CC);
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.y, n = blockIdx.z;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int oy0 = ty * p.TH, ox0 = tx * p.TW, c_base = chunk * p.CC;
+
+    if (tid == 0) {
+        dmbar_init(bar, 1);
+        dmbar_expect_tx(bar, (uint32_t)tile_bytes);
+        tma_load_4d(tile, &map_x, bar, c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
+    }
+    for (int i = tid; i < K * K * p.CC; i += blockDim.x) {
+        int tap = i / p.CC, c = i - tap * p.CC;
+        int src_tap = p.flip ? (K * K - 1 - tap) : tap;
+        wsm[i] = p.w[(size_t)(c_base + c) * K * K + src_tap];
+    }
+    __syncthreads();  // barrier init + weights visible
+    dmbar_wait(bar, 0);
+
+    const int CVn = p.CC / 8;
+    const int strips_x = p.TW / DW_P;
+    const int items = p.TH * strips_x * CVn;
+    for (int it = tid; it < items; it += blockDim.x) {
+        const int cv = it % CVn;
+        const int sidx = it / CVn;
+        const int sx = sidx % strips_x, sy = sidx / strips_x;
+        const int oy = oy0 + sy, oxs = ox0 + sx * DW_P;
+        if (oy >= p.OH || oxs >= p.OW) continue;
+        float acc[DW_P][8];
+#pragma unroll
+        for (int q = 0; q < DW_P; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = sy * p.stride + ky * p.dil;
+            const bf16 *rowp = tile + ((size_t)iy * p.ITW) * p.CC + cv * 8;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8 + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int q = 0; q < DW_P; ++q) {
+                    const int ix = (sx * DW_P + q) * p.stride + kx * p.dil;
+                    float v[8];
+                    load_vec<bf16, 8>(rowp + (size_t)ix * p.CC, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(v[j], wv[j], acc[q][j]);
+                }
+            }
+        }
+        const int c0 = c_base + cv * 8;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = p.scale ? p.scale[c0 + j] : 1.f;
+            sh[j] = p.shift ? p.shift[c0 + j] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < DW_P; ++q) {
+            const int ox = oxs + q;
+            if (ox >= p.OW) break;
+            if (p.scale || p.shift || p.act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[q][j] = apply_act(acc[q][j] * sc[j] + sh[j], p.act);
+            }
+            store_vec<bf16, 8>(p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.out_cs + c0, acc[q]);
+        }
+    }
+}
+
+// ---- weight gradient on tiles: thread = (tap, channel vector, pixel lane); persistent over the CTA's patches
+struct DwW {
+    int N, IH, IW, OH, OW, C;
+    int CC, nchunks;
+    int TH, TW, ITH, ITW;
+    int stride, dil, pad;
+    int tiles_x, tiles_y;
+    float *dw;  // [C][k*k]
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_dz, const DwW p) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
+    bf16 *xt = reinterpret_cast<bf16 *>(base);  // [ITH][ITW][CC]
+    const size_t xt_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
+    bf16 *zt = reinterpret_cast<bf16 *>(base + ((xt_bytes + 127) & ~(size_t)127));  // [TH][TW][CC]
+    const size_t zt_bytes = (size_t)p.TH * p.TW * p.CC * 2;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(zt) + ((zt_bytes + 127) & ~(size_t)127));
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.y, c_base = chunk * p.CC;
+    const int CVn = p.CC / 8;
+    const int pairs = K * K * CVn;          // (tap, cv) pairs
+    const int PLn = blockDim.x / pairs;     // pixel lanes per pair (>= 1 guaranteed by the host)
+    const int pair = tid % pairs, pl = tid / pairs;
+    const int tap = pair / CVn, cv = pair - tap * CVn;
+    const int ky = tap / K, kx = tap - ky * K;
+    const bool active = pl < PLn;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+
+    if (tid == 0) dmbar_init(bar, 1);
+    __syncthreads();
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int total = tiles_per_img * p.N;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int oy0 = ty * p.TH, ox0 = tx * p.TW;
+        if (tid == 0) {
+            dmbar_expect_tx(bar, (uint32_t)(xt_bytes + zt_bytes));
+            tma_load_4d(xt, &map_x, bar, c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
+            tma_load_4d(zt, &map_dz, bar, c_base, ox0, oy0, n);
+        }
+        dmbar_wait(bar, it & 1);
+        if (active) {
+            // out-of-image dz pixels are zero-filled by TMA, so the whole patch can be walked unconditionally
+            const int npx = p.TH * p.TW;
+            for (int px = pl; px < npx; px += PLn) {
+                const int sy = px / p.TW, sx = px - sy * p.TW;
+                float g[8], v[8];
+                load_vec<bf16, 8>(zt + (size_t)px * p.CC + cv * 8, g);
+                load_vec<bf16, 8>(xt + ((size_t)(sy * p.stride + ky * p.dil) * p.ITW + (sx * p.stride + kx * p.dil)) * p.CC + cv * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], v[j], acc[j]);
+            }
+        }
+        __syncthreads();  // everyone done with the patch before the next TMA overwrites it
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&p.dw[(size_t)(c_base + cv * 8 + j) * K * K + tap], acc[j]);
+    }
+}
+
+typedef CUresult (*DwEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static DwEncodeFn dw_get_encode() {
+    static DwEncodeFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (DwEncodeFn)ptr;
+    }
+    return fn;
+}
+
+// 4-D map (C, W, H, N) over an NHWC bf16 tensor, box (cc, bw, bh, 1), no swizzle
+static bool make_map4(CUtensorMap *m, const NasbTensor *t, int cc, int bw, int bh) {
+    DwEncodeFn enc = dw_get_encode();
+    if (!enc || bw > 256 || bh > 256 || cc > 256) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+    cuuint64_t strides[3] = {(cuuint64_t)t->cstride * 2, (cuuint64_t)t->w * t->cstride * 2, (cuuint64_t)t->h * t->w * t->cstride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// channel chunk: the largest multiple of 8 that divides C and is <= 64
+static int pick_cc(int C) {
+    for (int cc = 64; cc >= 8; cc -= 8)
+        if (C % cc == 0) return cc;
+    return 0;
+}
+
+struct TilePlan {
+    int CC, TH, TW, ITH, ITW;
+    size_t smem;
+};
+
+static bool plan_tiles(int C, int ks, int stride, int dil, size_t extra_per_cc, size_t budget, TilePlan &pl) {
+    int cc = pick_cc(C);
+    if (!cc) return false;
+    const int th_opts[3] = {8, 4, 2}, tw = stride == 1 ? 32 : 16;
+    for (int cci = cc; cci >= 8; cci -= 8) {
+        if (C % cci) continue;
+        for (int i = 0; i < 3; ++i) {
+            int th = th_opts[i];
+            int ith = (th - 1) * stride + (ks - 1) * dil + 1, itw = (tw - 1) * stride + (ks - 1) * dil + 1;
+            size_t bytes = (size_t)ith * itw * cci * 2 + extra_per_cc * cci + 1024;
+            if (bytes <= budget && ith <= 256 && itw <= 256) {
+                pl = {cci, th, tw, ith, itw, bytes};
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+}  // namespace nasb
+
+using namespace nasb;
+
+// Forward (mode 0) or stride-1 data gradient (mode 1: x = dz, out = dx, flipped kernel).  Returns NASB_ERR_UNSUPPORTED for
+// configurations the tile path does not cover (the caller then uses the gather kernels of dwconv.cu).
+extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
+                                const float *out_scale, const float *out_shift, int act, const NasbTensor *out, void *stream) {
+    if (!x || !out || !weight) return NASB_ERR_BAD_ARG;
+    if (x->dtype != NASB_BF16 || out->dtype != NASB_BF16 || x->c != out->c || x->n != out->n) return NASB_ERR_UNSUPPORTED;
+    if ((ks != 3 && ks != 5) || !vec_ok(*x, 8) || !vec_ok(*out, 8)) return NASB_ERR_UNSUPPORTED;
+    if (mode == 1 && stride != 1) return NASB_ERR_UNSUPPORTED;
+    if (x->n > 65535) return NASB_ERR_UNSUPPORTED;
+    const int epad = mode == 1 ? dil * (ks - 1) - pad : pad;
+    if (epad < 0) return NASB_ERR_UNSUPPORTED;
+    {
+        int eh = (x->h + 2 * epad - dil * (ks - 1) - 1) / stride + 1, ew = (x->w + 2 * epad - dil * (ks - 1) - 1) / stride + 1;
+        if (eh != out->h || ew != out->w) return NASB_ERR_BAD_ARG;
+    }
+    TilePlan pl;
+    if (!plan_tiles(x->c, ks, stride, dil, (size_t)ks * ks * 4, 72 * 1024, pl)) return NASB_ERR_UNSUPPORTED;
+    if (npix(*out) == 0) return 0;
+    DwT p{};
+    p.N = x->n;
+    p.IH = x->h;
+    p.IW = x->w;
+    p.OH = out->h;
+    p.OW = out->w;
+    p.C = x->c;
+    p.CC = pl.CC;
+    p.nchunks = x->c / pl.CC;
+    p.TH = pl.TH;
+    p.TW = pl.TW;
+    p.ITH = pl.ITH;
+    p.ITW = pl.ITW;
+    p.stride = stride;
+    p.dil = dil;
+    p.pad = epad;
+    p.flip = mode == 1 ? 1 : 0;
+    p.tiles_x = cdiv(out->w, pl.TW);
+    p.tiles_y = cdiv(out->h, pl.TH);
+    p.w = weight;
+    p.scale = out_scale;
+    p.shift = out_shift;
+    p.act = act;
+    p.out = (bf16 *)out->ptr;
+    p.out_cs = out->cstride;
+    CUtensorMap mx;
+    if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH)) return NASB_ERR_UNSUPPORTED;
+    size_t smem = pl.smem + 256;
+    dim3 grid(p.tiles_x * p.tiles_y, p.nchunks, x->n);
+    static bool cfg3 = false, cfg5 = false;
+    if (ks == 3) {
+        if (!cfg3) {
+            if (cudaFuncSetAttribute(dw_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfg3 = true;
+        }
+        dw_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, p);
+    } else {
+        if (!cfg5) {
+            if (cudaFuncSetAttribute(dw_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfg5 = true;
+        }
+        dw_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, p);
+    }
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz, int ks, int stride, int dil, int pad,
+                                      float *dweight, void *stream) {
+    if (!x || !dz || !dweight) return NASB_ERR_BAD_ARG;
+    if (x->dtype != NASB_BF16 || dz->dtype != NASB_BF16 || x->c != dz->c || x->n != dz->n) return NASB_ERR_UNSUPPORTED;
+    if ((ks != 3 && ks != 5) || !vec_ok(*x, 8) || !vec_ok(*dz, 8)) return NASB_ERR_UNSUPPORTED;
+    TilePlan pl;
+    // extra per channel: the dz patch (TH*TW <= 8*32 pixels) * 2 bytes
+    if (!plan_tiles(x->c, ks, stride, dil, (size_t)8 * 32 * 2, 88 * 1024, pl)) return NASB_ERR_UNSUPPORTED;
+    const int pairs = ks * ks * (pl.CC / 8);
+    if (pairs > 256) return NASB_ERR_UNSUPPORTED;
+    if (npix(*dz) == 0) return 0;
+    DwW p{};
+    p.N = x->n;
+    p.IH = x->h;
+    p.IW = x->w;
+    p.OH = dz->h;
+    p.OW = dz->w;
+    p.C = x->c;
+    p.CC = pl.CC;
+    p.nchunks = x->c / pl.CC;
+    p.TH = pl.TH;
+    p.TW = pl.TW;
+    p.ITH = pl.ITH;
+    p.ITW = pl.ITW;
+    p.stride = stride;
+    p.dil = dil;
+    p.pad = pad;
+    p.tiles_x = cdiv(dz->w, pl.TW);
+    p.tiles_y = cdiv(dz->h, pl.TH);
+    p.dw = dweight;
+    CUtensorMap mx, mz;
+    if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH) || !make_map4(&mz, dz, pl.CC, pl.TW, pl.TH)) return NASB_ERR_UNSUPPORTED;
+    size_t smem = pl.smem + 512;
+    long long total = (long long)p.tiles_x * p.tiles_y * x->n;
+    int per_sm = (int)((200 * 1024) / smem);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    long long gx = (long long)NASB_SM_COUNT * per_sm / p.nchunks;
+    if (gx < 1) gx = 1;
+    if (gx > total) gx = total;
+    dim3 grid((unsigned)gx, p.nchunks);
+    static bool cfg3 = false, cfg5 = false;
+    if (ks == 3) {
+        if (!cfg3) {
+            if (cudaFuncSetAttribute(dw_wgrad_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfg3 = true;
+        }
+        dw_wgrad_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, mz, p);
+    } else {
+        if (!cfg5) {
+            if (cudaFuncSetAttribute(dw_wgrad_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfg5 = true;
+        }
+        dw_wgrad_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, mz, p);
+    }
+    NASB_CHECK_LAUNCH();
+    return 0;
+}

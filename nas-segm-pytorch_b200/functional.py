@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import lib
-from .lib import ACT_NONE, ACT_RELU, ACT_RELU6, POOL_AVG, POOL_MAX, call, desc, ptr, ref  # noqa: F401
+from .lib import ACT_NONE, ACT_RELU, ACT_RELU6, POOL_AVG, POOL_MAX, call, desc, ptr, ref, try_call  # noqa: F401
 
 
 def act_dtype():
@@ -28,6 +28,11 @@ def _ws(dev, c=0):
 def _grad_in(dy, like_dtype):
     """Incoming gradient -> NHWC storage of the expected dtype (a no-op when it comes from our own kernels)."""
     return lib.to_nhwc(dy, like_dtype)
+
+
+def _tiles_on():
+    from . import config
+    return config().use_tma_tiles
 
 
 def _tc_ok(x, cin, cout, out_dtype):
@@ -91,9 +96,13 @@ class _ConvUnit(torch.autograd.Function):
                      ref(desc(r)) if r is not None else None, ref(desc(out)), ptr(stats))
                 return
             if dw:
+                assert r is None
+                if not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and try_call(
+                        "nasb_dwconv_tile", ref(dx0), ptr(weight), ks, stride, dil, pad, 0, ptr(scale), ptr(shift), a,
+                        ref(desc(out))):
+                    return
                 call("nasb_dwconv_fwd", ref(dx0), ptr(weight), ks, stride, dil, pad, in_relu, ptr(scale), ptr(shift), a,
                      ref(desc(out)))
-                assert r is None
             else:
                 call("nasb_conv_fwd", ref(dx0), ref(dx1), ptr(weight), ks, stride, dil, pad, None, None, in_relu,
                      ptr(scale), ptr(shift), a, ref(desc(r)) if r is not None else None, ref(desc(out)))
@@ -176,7 +185,9 @@ class _ConvUnit(torch.autograd.Function):
                     and _tc_wgrad_ok(x0, dz, cout)):
                 call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dweight))
             elif dw:
-                call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
+                if not (not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and try_call(
+                        "nasb_dwconv_wgrad_tile", ref(desc(x0)), ref(ddz), ks, stride, dil, pad, ptr(dweight))):
+                    call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
             else:
                 dsrc0 = lib.desc_nchw_f32(x0) if image else desc(x0)
                 call("nasb_conv_wgrad", ref(dsrc0), ref(desc(x1)) if has_x1 else None, None, None, in_relu, ref(ddz), ks,
@@ -191,7 +202,10 @@ class _ConvUnit(torch.autograd.Function):
                 call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
                      ref(desc(dx0)), None)
             elif dw:
-                call("nasb_dwconv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)))
+                if not (stride == 1 and dz.dtype == torch.bfloat16 and _tiles_on() and try_call(
+                        "nasb_dwconv_tile", ref(ddz), ptr(weight), ks, stride, dil, pad, 1, None, None, ACT_NONE,
+                        ref(desc(dx0)))):
+                    call("nasb_dwconv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)))
             else:
                 call("nasb_conv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)),
                      ref(desc(dx1)) if has_x1 else None)

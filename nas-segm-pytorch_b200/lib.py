@@ -37,6 +37,8 @@ _SIG = {
     "nasb_dwconv_fwd": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
     "nasb_dwconv_dgrad": [_TP, _P, _I, _I, _I, _I, _TP, _P],
     "nasb_dwconv_wgrad": [_TP, _I, _TP, _I, _I, _I, _I, _P, _P],
+    "nasb_dwconv_tile": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
+    "nasb_dwconv_wgrad_tile": [_TP, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_bn_fold": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "nasb_bn_stats_workspace": [_I],
     "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -121,6 +123,29 @@ def call(name, *args):
     launches += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError("%s failed with code %d%s" % (name, rc, _explain(rc)))
+
+
+def try_call(name, *args):
+    """Like call(), but NASB_ERR_UNSUPPORTED is returned (False) instead of raised: used where a specialised kernel
+    declines a shape and the general CUDA kernel takes over (still no CPU fallback)."""
+    global launches
+    fn = getattr(load(), name)
+    if _prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        ev1.record()
+        if rc == 0:
+            key, nbytes = _describe(name, args)
+            _prof.append((key, nbytes, ev0, ev1))
+    else:
+        rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc == 10001:
+        return False
+    if rc != 0:
+        raise RuntimeError("%s failed with code %d%s" % (name, rc, _explain(rc)))
+    launches += _KERNELS_PER_CALL.get(name, 1)
+    return True
 
 
 def _describe(name, args):
