@@ -241,19 +241,22 @@ def build_model(dev, genotype=W0):
     return Wrapper(Seg(enc, dec)).to(dev)
 
 
-def fwd_latency(dev, genotype, h, w, dtype, iters=10):
+def fwd_latency(dev, genotype, h, w, dtype, iters=20, graph=False):
+    """Eval-mode forward latency, batch 1 (the reference README's table); graph=True replays a captured CUDA graph."""
     import nas_segm_b200
+    from nas_segm_b200.graphs import GraphedForward
     nas_segm_b200.set_act_dtype(dtype)
     m = build_model(dev, genotype).eval()
     x = torch.randn(1, 3, h, w, device=dev)
+    run = GraphedForward(m, x) if graph else m
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
         for _ in range(3):
-            m(x)
+            run(x)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(iters):
-            m(x)
+            run(x)
         e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
@@ -391,6 +394,7 @@ def main():
                 for (hh, ww) in ((1024, 2048), (360, 480)):
                     for dn, dt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
                         extras["%s_fwd_ms_b1_%dx%d_%s" % (name, ww, hh, dn)] = fwd_latency(dev, g, hh, ww, dt)
+                        extras["%s_fwd_ms_b1_%dx%d_%s_cudagraph" % (name, ww, hh, dn)] = fwd_latency(dev, g, hh, ww, dt, graph=True)
         finally:
             nas_segm_b200.set_act_dtype(dtype)
 

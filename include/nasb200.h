@@ -78,6 +78,14 @@ int nasb_conv_wgrad(const NasbTensor *x0, const NasbTensor *x1, const float *in_
                     int in_relu, const NasbTensor *dz, int ks, int stride, int dil, int pad, float *dweight,
                     void *stream);
 
+/* Encoder stem (encoders.py:38): 3x3 convolution of the planar fp32 image (NASB_F32_NCHW, 3 channels) into 32 NHWC
+ * channels with the folded-BN / activation epilogue, and its weight gradient.  NASB_ERR_UNSUPPORTED for any other shape
+ * (the generic implicit GEMM then runs). */
+int nasb_stem_fwd(const NasbTensor *img, const float *weight, int ks, int stride, int dil, int pad, const float *out_scale,
+                  const float *out_shift, int act, const NasbTensor *out, void *stream);
+int nasb_stem_wgrad(const NasbTensor *img, const NasbTensor *dz, int ks, int stride, int dil, int pad, float *dweight,
+                    void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Tensor-core path of the pointwise (1x1, stride 1) convolution: bf16 activations, TMA-staged 128-byte-swizzled
  * operands, tcgen05.mma (kind::f16, M=128) with the fp32 accumulator in TMEM, fused epilogue, TMA store.

@@ -104,6 +104,9 @@ class _ConvUnit(torch.autograd.Function):
                 call("nasb_dwconv_fwd", ref(dx0), ptr(weight), ks, stride, dil, pad, in_relu, ptr(scale), ptr(shift), a,
                      ref(desc(out)))
             else:
+                if image and r is None and try_call("nasb_stem_fwd", ref(dx0), ptr(weight), ks, stride, dil, pad, ptr(scale),
+                                                    ptr(shift), a, ref(desc(out))):
+                    return
                 call("nasb_conv_fwd", ref(dx0), ref(dx1), ptr(weight), ks, stride, dil, pad, None, None, in_relu,
                      ptr(scale), ptr(shift), a, ref(desc(r)) if r is not None else None, ref(desc(out)))
 
@@ -188,6 +191,9 @@ class _ConvUnit(torch.autograd.Function):
                 if not (not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and try_call(
                         "nasb_dwconv_wgrad_tile", ref(desc(x0)), ref(ddz), ks, stride, dil, pad, ptr(dweight))):
                     call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
+            elif image and try_call("nasb_stem_wgrad", ref(lib.desc_nchw_f32(x0)), ref(ddz), ks, stride, dil, pad,
+                                    ptr(dweight)):
+                pass
             else:
                 dsrc0 = lib.desc_nchw_f32(x0) if image else desc(x0)
                 call("nasb_conv_wgrad", ref(dsrc0), ref(desc(x1)) if has_x1 else None, None, None, in_relu, ref(ddz), ks,

@@ -157,3 +157,26 @@ def test_network_bf16_mode(golden, tag):
         out = out[0]
     assert out.dtype == torch.float32
     assert rel_err(_np(out), fx["out"]) < 5e-2
+
+
+def test_cuda_graph_forward_matches_eager(golden):
+    """A captured CUDA graph of the eval forward replays to the same logits as the eager call (fp32 and bf16)."""
+    from nas_segm_b200.graphs import GraphedForward
+    fx = golden("net_W0")
+    enc, dec = build("W0", fx)
+    model = torch.nn.Sequential(enc, dec).eval()
+    for dtype in (torch.float32, torch.bfloat16):
+        nas_segm_b200.set_act_dtype(dtype)
+        try:
+            x = t(fx["x"]).cuda()
+            with torch.no_grad():
+                ref = model(x).clone()
+            g = GraphedForward(model, x)
+            out = g(x).clone()
+            assert torch.equal(out, ref)
+            x2 = x * 0.5 + 0.1
+            with torch.no_grad():
+                ref2 = model(x2)
+            assert torch.equal(g(x2), ref2)
+        finally:
+            nas_segm_b200.set_act_dtype(torch.float32)
