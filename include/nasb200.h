@@ -78,6 +78,25 @@ int nasb_conv_wgrad(const NasbTensor *x0, const NasbTensor *x1, const float *in_
                     int in_relu, const NasbTensor *dz, int ks, int stride, int dil, int pad, float *dweight,
                     void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense 3x3 convolution (stride 1, any dilation, output size == input size) as an implicit GEMM on the tensor cores:
+ * nine shifted 4-D TMA boxes per pixel patch (hardware zero fill = zero padding), tcgen05.mma, TMEM accumulation.
+ * Registry ops conv3x3 / conv3x3_dil3 / conv3x3_dil12 (layer_factory.py:61-75) and the classifier heads
+ * (micro_decoders.py:218-224,224).
+ * nasb_pack_conv3_bf16 : fp32 [C_out][C_in][3][3] -> bf16 [9][Nr][Kp]; mode 0 forward, mode 1 data gradient
+ *                        (transposed + spatially flipped).  nasb_pack_conv3_elems gives the element count.
+ * nasb_conv3_tc_fwd    : x bf16 (any channel count, 16-byte pixel pitch) -> out bf16 or fp32, fused epilogue and
+ *                        optional BN statistics; the data gradient is the same call on dz with the mode-1 pack and
+ *                        pad' = 2*dil - pad.
+ * nasb_conv3_tc_wgrad  : dweight[co][ci][tap] += sum_pixels dz[.,co] * x[.+offset(tap),ci].
+ * -------------------------------------------------------------------------------------------------------*/
+long long nasb_pack_conv3_elems(int Co, int Ci, int mode);
+int nasb_pack_conv3_bf16(const float *w, int Co, int Ci, int mode, void *out, void *stream);
+int nasb_conv3_tc_supported(int K, int N);
+int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, int dil, int pad, const float *scale,
+                      const float *shift, int act, const NasbTensor *out, double *stats, void *stream);
+int nasb_conv3_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, int dil, int pad, float *dweight, void *stream);
+
 /* Encoder stem (encoders.py:38): 3x3 convolution of the planar fp32 image (NASB_F32_NCHW, 3 channels) into 32 NHWC
  * channels with the folded-BN / activation epilogue, and its weight gradient.  NASB_ERR_UNSUPPORTED for any other shape
  * (the generic implicit GEMM then runs). */

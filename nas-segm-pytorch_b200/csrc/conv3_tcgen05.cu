@@ -1,0 +1,480 @@
+// conv3_tcgen05.cu -- dense 3x3 convolution (stride 1, any dilation) as an implicit GEMM on the 5th-generation tensor
+// cores.  The nine taps are nine shifted views of the same NHWC tensor: a 4-D TMA box (64 channels, TW, TH, 1) started at
+// (x0 + dx, y0 + dy) lands in shared memory as 128 consecutive 128-byte rows -- exactly the K-major SWIZZLE_128B operand
+// tile tcgen05.mma wants -- and pixels outside the image are zero-filled by the hardware, which IS the convolution's zero
+// padding.  So no im2col buffer exists anywhere: HBM sees the input once (halo re-reads hit L2) and the output once.
+//   forward / data gradient : D[128 pixels, 64 c_out] += A_tap[128, 64] * B_tap[64, 64]^T over (tap, C_in block), TMEM
+//                             accumulator, ring of TMA stages with look-ahead across patches, fused epilogue
+//                             (BN fold / bias / activation, optional BN statistics), bf16 TMA store or fp32 direct store.
+//                             The data gradient is the same kernel on dz with the transposed + flipped weight pack.
+//   weight gradient         : dW[:, :, tap] = x_tap^T dz.  Two taps share one M=128 instruction (rows 0-63 = tap 2j,
+//                             rows 64-127 = tap 2j+1, MN-major descriptors), 5 TMEM accumulators live across all the
+//                             CTA's patches, one atomic flush at the end.
+#include "tc_common.cuh"
+
+namespace nasb {
+
+constexpr int C3_THREADS = 128;
+constexpr int C3_TILE = 128;  // pixels per patch
+constexpr int C3_NB = 64;     // output channels per CTA
+
+struct C3Params {
+    int NI, H, W;        // images, height, width (input == output size: stride 1, pad == dil*(3-1)/2 .. general pad below)
+    int K, N;            // C_in, C_out of this GEMM
+    int nkb, nnb;        // K blocks of 64, N blocks of 64
+    int dil, pad;
+    int TH, TW, tiles_x, tiles_y;
+    int stages;
+    int nr;              // rows per tap in the packed weight (N rounded up to 64)
+    const float *scale, *shift;
+    int act;
+    void *out;           // fp32 output (direct stores) when out_f32, else the TMA map is used
+    int out_cs, out_f32;
+    double *stats;
+};
+
+__global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                           const __grid_constant__ CUtensorMap map_b,
+                                                           const __grid_constant__ CUtensorMap map_o, const C3Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nb_items = 9 * p.nkb;
+    uint8_t *sB = smem;                                        // 9*nkb x [64 x 128 B]
+    uint8_t *sA = sB + (size_t)nb_items * C3_NB * 128;         // stages x [128 x 128 B]
+    uint8_t *sO = sA + (size_t)p.stages * C3_TILE * 128;       // [128 x 128 B]
+    float *s_scale = (float *)(sO + (size_t)C3_TILE * 128);
+    float *s_shift = s_scale + C3_NB;
+    float *s_sum = s_shift + C3_NB;
+    float *s_sq = s_sum + C3_NB;
+    uint64_t *bar_b = (uint64_t *)(s_sq + C3_NB);
+    uint64_t *bar_acc = bar_b + 1;
+    uint64_t *full = bar_acc + 1;      // [stages]
+    uint64_t *done = full + 4;         // [stages]
+    uint32_t *s_tmem = (uint32_t *)(done + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = (int)blockIdx.x % p.nnb, n0 = nb * C3_NB;
+    const int nblk = p.N - n0 < C3_NB ? p.N - n0 : C3_NB;
+    const int npb = (nblk + 15) / 16 * 16;
+    const int tiles_img = p.tiles_x * p.tiles_y, total_patches = tiles_img * p.NI;
+    const int patch0 = (int)blockIdx.x / p.nnb, pstride = (int)gridDim.x / p.nnb;
+    const int my_patches = patch0 < total_patches ? (total_patches - 1 - patch0) / pstride + 1 : 0;
+    const uint32_t tmem_cols = npb > 32 ? 64u : 32u;
+    const int S = p.stages;
+
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_acc, 1);
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&done[i], 1);
+        }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < C3_NB; i += C3_THREADS) {
+        s_scale[i] = (p.scale && i < nblk) ? p.scale[n0 + i] : 1.f;
+        s_shift[i] = (p.shift && i < nblk) ? p.shift[n0 + i] : 0.f;
+        s_sum[i] = 0.f;
+        s_sq[i] = 0.f;
+    }
+    if (warp == 0) tmem_alloc(s_tmem, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t idesc = make_idesc_bf16(npb);
+
+    // patch index -> (image, y0, x0)
+    auto patch_origin = [&](int pi, int &n, int &y0, int &x0) {
+        const int t = patch0 + pi * pstride;
+        n = t / tiles_img;
+        const int r = t - n * tiles_img;
+        const int ty = r / p.tiles_x;
+        y0 = ty * p.TH;
+        x0 = (r - ty * p.tiles_x) * p.TW;
+    };
+    const long long total_items = (long long)my_patches * nb_items;
+    long long g_issued = 0;
+    auto issue = [&](long long g) {  // thread 0 only: TMA for pipeline item g = (patch, tap, k block)
+        const int s = (int)(g % S);
+        if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
+        const int pi = (int)(g / nb_items), j = (int)(g % nb_items);
+        const int tap = j / p.nkb, kb = j - tap * p.nkb;
+        int n, y0, x0;
+        patch_origin(pi, n, y0, x0);
+        mbar_expect_tx(&full[s], C3_TILE * 128);
+        tma_load_4d_sw(sA + (size_t)s * C3_TILE * 128, &map_x, &full[s], kb * 64, x0 - p.pad + (tap % 3) * p.dil,
+                       y0 - p.pad + (tap / 3) * p.dil, n);
+    };
+    if (tid == 0 && my_patches > 0) {
+        mbar_expect_tx(bar_b, (uint32_t)(nb_items * C3_NB * 128));
+        for (int j = 0; j < nb_items; ++j) {
+            const int tap = j / p.nkb, kb = j - tap * p.nkb;
+            tma_load_2d(sB + (size_t)j * C3_NB * 128, &map_b, bar_b, kb * 64, tap * p.nr + n0);
+        }
+        while (g_issued < total_items && g_issued < S) issue(g_issued++);
+    }
+
+    for (int pi = 0; pi < my_patches; ++pi) {
+        int n, y0, x0;
+        patch_origin(pi, n, y0, x0);
+        if (tid == 0) {
+            if (pi == 0) mbar_wait(bar_b, 0);
+            for (int j = 0; j < nb_items; ++j) {
+                const long long c = (long long)pi * nb_items + j;
+                if (c >= 1 && g_issued < total_items) issue(g_issued++);  // refill the slot freed one item ago
+                const int s = (int)(c % S);
+                mbar_wait(&full[s], (uint32_t)(c / S) & 1);
+                tc_fence_after();
+                const int kb = j % p.nkb;
+                const int krem = p.K - kb * 64;
+                const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)s * C3_TILE * 128) + ks * 32);
+                    uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)j * C3_NB * 128) + ks * 32);
+                    umma_f16(tmem_base, ad, bd, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&done[s]);
+            }
+            umma_commit(bar_acc);
+        }
+        mbar_wait(bar_acc, (uint32_t)pi & 1);
+        tc_fence_after();
+
+        const int row = warp * 32 + lane;
+        const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+        const bool row_ok = py < p.H && px < p.W;
+#pragma unroll 1
+        for (int c0 = 0; c0 < npb; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+            if (p.stats) {
+                float q[16], q2[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    q[j] = row_ok ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
+                    q2[j] = q[j] * q[j];
+                }
+                int col;
+                float t1 = warp_colsum16(q, lane, col), t2 = warp_colsum16(q2, lane, col);
+                if (!(lane & 1) && c0 + col < nblk) {
+                    atomicAdd(&s_sum[c0 + col], t1);
+                    atomicAdd(&s_sq[c0 + col], t2);
+                }
+            }
+            if (p.out_f32) {
+                if (row_ok) {
+                    float *o = reinterpret_cast<float *>(p.out) + (((size_t)n * p.H + py) * p.W + px) * p.out_cs + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < nblk) o[j] = v[j];
+                }
+            } else {
+                const int ch = c0 >> 3;
+                uint8_t *orow = sO + (size_t)row * 128;
+                uint4 q0, q1;
+                bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    e0[j] = __float2bfloat16_rn(v[j]);
+                    e1[j] = __float2bfloat16_rn(v[8 + j]);
+                }
+                *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
+                *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
+            }
+        }
+        if (!p.out_f32) fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (!p.out_f32 && tid == 0) {
+            tma_store_4d(&map_o, sO, n0, x0, y0, n);
+            tma_store_commit();
+            tma_store_wait_read();
+        }
+        __syncthreads();
+    }
+    if (tid == 0) tma_store_wait_all();
+    if (p.stats) {
+        __syncthreads();
+        for (int c = tid; c < nblk; c += C3_THREADS) {
+            atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
+            atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+struct C3WParams {
+    int NI, H, W;
+    int Ci, Co;          // this launch's channel blocks (<= 64 each)
+    int npb;             // Co rounded to 16
+    int dil, pad;
+    int TH, TW, tiles_x, tiles_y;
+    int tmem_cols;
+    float *dw;           // full weight gradient [Co_total][Ci_total][3][3]
+    int ci_total, co0, ci0;
+};
+
+__global__ void __launch_bounds__(C3_THREADS) c3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                 const __grid_constant__ CUtensorMap map_dz, const C3WParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int S = 2, PAIRS = 5;
+    uint8_t *sX = smem;                              // S x [2 taps x 128 x 128 B]
+    uint8_t *sZ = sX + (size_t)S * 2 * C3_TILE * 128;  // 2 x [128 x 128 B]
+    uint64_t *full = (uint64_t *)(sZ + (size_t)2 * C3_TILE * 128);
+    uint64_t *done = full + S;
+    uint64_t *final_bar = done + S;
+    uint32_t *s_tmem = (uint32_t *)(final_bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_img = p.tiles_x * p.tiles_y, total_patches = tiles_img * p.NI;
+    const int my_patches = (int)blockIdx.x < total_patches ? (total_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&done[i], 1);
+        }
+        mbar_init(final_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (tid == 0 && my_patches > 0) {
+        const uint32_t idesc = make_idesc_bf16(p.npb) | (1u << 15) | (1u << 16);  // A, B MN-major
+        const long long total_items = (long long)my_patches * PAIRS;
+        auto issue = [&](long long g) {
+            const int s = (int)(g % S);
+            if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
+            const int pi = (int)(g / PAIRS), j = (int)(g % PAIRS);
+            const int t = (int)blockIdx.x + pi * (int)gridDim.x;
+            const int n = t / tiles_img, r = t - n * tiles_img, ty = r / p.tiles_x;
+            const int y0 = ty * p.TH, x0 = (r - ty * p.tiles_x) * p.TW;
+            const int ntaps = j == PAIRS - 1 ? 1 : 2;
+            mbar_expect_tx(&full[s], (uint32_t)((ntaps + (j == 0 ? 1 : 0)) * C3_TILE * 128));
+            for (int q = 0; q < ntaps; ++q) {
+                const int tap = 2 * j + q;
+                tma_load_4d_sw(sX + ((size_t)s * 2 + q) * C3_TILE * 128, &map_x, &full[s], 0, x0 - p.pad + (tap % 3) * p.dil,
+                               y0 - p.pad + (tap / 3) * p.dil, n);
+            }
+            if (j == 0) tma_load_4d_sw(sZ + (size_t)(pi & 1) * C3_TILE * 128, &map_dz, &full[s], 0, x0, y0, n);
+        };
+        long long g_issued = 0;
+        while (g_issued < total_items && g_issued < S) issue(g_issued++);
+        for (long long c = 0; c < total_items; ++c) {
+            if (c >= 1 && g_issued < total_items) issue(g_issued++);
+            const int s = (int)(c % S), pi = (int)(c / PAIRS), j = (int)(c % PAIRS);
+            mbar_wait(&full[s], (uint32_t)(c / S) & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sX + (size_t)s * 2 * C3_TILE * 128);
+            const uint32_t b0 = smem_u32(sZ + (size_t)(pi & 1) * C3_TILE * 128);
+#pragma unroll
+            for (int ks = 0; ks < C3_TILE / 16; ++ks) {
+                uint64_t ad = make_desc_mn_sw128(a0 + ks * 2048, C3_TILE * 128);
+                uint64_t bd = make_desc_mn_sw128(b0 + ks * 2048, C3_TILE * 128);
+                umma_f16(tmem_base + (uint32_t)(j * p.npb), ad, bd, idesc, (pi > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(&done[s]);
+        }
+        umma_commit(final_bar);  // completes exactly once, after every MMA of this CTA
+    }
+    if (my_patches > 0) {
+        mbar_wait(final_bar, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const int ci = row & 63, half = row >> 6;
+        for (int j = 0; j < PAIRS; ++j) {
+            const int tap = 2 * j + half;
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.npb; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * p.npb + c0), v);
+                if (tap < 9 && ci < p.Ci) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (c0 + q < p.Co)
+                            atomicAdd(&p.dw[((size_t)(p.co0 + c0 + q) * p.ci_total + (p.ci0 + ci)) * 9 + tap], v[q]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// weight [Co][Ci][3][3] fp32 -> bf16 [9][Nr][Kp]
+//   mode 0 (forward)      : row n = co, col k = ci, tap unchanged
+//   mode 1 (data gradient): row n = ci, col k = co, tap flipped (8 - tap)
+__global__ void pack_conv3_kernel(const float *w, int Co, int Ci, int mode, bf16 *out, int Nr, int Kp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * Nr * Kp) return;
+    int k = i % Kp, t = i / Kp, n = t % Nr, tap = t / Nr;
+    float v = 0.f;
+    if (mode == 0) {
+        if (n < Co && k < Ci) v = w[((size_t)n * Ci + k) * 9 + tap];
+    } else {
+        if (n < Ci && k < Co) v = w[((size_t)k * Ci + n) * 9 + (8 - tap)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+static void pick_patch(int H, int W, int &TH, int &TW) {
+    if (W >= 96) { TH = 1; TW = 128; }
+    else if (W >= 48) { TH = 2; TW = 64; }
+    else if (W >= 24) { TH = 4; TW = 32; }
+    else { TH = 8; TW = 16; }
+    (void)H;
+}
+
+static size_t c3_smem(int nkb, int stages) {
+    return (size_t)9 * nkb * C3_NB * 128 + (size_t)stages * C3_TILE * 128 + (size_t)C3_TILE * 128 + 4 * C3_NB * 4 + 128 + 1024;
+}
+
+}  // namespace nasb
+
+using namespace nasb;
+
+extern "C" long long nasb_pack_conv3_elems(int Co, int Ci, int mode) {
+    int N = mode == 0 ? Co : Ci, K = mode == 0 ? Ci : Co;
+    return 9LL * ((N + 63) / 64 * 64) * ((K + 7) / 8 * 8);
+}
+
+extern "C" int nasb_pack_conv3_bf16(const float *w, int Co, int Ci, int mode, void *out, void *stream) {
+    if (!w || !out || Co <= 0 || Ci <= 0) return NASB_ERR_BAD_ARG;
+    int N = mode == 0 ? Co : Ci, K = mode == 0 ? Ci : Co;
+    int Nr = (N + 63) / 64 * 64, Kp = (K + 7) / 8 * 8;
+    pack_conv3_kernel<<<cdiv(9LL * Nr * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, Co, Ci, mode, (bf16 *)out, Nr, Kp);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// K = channels of x, N = channels of out.  Requires stride 1 and out spatial size == x spatial size (pad == dil).
+extern "C" int nasb_conv3_tc_supported(int K, int N) {
+    if (K < 8 || N < 1 || N > 4096) return 0;
+    int nkb = (K + 63) / 64;
+    return c3_smem(nkb, 2) <= 200 * 1024 ? 1 : 0;
+}
+
+extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, int dil, int pad, const float *scale,
+                                 const float *shift, int act, const NasbTensor *out, double *stats, void *stream) {
+    if (!x || !out || !wpack) return NASB_ERR_BAD_ARG;
+    if (x->dtype != NASB_BF16 || (out->dtype != NASB_BF16 && out->dtype != NASB_F32) || out->c != N) return NASB_ERR_UNSUPPORTED;
+    if (x->n != out->n || x->h != out->h || x->w != out->w || x->h + 2 * pad - 2 * dil != out->h) return NASB_ERR_UNSUPPORTED;
+    // TMA needs a 16-byte aligned base and a 16-byte multiple pixel pitch; the channel COUNT may be anything
+    if (((uintptr_t)x->ptr & 15) || (x->cstride % 8) || !nasb_conv3_tc_supported(x->c, N)) return NASB_ERR_UNSUPPORTED;
+    if (out->dtype == NASB_BF16 && (((uintptr_t)out->ptr & 15) || (out->cstride % 8))) return NASB_ERR_UNSUPPORTED;
+    if (npix(*x) == 0) return 0;
+    C3Params p{};
+    p.NI = x->n;
+    p.H = x->h;
+    p.W = x->w;
+    p.K = x->c;
+    p.N = N;
+    p.nkb = (p.K + 63) / 64;
+    p.nnb = (N + C3_NB - 1) / C3_NB;
+    p.dil = dil;
+    p.pad = pad;
+    pick_patch(p.H, p.W, p.TH, p.TW);
+    p.tiles_x = cdiv(p.W, p.TW);
+    p.tiles_y = cdiv(p.H, p.TH);
+    p.stages = c3_smem(p.nkb, 4) <= 110 * 1024 ? 4 : (c3_smem(p.nkb, 3) <= 200 * 1024 ? 3 : 2);
+    p.nr = (N + 63) / 64 * 64;
+    p.scale = scale;
+    p.shift = shift;
+    p.act = act;
+    p.out = out->ptr;
+    p.out_cs = out->cstride;
+    p.out_f32 = out->dtype == NASB_F32 ? 1 : 0;
+    p.stats = stats;
+    int Kp = (p.K + 7) / 8 * 8;
+    CUtensorMap mx, mb, mo;
+    if (!tc_make_map4(&mx, x, p.TW, p.TH)) return NASB_ERR_UNSUPPORTED;
+    if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)9 * p.nr, (uint64_t)Kp, C3_NB)) return NASB_ERR_UNSUPPORTED;
+    if (p.out_f32) {
+        mo = mx;  // unused
+    } else if (!tc_make_map4(&mo, out, p.TW, p.TH)) {
+        return NASB_ERR_UNSUPPORTED;
+    }
+    size_t smem = c3_smem(p.nkb, p.stages);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(c3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048) != cudaSuccess)
+            return NASB_ERR_UNSUPPORTED;
+        configured = true;
+    }
+    long long total = (long long)p.tiles_x * p.tiles_y * p.NI;
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;
+    if (grid < p.nnb) grid = p.nnb;
+    if (grid > total * p.nnb) grid = total * p.nnb;
+    c3_tc_kernel<<<(int)grid, C3_THREADS, smem, (cudaStream_t)stream>>>(mx, mb, mo, p);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// dweight[co][ci][tap] += sum_pixels dz[., co] * x[. + offset(tap), ci]   (fp32 [C_out][C_in][3][3])
+extern "C" int nasb_conv3_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, int dil, int pad, float *dweight, void *stream) {
+    if (!x || !dz || !dweight) return NASB_ERR_BAD_ARG;
+    if (x->dtype != NASB_BF16 || dz->dtype != NASB_BF16) return NASB_ERR_UNSUPPORTED;
+    if (x->n != dz->n || x->h != dz->h || x->w != dz->w) return NASB_ERR_UNSUPPORTED;
+    if (((uintptr_t)x->ptr & 15) || (x->cstride % 8) || ((uintptr_t)dz->ptr & 15) || (dz->cstride % 8)) return NASB_ERR_UNSUPPORTED;
+    if (npix(*x) == 0) return 0;
+    C3WParams p{};
+    p.NI = x->n;
+    p.H = x->h;
+    p.W = x->w;
+    p.dil = dil;
+    p.pad = pad;
+    pick_patch(p.H, p.W, p.TH, p.TW);
+    p.tiles_x = cdiv(p.W, p.TW);
+    p.tiles_y = cdiv(p.H, p.TH);
+    p.dw = dweight;
+    p.ci_total = x->c;
+    size_t smem = (size_t)2 * 2 * C3_TILE * 128 + (size_t)2 * C3_TILE * 128 + 128 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(c3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048) != cudaSuccess)
+            return NASB_ERR_UNSUPPORTED;
+        configured = true;
+    }
+    long long total = (long long)p.tiles_x * p.tiles_y * p.NI;
+    for (int co0 = 0; co0 < dz->c; co0 += 64) {
+        for (int ci0 = 0; ci0 < x->c; ci0 += 64) {
+            NasbTensor xs = *x, zs = *dz;
+            xs.ptr = (bf16 *)x->ptr + ci0;
+            xs.c = x->c - ci0 < 64 ? x->c - ci0 : 64;
+            zs.ptr = (bf16 *)dz->ptr + co0;
+            zs.c = dz->c - co0 < 64 ? dz->c - co0 : 64;
+            if (((uintptr_t)xs.ptr & 15) || ((uintptr_t)zs.ptr & 15)) return NASB_ERR_UNSUPPORTED;
+            p.Ci = xs.c;
+            p.Co = zs.c;
+            p.npb = (p.Co + 15) / 16 * 16;
+            int cols = 32;
+            while (cols < 5 * p.npb) cols <<= 1;
+            p.tmem_cols = cols;
+            p.co0 = co0;
+            p.ci0 = ci0;
+            CUtensorMap mx, mz;
+            if (!tc_make_map4(&mx, &xs, p.TW, p.TH) || !tc_make_map4(&mz, &zs, p.TW, p.TH)) return NASB_ERR_UNSUPPORTED;
+            int per_sm = 512 / cols;
+            if (per_sm > 2) per_sm = 2;
+            long long grid = (long long)NASB_SM_COUNT * per_sm;
+            if (grid > total) grid = total;
+            c3_wgrad_tc_kernel<<<(int)grid, C3_THREADS, smem, (cudaStream_t)stream>>>(mx, mz, p);
+            NASB_CHECK_LAUNCH();
+        }
+    }
+    return 0;
+}

@@ -54,6 +54,35 @@ def _tc_wgrad_ok(x, dz, cout):
     return bool(lib.load().nasb_pw_tc_wgrad_supported(int(cout), int(x.shape[1])))
 
 
+def _c3_ok(x, cin, cout, ks, stride, dil, pad):
+    """3x3 implicit GEMM on the tensor cores: bf16 input with a 16-byte pixel pitch, stride 1, 'same' geometry."""
+    from . import config
+    if not config().use_tcgen05 or ks != 3 or stride != 1 or pad != dil or x.dtype != torch.bfloat16:
+        return False
+    if x.data_ptr() % 16 or lib.desc(x).cstride % 8:
+        return False
+    return bool(lib.load().nasb_conv3_tc_supported(int(cin), int(cout)))
+
+
+def _pack_conv3(weight, mode):
+    cout, cin = weight.shape[0], weight.shape[1]
+    n = int(lib.load().nasb_pack_conv3_elems(cout, cin, mode))
+    wp = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
+    call("nasb_pack_conv3_bf16", ptr(weight), cout, cin, mode, ptr(wp))
+    return wp
+
+
+def _bf16_padded_copy(t):
+    """fp32 / bf16 NHWC tensor -> bf16 copy whose pixel pitch is a multiple of 8 elements (TMA needs a 16-byte pitch; the
+    channel count itself may be odd, e.g. the 19 / 21 logit channels)."""
+    n, c, h, w = t.shape
+    pitch = (c + 7) // 8 * 8
+    buf = torch.empty((n, h, w, pitch), dtype=torch.bfloat16, device=t.device)
+    view = buf[..., :c].permute(0, 3, 1, 2)
+    call("nasb_scale_copy", ref(desc(t)), None, 0, ref(desc(view)))
+    return view
+
+
 def _pack_weight(weight, transpose):
     """fp32 [C_out, C_in, 1, 1] -> bf16 [R][Kp] operand of the tensor-core kernel (a few KB; repacked per call because the
     optimiser rewrites the fp32 master weights every step)."""
@@ -89,8 +118,15 @@ class _ConvUnit(torch.autograd.Function):
         use_tc = (not dw and ks == 1 and stride == 1 and pad == 0 and x1 is None and not in_relu and not image
                   and _tc_ok(x0, x0.shape[1], cout, out_dtype))
         wpack = _pack_weight(weight, False) if use_tc else None
+        use_c3 = (not dw and x1 is None and not in_relu and not image and res is None
+                  and out_dtype in (torch.bfloat16, torch.float32) and _c3_ok(x0, x0.shape[1], cout, ks, stride, dil, pad))
+        wpack3 = _pack_conv3(weight, 0) if use_c3 else None
 
         def run_conv(out, scale, shift, a, r, stats=None):
+            if use_c3:
+                call("nasb_conv3_tc_fwd", ref(dx0), ptr(wpack3), cout, dil, pad, ptr(scale), ptr(shift), a, ref(desc(out)),
+                     ptr(stats))
+                return
             if use_tc:
                 call("nasb_pw_tc_fwd", ref(dx0), ptr(wpack), cout, ptr(scale), ptr(shift), a,
                      ref(desc(r)) if r is not None else None, ref(desc(out)), ptr(stats))
@@ -131,7 +167,7 @@ class _ConvUnit(torch.autograd.Function):
             ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
             sv = torch.empty((2, cout), dtype=torch.float32, device=dev)
             mom = 0.1 if bn.momentum is None else float(bn.momentum)
-            if use_tc:  # batch statistics are accumulated by the GEMM epilogue
+            if use_tc or use_c3:  # batch statistics are accumulated by the GEMM epilogue
                 sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
                 run_conv(z, None, None, ACT_NONE, None, sums)
                 call("nasb_bn_finalize", ptr(sums), C.c_longlong(n * oh * ow), cout, ptr(gamma), ptr(beta), float(bn.eps),
@@ -181,8 +217,15 @@ class _ConvUnit(torch.autograd.Function):
             dbias = torch.zeros(cout, dtype=torch.float32, device=dev)
             call("nasb_channel_sum", ref(desc(dz)), ptr(dbias), None)
         dweight = None
+        c3 = (not dw and not has_x1 and not in_relu and not image
+              and _c3_ok(x0, x0.shape[1], cout, ks, stride, dil, pad))
+        if c3 and (dz.dtype != torch.bfloat16 or dz.data_ptr() % 16 or desc(dz).cstride % 8):
+            dz = _bf16_padded_copy(dz)  # e.g. fp32 logit gradients with 19 channels
         ddz = desc(dz)
-        if need[2]:
+        if need[2] and c3:
+            dweight = torch.zeros_like(weight, dtype=torch.float32)
+            call("nasb_conv3_tc_wgrad", ref(desc(x0)), ref(ddz), dil, pad, ptr(dweight))
+        elif need[2]:
             dweight = torch.zeros_like(weight, dtype=torch.float32)
             if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image and not in_relu
                     and _tc_wgrad_ok(x0, dz, cout)):
@@ -203,7 +246,10 @@ class _ConvUnit(torch.autograd.Function):
             dx0 = lib.new_act(*x0.shape, x0.dtype, dev)
             if has_x1:
                 dx1 = lib.new_act(*x1.shape, x1.dtype, dev)
-            if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image
+            if c3:
+                call("nasb_conv3_tc_fwd", ref(ddz), ptr(_pack_conv3(weight, 1)), x0.shape[1], dil, 2 * dil - pad, None, None,
+                     ACT_NONE, ref(desc(dx0)), None)
+            elif (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image
                     and _tc_ok(dz, cout, x0.shape[1], x0.dtype)):
                 call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
                      ref(desc(dx0)), None)

@@ -28,6 +28,11 @@ _SIG = {
     "nasb_conv_fwd": [_TP, _TP, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _TP, _TP, _P],
     "nasb_conv_dgrad": [_TP, _P, _I, _I, _I, _I, _TP, _TP, _P],
     "nasb_conv_wgrad": [_TP, _TP, _P, _P, _I, _TP, _I, _I, _I, _I, _P, _P],
+    "nasb_pack_conv3_elems": [_I, _I, _I],
+    "nasb_pack_conv3_bf16": [_P, _I, _I, _I, _P, _P],
+    "nasb_conv3_tc_supported": [_I, _I],
+    "nasb_conv3_tc_fwd": [_TP, _P, _I, _I, _I, _P, _P, _I, _TP, _P, _P],
+    "nasb_conv3_tc_wgrad": [_TP, _TP, _I, _I, _P, _P],
     "nasb_stem_fwd": [_TP, _P, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
     "nasb_stem_wgrad": [_TP, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_pack_weight_bf16": [_P, _I, _I, _I, _P, _P],
@@ -72,7 +77,7 @@ _SIG = {
     "nasb_sumsq": [_P, _L, _P, _P],
     "nasb_version": [],
 }
-_RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L}
+_RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L}
 EXPORTS = tuple(sorted(_SIG))
 
 _lib = None

@@ -137,7 +137,7 @@ def test_network_train_step(golden, tag):
     # the real reference's fixture gradients (fp32) must sit in the same error band around fp64
     for k in [k for k in fx.files if k.startswith("grad/")]:
         g64 = sd64[k[5:]].grad.numpy()
-        assert rel_err(_np(named[k[5:]].grad), g64) <= max(2e-2, 3.0 * rel_err(fx[k], g64)), k
+        assert rel_err(_np(named[k[5:]].grad), g64) <= max(5e-2, 3.0 * rel_err(fx[k], g64)), k
 
 
 @pytest.mark.parametrize("tag", ["W0", "C0search"])
