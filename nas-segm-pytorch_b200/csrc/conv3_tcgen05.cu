@@ -360,7 +360,7 @@ extern "C" int nasb_pack_conv3_bf16(const float *w, int Co, int Ci, int mode, vo
 
 // K = channels of x, N = channels of out.  Requires stride 1 and out spatial size == x spatial size (pad == dil).
 extern "C" int nasb_conv3_tc_supported(int K, int N) {
-    if (K < 8 || N < 1 || N > 4096) return 0;
+    if (K < 1 || N < 1 || N > 4096) return 0;
     int nkb = (K + 63) / 64;
     return c3_smem(nkb, 2) <= 200 * 1024 ? 1 : 0;
 }
