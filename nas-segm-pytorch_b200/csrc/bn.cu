@@ -71,51 +71,87 @@ __global__ void __launch_bounds__(256) bn_sums_vec_kernel(const T *z, int cs, lo
     });
 }
 
-// training: g = dy*act'(act(z*scale+shift)), xhat = (z-mean)*rstd ; eval: g = dy*act'(y), xhat = (y-beta)/gamma
+// training: g = dy*act'(z*scale+shift), xhat = (z-mean)*rstd ; eval: g = dy*act'(y), xhat = (y-beta)/gamma
+// Two pixels per iteration are in flight per thread (4 x 16-byte loads) and three CTAs (768 threads) are resident per SM: the pass is a pure HBM stream.
+__device__ __forceinline__ float pre_mask(float y_pre, int act) {
+    if (act == NASB_ACT_RELU) return y_pre > 0.f ? 1.f : 0.f;
+    if (act == NASB_ACT_RELU6) return (y_pre > 0.f && y_pre < 6.f) ? 1.f : 0.f;
+    return 1.f;
+}
+
 template <typename T, int V>
-__global__ void __launch_bounds__(256) bn_bwd_sums_vec_kernel(const T *dy, int dy_cs, const T *yz, int yz_cs, int training,
-                                                              const float *scale, const float *shift, const float *mean,
-                                                              const float *rstd, const float *gamma, const float *beta,
-                                                              int act, long long P, int C, double *ws,
-                                                              long long rows_per_cta) {
+__global__ void __launch_bounds__(256, 3) bn_bwd_sums_vec_kernel(const T *dy, int dy_cs, const T *yz, int yz_cs, int training,
+                                                                 const float *scale, const float *shift, const float *mean,
+                                                                 const float *rstd, const float *gamma, const float *beta,
+                                                                 int act, long long P, int C, double *ws,
+                                                                 long long rows_per_cta) {
+    extern __shared__ float red_sm[];  // [2][PL][C]
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
-    // this thread's channel vector is fixed: keep its per-channel constants in registers
-    const int my_c0 = (threadIdx.x % (C / V)) * V;
+    const int CV = C / V, PL = blockDim.x / CV;
+    const int t = threadIdx.x, cv = t % CV, pl = t / CV, c0 = cv * V;
+    // per-channel constants of this thread's fixed channel vector: mask from y_pre = v*k_s + k_b, xhat = (v - k_mu)*k_rs
     float k_s[V], k_b[V], k_mu[V], k_rs[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        const int c = my_c0 + j;
+        const int c = c0 + j;
         if (training) {
             k_s[j] = scale[c];
             k_b[j] = shift[c];
             k_mu[j] = mean[c];
             k_rs[j] = rstd[c];
-        } else {  // eval: xhat = (y - beta) / gamma  ->  (y - k_mu) * k_rs
+        } else {  // eval: the mask is taken on y itself (identity pre-map), xhat = (y - beta) / gamma
             float ga = gamma ? gamma[c] : 1.f;
-            k_s[j] = k_b[j] = 0.f;
+            k_s[j] = 1.f;
+            k_b[j] = 0.f;
             k_mu[j] = beta ? beta[c] : 0.f;
             k_rs[j] = ga != 0.f ? 1.f / ga : 0.f;
         }
     }
-    colreduce2<V>(r0, r1, C, ws, [&](long long m, int c0, float (&a)[V], float (&b)[V]) {
-        float g[V], v[V];
-        load_vec<T, V>(dy + m * dy_cs + c0, g);
-        load_vec<T, V>(yz + m * yz_cs + c0, v);
+    float a[V], b[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = b[j] = 0.f;
+    if (pl < PL) {
+        for (long long m = r0 + pl; m < r1; m += 2 * PL) {
+            const long long m1 = m + PL;
+            const bool two = m1 < r1;
+            float g0[V], v0[V], g1[V], v1[V];
+            load_vec<T, V>(dy + m * dy_cs + c0, g0);
+            load_vec<T, V>(yz + m * yz_cs + c0, v0);
+            if (two) {
+                load_vec<T, V>(dy + m1 * dy_cs + c0, g1);
+                load_vec<T, V>(yz + m1 * yz_cs + c0, v1);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float gm = g0[j] * pre_mask(v0[j] * k_s[j] + k_b[j], act);
+                a[j] += gm;
+                b[j] = fmaf(gm, (v0[j] - k_mu[j]) * k_rs[j], b[j]);
+            }
+            if (two) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float gm = g1[j] * pre_mask(v1[j] * k_s[j] + k_b[j], act);
+                    a[j] += gm;
+                    b[j] = fmaf(gm, (v1[j] - k_mu[j]) * k_rs[j], b[j]);
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            float yy, xh;
-            if (training) {
-                yy = apply_act(v[j] * k_s[j] + k_b[j], act);
-                xh = (v[j] - k_mu[j]) * k_rs[j];
-            } else {
-                yy = v[j];
-                xh = (yy - k_mu[j]) * k_rs[j];
-            }
-            float gm = g[j] * act_mask(yy, act);
-            a[j] += gm;
-            b[j] = fmaf(gm, xh, b[j]);
+            red_sm[(size_t)pl * C + c0 + j] = a[j];
+            red_sm[(size_t)(PL + pl) * C + c0 + j] = b[j];
         }
-    });
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < PL; ++i) {
+            s1 += (double)red_sm[(size_t)i * C + c];
+            s2 += (double)red_sm[(size_t)(PL + i) * C + c];
+        }
+        atomicAdd(&ws[c], s1);
+        atomicAdd(&ws[C + c], s2);
+    }
 }
 
 // scalar fallbacks (channel counts / pitches that are not 16-byte addressable)
@@ -280,7 +316,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, 
 // Element-wise passes with a FIXED channel vector per thread: thread t owns channel vector cv = t % CV for its whole
 // life, so the per-channel constants live in registers and the inner loop is 16-byte loads / stores only.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) affine_act_fixed_kernel(const T *z, int z_cs, const float *scale, const float *shift,
+__global__ void __launch_bounds__(256, 4) affine_act_fixed_kernel(const T *z, int z_cs, const float *scale, const float *shift,
                                                                int act, T *y, int y_cs, long long P, int C) {
     const int CV = C / V, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * V;
@@ -309,40 +345,55 @@ __global__ void __launch_bounds__(256) affine_act_fixed_kernel(const T *z, int z
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256) bn_bwd_dz_fixed_kernel(const T *dy, int dy_cs, const T *yz, int yz_cs, int training,
-                                                              const float *scale, const float *shift, const float *mean,
-                                                              const float *rstd, const float *coef, int act, T *dz, int dz_cs,
-                                                              long long P, int C) {
+__global__ void __launch_bounds__(256, 3) bn_bwd_dz_fixed_kernel(const T *dy, int dy_cs, const T *yz, int yz_cs, int training,
+                                                                 const float *scale, const float *shift, const float *mean,
+                                                                 const float *rstd, const float *coef, int act, T *dz, int dz_cs,
+                                                                 long long P, int C) {
     const int CV = C / V, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * V;
     if (pl >= PL) return;
-    float s[V], b[V], mu[V], rs[V], k1[V], k2[V];
+    // training: dz = s*(g*mask - k1 - xhat*k2) = (s*mask)*g + A*z + B  with A = -s*k2*rstd, B = s*(k2*rstd*mean - k1);
+    //           mask from y_pre = z*s + b.   eval: dz = s*g*mask(y)  (A = B = 0, y_pre = y)
+    float s[V], b[V], A[V], B[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        s[j] = scale ? scale[c0 + j] : 1.f;
-        b[j] = (training && shift) ? shift[c0 + j] : 0.f;
-        mu[j] = training ? mean[c0 + j] : 0.f;
-        rs[j] = training ? rstd[c0 + j] : 0.f;
-        k1[j] = training ? coef[c0 + j] : 0.f;
-        k2[j] = training ? coef[C + c0 + j] : 0.f;
+        const int c = c0 + j;
+        s[j] = scale ? scale[c] : 1.f;
+        if (training) {
+            const float k1 = coef[c], k2 = coef[C + c], rs = rstd[c];
+            b[j] = shift[c];
+            A[j] = -s[j] * k2 * rs;
+            B[j] = s[j] * (k2 * rs * mean[c] - k1);
+        } else {
+            b[j] = 0.f;
+            A[j] = B[j] = 0.f;
+        }
     }
     const long long G = (long long)gridDim.x * PL;
-    for (long long m = (long long)blockIdx.x * PL + pl; m < P; m += G) {
-        float g[V], v[V];
-        load_vec<T, V>(dy + m * dy_cs + c0, g);
-        load_vec<T, V>(yz + m * yz_cs + c0, v);
+    for (long long m = (long long)blockIdx.x * PL + pl; m < P; m += 2 * G) {
+        const long long m1 = m + G;
+        const bool two = m1 < P;
+        float g0[V], v0[V], g1[V], v1[V];
+        load_vec<T, V>(dy + m * dy_cs + c0, g0);
+        load_vec<T, V>(yz + m * yz_cs + c0, v0);
+        if (two) {
+            load_vec<T, V>(dy + m1 * dy_cs + c0, g1);
+            load_vec<T, V>(yz + m1 * yz_cs + c0, v1);
+        }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            if (training) {
-                float yy = apply_act(v[j] * s[j] + b[j], act);
-                float gm = g[j] * act_mask(yy, act);
-                float xh = (v[j] - mu[j]) * rs[j];
-                g[j] = s[j] * (gm - k1[j] - xh * k2[j]);
-            } else {
-                g[j] = s[j] * g[j] * act_mask(v[j], act);
-            }
+            const float ypre = training ? v0[j] * s[j] + b[j] : v0[j];
+            g0[j] = s[j] * pre_mask(ypre, act) * g0[j] + (A[j] * v0[j] + B[j]);
         }
-        store_vec<T, V>(dz + m * dz_cs + c0, g);
+        store_vec<T, V>(dz + m * dz_cs + c0, g0);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float ypre = training ? v1[j] * s[j] + b[j] : v1[j];
+                g1[j] = s[j] * pre_mask(ypre, act) * g1[j] + (A[j] * v1[j] + B[j]);
+            }
+            store_vec<T, V>(dz + m1 * dz_cs + c0, g1);
+        }
     }
 }
 
