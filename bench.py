@@ -53,6 +53,7 @@ def args_():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="replay the training iteration as one CUDA graph (default on)")
     ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of one instrumented step")
     return ap.parse_args()
 
@@ -228,7 +229,8 @@ def workload_config(a):
     return {"workload": "WACV arch0 (mbv2 2-tap encoder + TemplateDecoder agg64 rep2, %d classes) training iteration "
                         "fwd+CE+bwd+clip+SGD/Adam, BN train mode, batch %d @%dx%d" % (NUM_CLASSES, a.batch, a.width, a.height),
             "global_batch_per_gpu": a.batch, "resolution": [a.width, a.height], "l2": "inputs_exceed_L2",
-            "parallelism": "one candidate per GPU (replicas), 1 all-gather of 16 B per step"}
+            "parallelism": "one candidate per GPU (replicas), 1 all-gather of 16 B per step",
+            "cuda_graph": bool(getattr(a, "cuda_graph", 0))}
 
 
 # ------------------------------------------------------------------------------------------------------------ CUDA arm
@@ -293,8 +295,19 @@ def main():
     rec = torch.zeros(4, dtype=torch.float32, device=dev)
     gathered = torch.zeros(4 * world, dtype=torch.float32, device=dev) if dist else None
 
+    nas_segm_b200.config().cuda_graphs = bool(a.cuda_graph)
+    if a.cuda_graph:
+        from nas_segm_b200.graphs import StepGraph, make_capturable
+        make_capturable(optim_enc)
+        make_capturable(optim_dec)
+        graphed = StepGraph(lambda im, tg: trainer.segmenter_step(seg, im, tg, optim_enc, optim_dec, crit, 3.0, 3.0, False),
+                            [img_d, lab_d])
+
     def step():
-        loss = trainer.segmenter_step(seg, img_d, lab_d, optim_enc, optim_dec, crit, 3.0, 3.0, False)
+        if a.cuda_graph:
+            loss = graphed(img_d, lab_d)
+        else:
+            loss = trainer.segmenter_step(seg, img_d, lab_d, optim_enc, optim_dec, crit, 3.0, 3.0, False)
         if dist:
             rec[0] = loss.detach()
             td.all_gather_into_tensor(gathered, rec)
@@ -305,7 +318,7 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
+    for _ in range(max(a.warmup, 3) + (2 if a.cuda_graph else 0)):  # graph mode: 3 eager iterations, then capture + replays
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -330,7 +343,7 @@ def main():
     # ---- end to end through the engine API: pinned host batches in, loss read back every iteration
     pinned = [{"image": img_h.clone().pin_memory(), "mask": lab_h.clone().pin_memory()} for _ in range(2)]
     loader = HostLoader(pinned[i % 2] for i in range(a.steps))
-    warm = HostLoader(pinned[i % 2] for i in range(2))
+    warm = HostLoader(pinned[i % 2] for i in range(2 + (4 if a.cuda_graph else 0)))
     trainer.train_segmenter(seg, warm, optim_enc, optim_dec, 0, crit, False, 3.0, 3.0, False, print_every=1)
     barrier()
     e0.record()

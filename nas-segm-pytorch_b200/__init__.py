@@ -22,6 +22,8 @@ class _Config:
         import torch
         self.act_dtype = torch.float32
         self.use_tcgen05 = True  # bf16 pointwise convolutions on the tensor cores when shapes allow
+        self.graph_warmup = 3  # eager iterations before an engine loop captures its CUDA graph
+        self.cuda_graphs = False  # engine loops replay one captured CUDA graph per iteration (graphs.StepGraph)
         self.use_tma_tiles = True  # bf16 depthwise convolutions on TMA-staged shared-memory tiles when shapes allow
 
 

@@ -21,7 +21,9 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import config as _config
 from .. import functional as Fn
+from ..graphs import StepGraph, make_capturable
 from ..helpers.utils import try_except
 
 logger = logging.getLogger(__name__)
@@ -114,8 +116,8 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
     out_size = tuple(Xy_train["out_size"])
     loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
     start = time.time()
-    for i in range(n_passes):
-        idx = torch.from_numpy(indices[i * batch_size:(i + 1) * batch_size]).to(dev)
+
+    def iteration(idx):
         encoder_outputs = [_gather(Xy_train[k], idx) for k in feat_keys]
         y = _gather(Xy_train["y"], idx)
         output = decoder(encoder_outputs)
@@ -133,10 +135,26 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
         loss.backward()
         nn.utils.clip_grad_norm_(decoder.parameters(), dec_grad_clip)
         optim_dec.step()
-        loss_sum += loss.detach()
         if do_polyak:
             for p, avg_p in zip(decoder.parameters(), avg_param):
                 avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+        return loss
+
+    step = iteration
+    if _config().cuda_graphs:
+        make_capturable(optim_dec)
+        sg = getattr(decoder, "_nasb_task0_graph", None)
+        key = (id(optim_dec), id(Xy_train), id(avg_param), batch_size, bool(do_kd), float(kd_coeff), float(aux_weight),
+               bool(do_polyak), float(polyak_decay), bool(freeze_bn), float(dec_grad_clip))
+        if sg is None or sg.key != key:
+            sg = StepGraph(iteration, [torch.zeros(batch_size, dtype=torch.int64, device=dev)])
+            sg.key = key
+            decoder._nasb_task0_graph = sg
+        step = sg
+    for i in range(n_passes):
+        idx = torch.from_numpy(indices[i * batch_size:(i + 1) * batch_size]).to(dev, non_blocking=True)
+        loss = step(idx)
+        loss_sum += loss.detach()
     avg_loss = float(loss_sum.item()) / max(n_passes, 1)
     logger.info(" Train epoch: {}\tAvg. Loss: {:.3f}\tAvg. Time: {:.3f}".format(
         epoch, avg_loss, (time.time() - start) / max(n_passes, 1)))
@@ -181,11 +199,25 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
             if isinstance(m, nn.BatchNorm2d):
                 m.eval()
     loss_sum, n_it, start = None, 0, time.time()
+    use_graph = _config().cuda_graphs
+    if use_graph:
+        make_capturable(optim_enc)
+        make_capturable(optim_dec)
     for i, sample in enumerate(train_loader):
         image = sample["image"].float().cuda(non_blocking=True)
         target = sample["mask"].cuda(non_blocking=True)
-        loss = segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
-                              do_polyak, aux_weight, avg_param, polyak_decay)
+        if use_graph:
+            sg = getattr(segmenter, "_nasb_step_graph", None)
+            if sg is None or sg.key != (id(optim_enc), id(optim_dec)) or not sg.matches((image, target)):
+                sg = StepGraph(lambda im, tg: segmenter_step(segmenter, im, tg, optim_enc, optim_dec, segm_crit, enc_grad_clip,
+                                                             dec_grad_clip, do_polyak, aux_weight, avg_param, polyak_decay),
+                               [torch.empty_like(image), torch.empty_like(target)])
+                sg.key = (id(optim_enc), id(optim_dec))
+                segmenter._nasb_step_graph = sg
+            loss = sg(image, target)
+        else:
+            loss = segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
+                                  do_polyak, aux_weight, avg_param, polyak_decay)
         loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
         n_it += 1
         if i % print_every == 0:

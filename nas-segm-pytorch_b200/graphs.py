@@ -31,3 +31,65 @@ class GraphedForward:
         self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+def make_capturable(optim):
+    """Put a torch optimiser into graph-capturable form (Adam/AdamW keep their step counters on the device)."""
+    if optim is None:
+        return
+    for g in optim.param_groups:
+        if "capturable" in g:
+            g["capturable"] = True
+    for st in optim.state.values():
+        if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
+            p = next(iter(optim.param_groups[0]["params"]))
+            st["step"] = st["step"].to(p.device)
+
+
+class StepGraph:
+    """A whole training iteration (forward, loss, backward, gradient clipping, optimiser steps, Polyak) as one CUDA graph.
+
+    ``fn(*static_inputs) -> loss`` must read only from the static input tensors.  The first ``warmup`` calls run eagerly
+    (they are real iterations on the caller's data; they also initialise optimiser state and per-kernel attributes), the
+    next call captures the iteration and replays it, later calls copy the inputs and replay.  At the NAS-loop sizes
+    (64x64 cached features, ~1300 launches per iteration) the host cannot issue launches as fast as the GPU retires
+    them; a replayed graph removes that bound."""
+
+    def __init__(self, fn, static_inputs, warmup=None):
+        from . import config
+        warmup = config().graph_warmup if warmup is None else warmup
+        self.fn, self.static_inputs, self.warmup = fn, list(static_inputs), warmup
+        self.calls, self.graph, self.static_loss = 0, None, None
+        self.launches_per_replay = 0
+        self.side = torch.cuda.Stream()
+
+    def matches(self, inputs):
+        return len(inputs) == len(self.static_inputs) and all(
+            tuple(a.shape) == tuple(b.shape) and a.dtype == b.dtype for a, b in zip(inputs, self.static_inputs))
+
+    def __call__(self, *inputs):
+        from . import lib
+        for dst, src in zip(self.static_inputs, inputs):
+            if dst is not src:
+                dst.copy_(src, non_blocking=True)
+        self.calls += 1
+        if self.graph is not None:
+            self.graph.replay()
+            lib.launches += self.launches_per_replay
+            return self.static_loss
+        if self.calls <= self.warmup:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                loss = self.fn(*self.static_inputs)
+            torch.cuda.current_stream().wait_stream(self.side)
+            return loss.detach()
+        torch.cuda.synchronize()
+        l0 = lib.launches
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self.fn(*self.static_inputs).detach()
+        self.launches_per_replay = lib.launches - l0
+        lib.launches = l0  # capture launched nothing
+        self.graph.replay()
+        lib.launches += self.launches_per_replay
+        return self.static_loss

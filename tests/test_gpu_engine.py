@@ -24,8 +24,12 @@ class Seg(nn.Module):
         return self.decoder(self.encoder(x))
 
 
-def test_train_task0_matches_reference_trajectory(golden):
+@pytest.mark.parametrize("graphs", [False, True])
+def test_train_task0_matches_reference_trajectory(golden, graphs):
+    """graphs=True: the same trajectory with every iteration after the first replayed from one captured CUDA graph."""
     from nas_segm_b200.engine import trainer
+    nas_segm_b200.config().cuda_graphs = graphs
+    nas_segm_b200.config().graph_warmup = 1
     from nas_segm_b200.nn.encoders import mbv2
     from nas_segm_b200.nn.micro_decoders import MicroDecoder
     nas_segm_b200.set_act_dtype(torch.float32)
@@ -56,6 +60,10 @@ def test_train_task0_matches_reference_trajectory(golden):
             assert r is None
     finally:
         trainer.logger.info = orig
+        nas_segm_b200.config().cuda_graphs = False
+        nas_segm_b200.config().graph_warmup = 3
+    if graphs:
+        assert dec._nasb_task0_graph.graph is not None and dec._nasb_task0_graph.calls == 4
     assert np.allclose(losses, fx["logged_avg_loss"], atol=2e-3), (losses, fx["logged_avg_loss"])
     sd = dec.state_dict()
     tot = ok = 0
