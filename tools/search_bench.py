@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--cuda-graph", type=int, default=1)
     ap.add_argument("--epochs", type=int, default=5)
+    ap.add_argument("--profile-out", default=None)
     a = ap.parse_args()
     rank, world, dev = parallel.init()
     nas_segm_b200.set_act_dtype(torch.bfloat16 if a.dtype == "bf16" else torch.float32)
@@ -114,6 +115,27 @@ def main():
         t_val = time.time() - t0
         times.append((t_train, t_val))
         recs.append([float(reward), 0.0, 0.0, 0.0])
+    if a.profile_out and rank == 0:  # per-call CUDA events of ONE eager task0 epoch of the last candidate
+        from nas_segm_b200 import lib
+        nas_segm_b200.config().cuda_graphs = False
+        small = {k: (v[:64] if k != "out_size" else v) for k, v in Xy.items()}
+        lib.profile_begin()
+        trainer.train_task0(small, seg, optim_dec, 0, crit, kd_crit, 64, False, True, 0.3, 3.0, True, avg_param=avg,
+                            polyak_decay=0.9, aux_weight=0.15)
+        prof = lib.profile_end()
+        by = {}
+        for k, (c, t_ms, b) in prof.items():
+            e = by.setdefault(k.split("[")[0], [0, 0.0])
+            e[0] += c
+            e[1] += t_ms
+        with open(a.profile_out, "w") as f:
+            f.write("# one task0 iteration (batch 64, 64x64 features), eager, CUDA events per C-ABI call: total %.3f ms, %d calls\n" % (
+                sum(v[1] for v in by.values()), sum(v[0] for v in by.values())))
+            for k, (c, t_ms) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+                f.write("%9.3f ms %5d calls %7.1f us/call  %s\n" % (t_ms, c, 1e3 * t_ms / c, k))
+            f.write("# top individual calls\n")
+            for k, (c, t_ms, b) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:40]:
+                f.write("%9.3f ms %4d x %8.4f ms %8.1f GB/s  %s\n" % (t_ms, c, t_ms / c, b / (t_ms / c * 1e-3) / 1e9, k))
     table = parallel.gather_records(recs, dev)  # the single collective
     iters = a.epochs * (a.n_task0 // 64)
     # the first candidate pays the one-off kernel-attribute / graph-capture warm-up; report the steady state
