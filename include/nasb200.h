@@ -141,6 +141,8 @@ int nasb_dwconv_wgrad(const NasbTensor *x, int in_relu, const NasbTensor *dz, in
  * the host then uses the gather kernels above. */
 int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
                      const float *out_scale, const float *out_shift, int act, const NasbTensor *out, void *stream);
+int nasb_dwconv_dgrad_strided_tile(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
+                                   const NasbTensor *dx, void *stream);
 int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz, int ks, int stride, int dil, int pad,
                            float *dweight, void *stream);
 

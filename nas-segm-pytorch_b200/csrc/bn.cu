@@ -401,7 +401,7 @@ static inline bool fixed_cfg(int C, int V, long long P, int &blocks) {
     if (C % V || C / V > 256 || C / V < 1) return false;
     int PL = 256 / (C / V);
     long long b = (P + (long long)PL * 4 - 1) / ((long long)PL * 4);  // >= 4 pixels per thread
-    long long cap = (long long)NASB_SM_COUNT * 16;
+    long long cap = (long long)NASB_SM_COUNT * 12;  // whole waves for 3 or 4 resident CTAs per SM
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     blocks = (int)b;
@@ -422,7 +422,7 @@ template <int V>
 static inline bool vec_reduce_cfg(int C, long long P, int &blocks, long long &rows, size_t &smem) {
     if (C % V || C / V > 256 || C / V < 1) return false;
     int PL = 256 / (C / V);
-    long long want = (long long)NASB_SM_COUNT * 8;
+    long long want = (long long)NASB_SM_COUNT * 6;  // two full waves of the 3 resident CTAs per SM: no partial tail wave
     rows = (P + want - 1) / want;
     long long minrows = (long long)PL * 8;
     if (rows < minrows) rows = minrows;

@@ -210,6 +210,80 @@ __global__ void __launch_bounds__(256) dw_wgrad_tile_kernel(const __grid_constan
     }
 }
 
+
+// ---- strided data gradient on tiles: dx[iy,ix] = sum_{taps with (iy+pad-ky*dil) % s == 0 ...} dz[(iy+pad-ky*dil)/s, ...] * w[ky,kx]
+// One CTA owns a TH x TW patch of dx pixels; the dz patch that can contribute is staged by one TMA box (zero fill outside).
+struct DwG {
+    int N, IH, IW, OH, OW, C;     // dx is IH x IW, dz is OH x OW
+    int CC, nchunks;
+    int TH, TW, ZTH, ZTW;         // dx patch, dz patch
+    int stride, dil, pad;
+    int tiles_x, tiles_y;
+    const float *w;
+    bf16 *dx;
+    int dx_cs;
+};
+
+__device__ __forceinline__ int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int K>
+__global__ void __launch_bounds__(256) dw_dgrad_strided_tile_kernel(const __grid_constant__ CUtensorMap map_dz, const DwG p) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
+    bf16 *zt = reinterpret_cast<bf16 *>(base);  // [ZTH][ZTW][CC]
+    const size_t zt_bytes = (size_t)p.ZTH * p.ZTW * p.CC * 2;
+    float *wsm = reinterpret_cast<float *>(base + ((zt_bytes + 127) & ~(size_t)127));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + K * K * p.CC);
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.y, n = blockIdx.z, c_base = chunk * p.CC;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int iy0 = ty * p.TH, ix0 = tx * p.TW;
+    // first dz row / column that any pixel of this patch can touch: min over taps of (i + pad - k*dil) / s
+    const int zy0 = floordiv(iy0 + p.pad - (K - 1) * p.dil, p.stride), zx0 = floordiv(ix0 + p.pad - (K - 1) * p.dil, p.stride);
+    if (tid == 0) {
+        dmbar_init(bar, 1);
+        dmbar_expect_tx(bar, (uint32_t)zt_bytes);
+        tma_load_4d(zt, &map_dz, bar, c_base, zx0, zy0, n);
+    }
+    for (int i = tid; i < K * K * p.CC; i += blockDim.x) {
+        int tap = i / p.CC, c = i - tap * p.CC;
+        wsm[i] = p.w[(size_t)(c_base + c) * K * K + tap];
+    }
+    __syncthreads();
+    dmbar_wait(bar, 0);
+    const int CVn = p.CC / 8;
+    const int items = p.TH * p.TW * CVn;
+    for (int it = tid; it < items; it += blockDim.x) {
+        const int cv = it % CVn, px = it / CVn;
+        const int sy = px / p.TW, sx = px - sy * p.TW;
+        const int iy = iy0 + sy, ix = ix0 + sx;
+        if (iy >= p.IH || ix >= p.IW) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int ty_ = iy + p.pad - ky * p.dil;
+            if (ty_ < 0 || ty_ % p.stride) continue;
+            const int zy = ty_ / p.stride - zy0;
+            if (zy < 0 || zy >= p.ZTH) continue;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int tx_ = ix + p.pad - kx * p.dil;
+                if (tx_ < 0 || tx_ % p.stride) continue;
+                const int zx = tx_ / p.stride - zx0;
+                if (zx < 0 || zx >= p.ZTW) continue;
+                float v[8];
+                load_vec<bf16, 8>(zt + ((size_t)zy * p.ZTW + zx) * p.CC + cv * 8, v);
+                const float *wt = wsm + (ky * K + kx) * p.CC + cv * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wt[j], acc[j]);
+            }
+        }
+        store_vec<bf16, 8>(p.dx + (((size_t)n * p.IH + iy) * p.IW + ix) * p.dx_cs + c_base + cv * 8, acc);
+    }
+}
+
 typedef CUresult (*DwEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -395,6 +469,68 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
             cfg5 = true;
         }
         dw_wgrad_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, mz, p);
+    }
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// Strided (stride >= 2) data gradient on tiles; stride-1 goes through nasb_dwconv_tile(mode 1).
+extern "C" int nasb_dwconv_dgrad_strided_tile(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
+                                              const NasbTensor *dx, void *stream) {
+    if (!dz || !dx || !weight) return NASB_ERR_BAD_ARG;
+    if (dz->dtype != NASB_BF16 || dx->dtype != NASB_BF16 || dz->c != dx->c || dz->n != dx->n) return NASB_ERR_UNSUPPORTED;
+    if ((ks != 3 && ks != 5) || stride < 2 || !vec_ok(*dz, 8) || !vec_ok(*dx, 8) || dx->n > 65535) return NASB_ERR_UNSUPPORTED;
+    int cc = pick_cc(dx->c);
+    if (!cc) return NASB_ERR_UNSUPPORTED;
+    const int TH = 16, TW = 32;
+    DwG p{};
+    // dz rows touched by TH dx rows: ((TH-1) + (ks-1)*dil) / stride + 2
+    p.ZTH = (TH - 1 + (ks - 1) * dil) / stride + 2;
+    p.ZTW = (TW - 1 + (ks - 1) * dil) / stride + 2;
+    while (cc >= 8) {
+        if (dx->c % cc == 0 && (size_t)p.ZTH * p.ZTW * cc * 2 + (size_t)ks * ks * cc * 4 + 1024 <= 72 * 1024) break;
+        cc -= 8;
+    }
+    if (cc < 8) return NASB_ERR_UNSUPPORTED;
+    if (npix(*dx) == 0) return 0;
+    p.N = dx->n;
+    p.IH = dx->h;
+    p.IW = dx->w;
+    p.OH = dz->h;
+    p.OW = dz->w;
+    p.C = dx->c;
+    p.CC = cc;
+    p.nchunks = dx->c / cc;
+    p.TH = TH;
+    p.TW = TW;
+    p.stride = stride;
+    p.dil = dil;
+    p.pad = pad;
+    p.tiles_x = cdiv(dx->w, TW);
+    p.tiles_y = cdiv(dx->h, TH);
+    p.w = weight;
+    p.dx = (bf16 *)dx->ptr;
+    p.dx_cs = dx->cstride;
+    CUtensorMap mz;
+    if (!make_map4(&mz, dz, cc, p.ZTW, p.ZTH)) return NASB_ERR_UNSUPPORTED;
+    size_t smem = (size_t)p.ZTH * p.ZTW * cc * 2 + (size_t)ks * ks * cc * 4 + 1024 + 256;
+    dim3 grid(p.tiles_x * p.tiles_y, p.nchunks, dx->n);
+    if (ks == 3) {
+        static bool cfg = false;
+        if (!cfg) {
+            if (cudaFuncSetAttribute(dw_dgrad_strided_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfg = true;
+        }
+        dw_dgrad_strided_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(mz, p);
+    } else {
+        static bool cfg = false;
+        if (!cfg) {
+            if (cudaFuncSetAttribute(dw_dgrad_strided_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfg = true;
+        }
+        dw_dgrad_strided_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mz, p);
     }
     NASB_CHECK_LAUNCH();
     return 0;

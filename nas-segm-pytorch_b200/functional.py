@@ -254,9 +254,15 @@ class _ConvUnit(torch.autograd.Function):
                 call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
                      ref(desc(dx0)), None)
             elif dw:
-                if not (stride == 1 and dz.dtype == torch.bfloat16 and _tiles_on() and try_call(
-                        "nasb_dwconv_tile", ref(ddz), ptr(weight), ks, stride, dil, pad, 1, None, None, ACT_NONE,
-                        ref(desc(dx0)))):
+                tiled = False
+                if dz.dtype == torch.bfloat16 and _tiles_on():
+                    if stride == 1:
+                        tiled = try_call("nasb_dwconv_tile", ref(ddz), ptr(weight), ks, stride, dil, pad, 1, None, None, ACT_NONE,
+                                         ref(desc(dx0)))
+                    else:
+                        tiled = try_call("nasb_dwconv_dgrad_strided_tile", ref(ddz), ptr(weight), ks, stride, dil, pad,
+                                         ref(desc(dx0)))
+                if not tiled:
                     call("nasb_dwconv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)))
             else:
                 call("nasb_conv_dgrad", ref(ddz), ptr(weight), ks, stride, dil, pad, ref(desc(dx0)),

@@ -53,10 +53,15 @@ def test_dw_tile_forward_dgrad_wgrad():
             e = float((dw - wr.grad).abs().max() / wr.grad.abs().max().clamp_min(1e-6))
             if e > 5e-3:
                 bad.append(("wgrad", C, k, s, d, H, W, e))
+            dx = lib.new_act(2, C, H, W, torch.bfloat16, "cuda")
+            dx.fill_(float("nan"))
             if s == 1:
-                dx = lib.new_act(2, C, H, W, torch.bfloat16, "cuda")
-                assert lib.try_call("nasb_dwconv_tile", lib.ref(lib.desc(dz)), lib.ptr(w), k, s, d, pad, 1, None, None,
+                done = lib.try_call("nasb_dwconv_tile", lib.ref(lib.desc(dz)), lib.ptr(w), k, s, d, pad, 1, None, None,
                                     lib.ACT_NONE, lib.ref(lib.desc(dx)))
+            else:
+                done = lib.try_call("nasb_dwconv_dgrad_strided_tile", lib.ref(lib.desc(dz)), lib.ptr(w), k, s, d, pad,
+                                    lib.ref(lib.desc(dx)))
+            if done:
                 torch.cuda.synchronize()
                 e = float((dx.float() - xr.grad).abs().max() / xr.grad.abs().max().clamp_min(1e-6))
                 if e > 1e-2:
