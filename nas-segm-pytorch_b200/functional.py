@@ -205,7 +205,9 @@ class _ConvUnit(torch.autograd.Function):
         dbeta = torch.zeros(cout, dtype=torch.float32, device=dev) if has_b else None
         if ctx.bn_mode or act != ACT_NONE:
             dz = lib.new_act(*y.shape, y.dtype, dev)
-            call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)), ref(desc(z)) if z is not None else None, act, ptr(gamma),
+            # training: the mask is recomputed from z, y is neither read nor passed
+            call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)) if z is None else None, ref(desc(z)) if z is not None else None,
+                 act, ptr(gamma),
                  ptr(beta), ptr(ss[0]) if ss is not None else None, ptr(ss[1]) if ss is not None else None,
                  ptr(sv[0]) if sv is not None else None,
                  ptr(sv[1]) if sv is not None else None, 1 if ctx.bn_mode == 2 else 0, ptr(dgamma), ptr(dbeta),
@@ -322,7 +324,8 @@ class _BnAct(torch.autograd.Function):
         dgamma = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[0] else None
         dbeta = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[1] else None
         dx = lib.new_act(*y.shape, y.dtype, dev)
-        call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)), ref(desc(x)) if ctx.training else None, ctx.act, ptr(gamma),
+        call("nasb_bn_act_bwd", ref(desc(dy)), None if ctx.training else ref(desc(y)), ref(desc(x)) if ctx.training else None,
+             ctx.act, ptr(gamma),
              ptr(beta), ptr(ss[0]), ptr(ss[1]), ptr(sv[0]) if sv is not None else None, ptr(sv[1]) if sv is not None else None,
              1 if ctx.training else 0, ptr(dgamma), ptr(dbeta), ref(desc(dx)), ptr(_ws(dev, c)))
         return dx, dgamma, dbeta, None, None
