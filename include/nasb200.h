@@ -137,10 +137,12 @@ int nasb_dwconv_wgrad(const NasbTensor *x, int in_relu, const NasbTensor *dz, in
                       float *dweight, void *stream);
 /* TMA-tiled variants (bf16, k in {3,5}): one 4-D TMA box stages the input patch with its halo (zero padding = the
  * hardware's out-of-bounds fill), compute runs out of shared memory.  mode 0 = forward (+ folded BN / activation),
- * mode 1 = stride-1 data gradient (x = dz, out = dx).  Return NASB_ERR_UNSUPPORTED for shapes outside their envelope;
+ * mode 1 = stride-1 data gradient (x = dz, out = dx); stats (optional) accumulates fp64 [2][C] sum / sum of squares of the
+ * stored output (training-mode BN statistics fused, finish with nasb_bn_finalize).  Return NASB_ERR_UNSUPPORTED for shapes outside their envelope;
  * the host then uses the gather kernels above. */
 int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
-                     const float *out_scale, const float *out_shift, int act, const NasbTensor *out, void *stream);
+                     const float *out_scale, const float *out_shift, int act, const NasbTensor *out, double *stats,
+                     void *stream);
 int nasb_dwconv_dgrad_strided_tile(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
                                    const NasbTensor *dx, void *stream);
 int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz, int ks, int stride, int dil, int pad,

@@ -57,6 +57,7 @@ struct DwT {
     int act;
     bf16 *out;
     int out_cs;
+    double *stats;                // optional [2][C]: sum / sum of squares of the stored output (training-mode BN fused)
 };
 
 constexpr int DW_P = 4;  // output pixels per strip
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CU
     const size_t tile_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
     float *wsm = reinterpret_cast<float *>(base + ((tile_bytes + 127) & ~(size_t)127));   // [K*K][CC]
     uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + K * K * p.CC);
+    float *ssum = reinterpret_cast<float *>(bar + 1);  // [2][CC] per-CTA statistics
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y, n = blockIdx.z;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CU
         dmbar_expect_tx(bar, (uint32_t)tile_bytes);
         tma_load_4d(tile, &map_x, bar, c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
     }
+    if (p.stats)
+        for (int i = tid; i < 2 * p.CC; i += blockDim.x) ssum[i] = 0.f;
     for (int i = tid; i < K * K * p.CC; i += blockDim.x) {
         int tap = i / p.CC, c = i - tap * p.CC;
         int src_tap = p.flip ? (K * K - 1 - tap) : tap;
@@ -122,11 +126,12 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CU
             }
         }
         const int c0 = c_base + cv * 8;
-        float sc[8], sh[8];
+        float sc[8], sh[8], s1[8], s2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             sc[j] = p.scale ? p.scale[c0 + j] : 1.f;
             sh[j] = p.shift ? p.shift[c0 + j] : 0.f;
+            s1[j] = s2[j] = 0.f;
         }
 #pragma unroll
         for (int q = 0; q < DW_P; ++q) {
@@ -137,6 +142,28 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j) acc[q][j] = apply_act(acc[q][j] * sc[j] + sh[j], p.act);
             }
             store_vec<bf16, 8>(p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.out_cs + c0, acc[q]);
+            if (p.stats) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = __bfloat162float(__float2bfloat16_rn(acc[q][j]));  // statistics of the stored value
+                    s1[j] += v;
+                    s2[j] = fmaf(v, v, s2[j]);
+                }
+            }
+        }
+        if (p.stats) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&ssum[cv * 8 + j], s1[j]);
+                atomicAdd(&ssum[p.CC + cv * 8 + j], s2[j]);
+            }
+        }
+    }
+    if (p.stats) {
+        __syncthreads();
+        for (int i = tid; i < p.CC; i += blockDim.x) {
+            atomicAdd(&p.stats[c_base + i], (double)ssum[i]);
+            atomicAdd(&p.stats[p.C + c_base + i], (double)ssum[p.CC + i]);
         }
     }
 }
@@ -349,7 +376,8 @@ using namespace nasb;
 // Forward (mode 0) or stride-1 data gradient (mode 1: x = dz, out = dx, flipped kernel).  Returns NASB_ERR_UNSUPPORTED for
 // configurations the tile path does not cover (the caller then uses the gather kernels of dwconv.cu).
 extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
-                                const float *out_scale, const float *out_shift, int act, const NasbTensor *out, void *stream) {
+                                const float *out_scale, const float *out_shift, int act, const NasbTensor *out, double *stats,
+                                void *stream) {
     if (!x || !out || !weight) return NASB_ERR_BAD_ARG;
     if (x->dtype != NASB_BF16 || out->dtype != NASB_BF16 || x->c != out->c || x->n != out->n) return NASB_ERR_UNSUPPORTED;
     if ((ks != 3 && ks != 5) || !vec_ok(*x, 8) || !vec_ok(*out, 8)) return NASB_ERR_UNSUPPORTED;
@@ -389,9 +417,10 @@ extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks
     p.act = act;
     p.out = (bf16 *)out->ptr;
     p.out_cs = out->cstride;
+    p.stats = stats;
     CUtensorMap mx;
     if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH)) return NASB_ERR_UNSUPPORTED;
-    size_t smem = pl.smem + 256;
+    size_t smem = pl.smem + 256 + 2 * pl.CC * 4 + 16;
     dim3 grid(p.tiles_x * p.tiles_y, p.nchunks, x->n);
     static bool cfg3 = false, cfg5 = false;
     if (ks == 3) {

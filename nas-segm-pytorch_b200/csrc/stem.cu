@@ -90,24 +90,16 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemP p) {
 
 constexpr int STEM_WP = 64;  // pixels staged per step of the weight gradient
 
-// dW[co][k] = sum_px dz[px][co] * patch[px][k].  Register tile: thread (co group of 4, k group of 7, pixel lane of 8) keeps a
-// 4 x 7 block of dW; per staged pixel it reads one float4 of dz and seven patch values (broadcast within the warp) for 28
-// FMAs.  The 8 pixel lanes are folded with shuffles, one atomic flush per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const StemP p, const T *dz, int dz_cs, float *dw, long long rows_per_cta) {
-    __shared__ __align__(16) float Zs[STEM_WP][STEM_CO];
-    __shared__ __align__(16) float Xs[STEM_WP][28];
+    __shared__ float Zs[STEM_WP][STEM_CO];
+    __shared__ float Xs[STEM_WP][STEM_K + 1];
     const int tid = threadIdx.x;
-    const int pl = tid & 7, grp = tid >> 3;      // 8 pixel lanes (adjacent lanes of a warp), 32 (co, k) groups
-    const int cg = grp & 7, kg = grp >> 3;       // co = cg*4 .. +3 ; k = kg*7 .. +6
+    const int co = tid & 31, kg = tid >> 5;  // warp = one k-group, lanes = output channels
     const long long M = (long long)p.N * p.OH * p.OW;
     const long long plane = (long long)p.IH * p.IW;
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
-    float acc[4][7];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long m0 = r0; m0 < r1; m0 += STEM_WP) {
         __syncthreads();
         for (int i = tid; i < STEM_WP * STEM_CO; i += blockDim.x) {
@@ -115,11 +107,11 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const StemP p, const T 
             long long m = m0 + pp;
             Zs[pp][c] = m < r1 ? to_f(dz[m * dz_cs + c]) : 0.f;
         }
-        for (int i = tid; i < STEM_WP * 28; i += blockDim.x) {
-            int pp = i / 28, k = i - pp * 28;
+        for (int i = tid; i < STEM_WP * STEM_K; i += blockDim.x) {
+            int pp = i / STEM_K, k = i - pp * STEM_K;
             long long m = m0 + pp;
             float x = 0.f;
-            if (m < r1 && k < STEM_K) {
+            if (m < r1) {
                 int ox = (int)(m % p.OW);
                 long long t = m / p.OW;
                 int oy = (int)(t % p.OH);
@@ -131,31 +123,21 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const StemP p, const T 
             Xs[pp][k] = x;
         }
         __syncthreads();
+#pragma unroll 4
+        for (int pp = 0; pp < STEM_WP; ++pp) {
+            float z = Zs[pp][co];
 #pragma unroll
-        for (int q = 0; q < STEM_WP / 8; ++q) {
-            const int pp = q * 8 + pl;
-            const float4 z = *reinterpret_cast<const float4 *>(&Zs[pp][cg * 4]);
-            const float zv[4] = {z.x, z.y, z.z, z.w};
-            float xv[7];
-#pragma unroll
-            for (int j = 0; j < 7; ++j) xv[j] = Xs[pp][kg * 7 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 7; ++j) acc[i][j] = fmaf(zv[i], xv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) {
+                int k = kg + 8 * j;
+                if (k < STEM_K) acc[j] = fmaf(z, Xs[pp][k], acc[j]);
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            float v = acc[i][j];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            const int k = kg * 7 + j;
-            if (pl == 0 && k < STEM_K) atomicAdd(&dw[(cg * 4 + i) * STEM_K + k], v);
-        }
+    for (int j = 0; j < 4; ++j) {
+        int k = kg + 8 * j;
+        if (k < STEM_K) atomicAdd(&dw[co * STEM_K + k], acc[j]);
+    }
 }
 
 }  // namespace nasb

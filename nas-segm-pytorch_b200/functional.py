@@ -135,8 +135,8 @@ class _ConvUnit(torch.autograd.Function):
                 assert r is None
                 if not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and try_call(
                         "nasb_dwconv_tile", ref(dx0), ptr(weight), ks, stride, dil, pad, 0, ptr(scale), ptr(shift), a,
-                        ref(desc(out))):
-                    return
+                        ref(desc(out)), ptr(stats)):
+                    return True
                 call("nasb_dwconv_fwd", ref(dx0), ptr(weight), ks, stride, dil, pad, in_relu, ptr(scale), ptr(shift), a,
                      ref(desc(out)))
             else:
@@ -167,13 +167,17 @@ class _ConvUnit(torch.autograd.Function):
             ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
             sv = torch.empty((2, cout), dtype=torch.float32, device=dev)
             mom = 0.1 if bn.momentum is None else float(bn.momentum)
-            if use_tc or use_c3:  # batch statistics are accumulated by the GEMM epilogue
+            fused_stats = use_tc or use_c3
+            sums = None
+            if fused_stats or (dw and not in_relu and x0.dtype == torch.bfloat16 and _tiles_on()):
                 sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
-                run_conv(z, None, None, ACT_NONE, None, sums)
+                fused_stats = bool(run_conv(z, None, None, ACT_NONE, None, sums)) or fused_stats
+            if fused_stats:  # batch statistics were accumulated by the conv kernel's epilogue
                 call("nasb_bn_finalize", ptr(sums), C.c_longlong(n * oh * ow), cout, ptr(gamma), ptr(beta), float(bn.eps),
                      mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]))
             else:
-                run_conv(z, None, None, ACT_NONE, None)
+                if sums is None:
+                    run_conv(z, None, None, ACT_NONE, None)
                 call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
                      ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, cout)))
             if bn.num_batches_tracked is not None:
@@ -260,7 +264,7 @@ class _ConvUnit(torch.autograd.Function):
                 if dz.dtype == torch.bfloat16 and _tiles_on():
                     if stride == 1:
                         tiled = try_call("nasb_dwconv_tile", ref(ddz), ptr(weight), ks, stride, dil, pad, 1, None, None, ACT_NONE,
-                                         ref(desc(dx0)))
+                                         ref(desc(dx0)), None)
                     else:
                         tiled = try_call("nasb_dwconv_dgrad_strided_tile", ref(ddz), ptr(weight), ks, stride, dil, pad,
                                          ref(desc(dx0)))

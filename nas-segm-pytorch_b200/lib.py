@@ -44,7 +44,7 @@ _SIG = {
     "nasb_dwconv_fwd": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
     "nasb_dwconv_dgrad": [_TP, _P, _I, _I, _I, _I, _TP, _P],
     "nasb_dwconv_wgrad": [_TP, _I, _TP, _I, _I, _I, _I, _P, _P],
-    "nasb_dwconv_tile": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
+    "nasb_dwconv_tile": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P, _P],
     "nasb_dwconv_dgrad_strided_tile": [_TP, _P, _I, _I, _I, _I, _TP, _P],
     "nasb_dwconv_wgrad_tile": [_TP, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_bn_fold": [_P, _P, _P, _P, _F, _I, _P, _P, _P],

@@ -33,7 +33,7 @@ def test_dw_tile_forward_dgrad_wgrad():
         OH, OW = ref.shape[2:]
         out = lib.new_act(2, C, OH, OW, torch.bfloat16, "cuda")
         ok = lib.try_call("nasb_dwconv_tile", lib.ref(lib.desc(x)), lib.ptr(w), k, s, d, pad, 0, lib.ptr(scale), lib.ptr(shift),
-                          lib.ACT_RELU6, lib.ref(lib.desc(out)))
+                          lib.ACT_RELU6, lib.ref(lib.desc(out)), None)
         if not ok:
             continue
         covered += 1
@@ -57,7 +57,7 @@ def test_dw_tile_forward_dgrad_wgrad():
             dx.fill_(float("nan"))
             if s == 1:
                 done = lib.try_call("nasb_dwconv_tile", lib.ref(lib.desc(dz)), lib.ptr(w), k, s, d, pad, 1, None, None,
-                                    lib.ACT_NONE, lib.ref(lib.desc(dx)))
+                                    lib.ACT_NONE, lib.ref(lib.desc(dx)), None)
             else:
                 done = lib.try_call("nasb_dwconv_dgrad_strided_tile", lib.ref(lib.desc(dz)), lib.ptr(w), k, s, d, pad,
                                     lib.ref(lib.desc(dx)))
@@ -77,9 +77,12 @@ def test_dw_tile_channel_slices():
     w = torch.randn(48, 1, 3, 3, generator=g, device="cuda") / 3
     outw = torch.zeros(2, 21, 30, 80, device="cuda", dtype=torch.bfloat16)
     out = outw.permute(0, 3, 1, 2)[:, 8:56]
+    st = torch.zeros(2 * 48, dtype=torch.float64, device="cuda")
     assert lib.try_call("nasb_dwconv_tile", lib.ref(lib.desc(x)), lib.ptr(w), 3, 1, 1, 1, 0, None, None, lib.ACT_NONE,
-                        lib.ref(lib.desc(out)))
+                        lib.ref(lib.desc(out)), lib.ptr(st))
     torch.cuda.synchronize()
     ref = F.conv2d(x.float(), w, None, 1, 1, 1, groups=48)
     assert float((out.float() - ref).abs().max() / ref.abs().max()) < 1e-2
     assert float(outw[..., :8].abs().max()) == 0 and float(outw[..., 56:].abs().max()) == 0
+    od = out.double().permute(0, 2, 3, 1).reshape(-1, 48)  # fused statistics == sums of the stored (bf16) output
+    assert torch.allclose(st[:48], od.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(st[48:], (od * od).sum(0), rtol=1e-4, atol=1e-2)
