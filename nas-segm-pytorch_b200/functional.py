@@ -30,6 +30,11 @@ def _grad_in(dy, like_dtype):
     return lib.to_nhwc(dy, like_dtype)
 
 
+def _dw_stats_on():
+    from . import config
+    return config().fuse_dw_stats
+
+
 def _tiles_on():
     from . import config
     return config().use_tma_tiles
@@ -169,7 +174,7 @@ class _ConvUnit(torch.autograd.Function):
             mom = 0.1 if bn.momentum is None else float(bn.momentum)
             fused_stats = use_tc or use_c3
             sums = None
-            if fused_stats or (dw and not in_relu and x0.dtype == torch.bfloat16 and _tiles_on()):
+            if fused_stats or (dw and not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and _dw_stats_on()):
                 sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
                 fused_stats = bool(run_conv(z, None, None, ACT_NONE, None, sums)) or fused_stats
             if fused_stats:  # batch statistics were accumulated by the conv kernel's epilogue
