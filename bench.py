@@ -104,17 +104,19 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  Started before the warm-up (nvidia-smi needs a moment to
+    come up, longer on an 8-GPU box); `mark()` brackets the timed region and the summary uses the samples that arrived
+    inside it (falling back to every sample taken under load if the region was shorter than one period)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -124,9 +126,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -135,9 +143,14 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= (self.t1 or 1e18) + 0.15]
+        src = "timed region"
+        if not inside:  # region shorter than a sampling period: use the samples taken while the warm-up kept the GPU busy
+            inside = [r for t, r in self.rows if self.t1 is None or t <= self.t1 + 0.15][-5:]
+            src = "warm-up + timed region"
+        sm, mx, reasons = [], 0, set()
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -147,7 +160,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": src}
 
 
 # ------------------------------------------------------------------------------------------------------------ reference arm
@@ -318,18 +331,21 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local).start()
     for _ in range(max(a.warmup, 3) + (2 if a.cuda_graph else 0)):  # graph mode: 3 eager iterations, then capture + replays
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.launches
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(a.steps):
-            loss = step()
-        e1.record()
-        barrier()
+    barrier()
+    clk.mark_begin()
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    clk.mark_end()
+    clk.stop()
     launches = lib.launches - l0
     ms = e0.elapsed_time(e1)
     tmax = torch.tensor([ms], device=dev)
