@@ -62,109 +62,119 @@ struct DwT {
 
 constexpr int DW_P = 4;  // output pixels per strip
 
+// Persistent: CTA (x, chunk) walks the patches x, x + gridDim.x, ... of its channel chunk with two shared-memory buffers; the
+// TMA box of the next patch is in flight while the current one is consumed.
 template <int K>
 __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const DwT p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
-    bf16 *tile = reinterpret_cast<bf16 *>(base);                                   // [ITH][ITW][CC]
     const size_t tile_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
-    float *wsm = reinterpret_cast<float *>(base + ((tile_bytes + 127) & ~(size_t)127));   // [K*K][CC]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + K * K * p.CC);
-    float *ssum = reinterpret_cast<float *>(bar + 1);  // [2][CC] per-CTA statistics
+    const size_t tile_stride = (tile_bytes + 127) & ~(size_t)127;
+    bf16 *tiles[2] = {reinterpret_cast<bf16 *>(base), reinterpret_cast<bf16 *>(base + tile_stride)};  // [ITH][ITW][CC] x 2
+    float *wsm = reinterpret_cast<float *>(base + 2 * tile_stride);                                   // [K*K][CC]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + K * K * p.CC);                                 // [2]
 
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.y, n = blockIdx.z;
-    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
-    const int oy0 = ty * p.TH, ox0 = tx * p.TW, c_base = chunk * p.CC;
-
+    const int chunk = blockIdx.y, c_base = chunk * p.CC;
+    const int tiles_img = p.tiles_x * p.tiles_y, total = tiles_img * p.N;
+    auto origin = [&](int t, int &n, int &oy0, int &ox0) {
+        n = t / tiles_img;
+        const int r = t - n * tiles_img, ty = r / p.tiles_x;
+        oy0 = ty * p.TH;
+        ox0 = (r - ty * p.tiles_x) * p.TW;
+    };
+    auto issue = [&](int t, int buf) {  // thread 0
+        int n, oy0, ox0;
+        origin(t, n, oy0, ox0);
+        dmbar_expect_tx(&bar[buf], (uint32_t)tile_bytes);
+        tma_load_4d(tiles[buf], &map_x, &bar[buf], c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
+    };
     if (tid == 0) {
-        dmbar_init(bar, 1);
-        dmbar_expect_tx(bar, (uint32_t)tile_bytes);
-        tma_load_4d(tile, &map_x, bar, c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
+        dmbar_init(&bar[0], 1);
+        dmbar_init(&bar[1], 1);
     }
-    if (p.stats)
-        for (int i = tid; i < 2 * p.CC; i += blockDim.x) ssum[i] = 0.f;
     for (int i = tid; i < K * K * p.CC; i += blockDim.x) {
         int tap = i / p.CC, c = i - tap * p.CC;
         int src_tap = p.flip ? (K * K - 1 - tap) : tap;
         wsm[i] = p.w[(size_t)(c_base + c) * K * K + src_tap];
     }
     __syncthreads();  // barrier init + weights visible
-    dmbar_wait(bar, 0);
+    if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
 
     const int CVn = p.CC / 8;
     const int strips_x = p.TW / DW_P;
     const int items = p.TH * strips_x * CVn;
-    for (int it = tid; it < items; it += blockDim.x) {
-        const int cv = it % CVn;
-        const int sidx = it / CVn;
-        const int sx = sidx % strips_x, sy = sidx / strips_x;
-        const int oy = oy0 + sy, oxs = ox0 + sx * DW_P;
-        if (oy >= p.OH || oxs >= p.OW) continue;
-        float acc[DW_P][8];
+    const bool epi = p.scale || p.shift || p.act;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, buf ^ 1);  // buffer buf^1 was released by the last sync
+        int n, oy0, ox0;
+        origin(t, n, oy0, ox0);
+        dmbar_wait(&bar[buf], (it >> 1) & 1);
+        const bf16 *tile = tiles[buf];
+        for (int item = tid; item < items; item += blockDim.x) {
+            const int cv = item % CVn;
+            const int sidx = item / CVn;
+            const int sx = sidx % strips_x, sy = sidx / strips_x;
+            const int oy = oy0 + sy, oxs = ox0 + sx * DW_P;
+            if (oy >= p.OH || oxs >= p.OW) continue;
+            float acc[DW_P][8];
 #pragma unroll
-        for (int q = 0; q < DW_P; ++q)
+            for (int q = 0; q < DW_P; ++q)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+                for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-            const int iy = sy * p.stride + ky * p.dil;
-            const bf16 *rowp = tile + ((size_t)iy * p.ITW) * p.CC + cv * 8;
+            for (int ky = 0; ky < K; ++ky) {
+                const int iy = sy * p.stride + ky * p.dil;
+                const bf16 *rowp = tile + ((size_t)iy * p.ITW) * p.CC + cv * 8;
 #pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8);
-                const float4 w1 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8 + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                for (int kx = 0; kx < K; ++kx) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8 + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int q = 0; q < DW_P; ++q) {
-                    const int ix = (sx * DW_P + q) * p.stride + kx * p.dil;
-                    float v[8];
-                    load_vec<bf16, 8>(rowp + (size_t)ix * p.CC, v);
+                    for (int q = 0; q < DW_P; ++q) {
+                        const int ix = (sx * DW_P + q) * p.stride + kx * p.dil;
+                        float v[8];
+                        load_vec<bf16, 8>(rowp + (size_t)ix * p.CC, v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(v[j], wv[j], acc[q][j]);
+                        for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(v[j], wv[j], acc[q][j]);
+                    }
                 }
             }
-        }
-        const int c0 = c_base + cv * 8;
-        float sc[8], sh[8], s1[8], s2[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sc[j] = p.scale ? p.scale[c0 + j] : 1.f;
-            sh[j] = p.shift ? p.shift[c0 + j] : 0.f;
-            s1[j] = s2[j] = 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < DW_P; ++q) {
-            const int ox = oxs + q;
-            if (ox >= p.OW) break;
-            if (p.scale || p.shift || p.act) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[q][j] = apply_act(acc[q][j] * sc[j] + sh[j], p.act);
-            }
-            store_vec<bf16, 8>(p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.out_cs + c0, acc[q]);
-            if (p.stats) {
+            const int c0 = c_base + cv * 8;
+            bf16 *orow = p.out + (((size_t)n * p.OH + oy) * p.OW + oxs) * p.out_cs + c0;
+            if (epi) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float v = __bfloat162float(__float2bfloat16_rn(acc[q][j]));  // statistics of the stored value
-                    s1[j] += v;
-                    s2[j] = fmaf(v, v, s2[j]);
+                    const float sc = p.scale ? p.scale[c0 + j] : 1.f, sh = p.shift ? p.shift[c0 + j] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < DW_P; ++q) acc[q][j] = apply_act(acc[q][j] * sc + sh, p.act);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < DW_P; ++q) {
+                if (oxs + q >= p.OW) break;
+                store_vec<bf16, 8>(orow + (size_t)q * p.out_cs, acc[q]);
+            }
+            if (p.stats) {  // optional fused statistics of the stored values (off by default, see __init__.py)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < DW_P; ++q)
+                        if (oxs + q < p.OW) {
+                            const float v = __bfloat162float(__float2bfloat16_rn(acc[q][j]));
+                            s1 += v;
+                            s2 = fmaf(v, v, s2);
+                        }
+                    atomicAdd(&p.stats[c0 + j], (double)s1);
+                    atomicAdd(&p.stats[p.C + c0 + j], (double)s2);
                 }
             }
         }
-        if (p.stats) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                atomicAdd(&ssum[cv * 8 + j], s1[j]);
-                atomicAdd(&ssum[p.CC + cv * 8 + j], s2[j]);
-            }
-        }
-    }
-    if (p.stats) {
-        __syncthreads();
-        for (int i = tid; i < p.CC; i += blockDim.x) {
-            atomicAdd(&p.stats[c_base + i], (double)ssum[i]);
-            atomicAdd(&p.stats[p.C + c_base + i], (double)ssum[p.CC + i]);
-        }
+        __syncthreads();  // everyone is done with tiles[buf]; it may be refilled two iterations from now
     }
 }
 
@@ -183,11 +193,11 @@ __global__ void __launch_bounds__(256) dw_wgrad_tile_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap map_dz, const DwW p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
-    bf16 *xt = reinterpret_cast<bf16 *>(base);  // [ITH][ITW][CC]
-    const size_t xt_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
-    bf16 *zt = reinterpret_cast<bf16 *>(base + ((xt_bytes + 127) & ~(size_t)127));  // [TH][TW][CC]
-    const size_t zt_bytes = (size_t)p.TH * p.TW * p.CC * 2;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(zt) + ((zt_bytes + 127) & ~(size_t)127));
+    const size_t xt_bytes = (size_t)p.ITH * p.ITW * p.CC * 2, zt_bytes = (size_t)p.TH * p.TW * p.CC * 2;
+    const size_t xs = (xt_bytes + 127) & ~(size_t)127, zs = (zt_bytes + 127) & ~(size_t)127;
+    bf16 *xt[2] = {reinterpret_cast<bf16 *>(base), reinterpret_cast<bf16 *>(base + xs + zs)};            // [ITH][ITW][CC]
+    bf16 *zt[2] = {reinterpret_cast<bf16 *>(base + xs), reinterpret_cast<bf16 *>(base + 2 * xs + zs)};   // [TH][TW][CC]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(base + 2 * (xs + zs));                                  // [2]
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y, c_base = chunk * p.CC;
@@ -202,41 +212,50 @@ __global__ void __launch_bounds__(256) dw_wgrad_tile_kernel(const __grid_constan
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 
-    if (tid == 0) dmbar_init(bar, 1);
-    __syncthreads();
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int total = tiles_per_img * p.N;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    auto issue = [&](int t, int buf) {  // thread 0
         const int n = t / tiles_per_img, r = t - n * tiles_per_img;
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int oy0 = ty * p.TH, ox0 = tx * p.TW;
-        if (tid == 0) {
-            dmbar_expect_tx(bar, (uint32_t)(xt_bytes + zt_bytes));
-            tma_load_4d(xt, &map_x, bar, c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
-            tma_load_4d(zt, &map_dz, bar, c_base, ox0, oy0, n);
-        }
-        dmbar_wait(bar, it & 1);
+        dmbar_expect_tx(&bar[buf], (uint32_t)(xt_bytes + zt_bytes));
+        tma_load_4d(xt[buf], &map_x, &bar[buf], c_base, ox0 * p.stride - p.pad, oy0 * p.stride - p.pad, n);
+        tma_load_4d(zt[buf], &map_dz, &bar[buf], c_base, ox0, oy0, n);
+    };
+    if (tid == 0) {
+        dmbar_init(&bar[0], 1);
+        dmbar_init(&bar[1], 1);
+    }
+    __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
+        dmbar_wait(&bar[buf], (it >> 1) & 1);
         if (active) {
             // out-of-image dz pixels are zero-filled by TMA, so the whole patch can be walked unconditionally
-            const int npx = p.TH * p.TW;
-            for (int px = pl; px < npx; px += PLn) {
-                const int sy = px / p.TW, sx = px - sy * p.TW;
-                float g[8], v[8];
-                load_vec<bf16, 8>(zt + (size_t)px * p.CC + cv * 8, g);
-                load_vec<bf16, 8>(xt + ((size_t)(sy * p.stride + ky * p.dil) * p.ITW + (sx * p.stride + kx * p.dil)) * p.CC + cv * 8, v);
+            const bf16 *zb = zt[buf] + cv * 8;
+            const bf16 *xb = xt[buf] + ((size_t)(ky * p.dil) * p.ITW + kx * p.dil) * p.CC + cv * 8;
+            for (int sy = 0; sy < p.TH; ++sy) {
+                const bf16 *zr = zb + (size_t)sy * p.TW * p.CC;
+                const bf16 *xr = xb + (size_t)(sy * p.stride) * p.ITW * p.CC;
+                for (int sx = pl; sx < p.TW; sx += PLn) {
+                    float g[8], v[8];
+                    load_vec<bf16, 8>(zr + (size_t)sx * p.CC, g);
+                    load_vec<bf16, 8>(xr + (size_t)(sx * p.stride) * p.CC, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], v[j], acc[j]);
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], v[j], acc[j]);
+                }
             }
         }
-        __syncthreads();  // everyone done with the patch before the next TMA overwrites it
+        __syncthreads();  // everyone done with buffer `buf` before it is refilled
     }
     if (active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(&p.dw[(size_t)(c_base + cv * 8 + j) * K * K + tap], acc[j]);
     }
 }
-
 
 // ---- strided data gradient on tiles: dx[iy,ix] = sum_{taps with (iy+pad-ky*dil) % s == 0 ...} dz[(iy+pad-ky*dil)/s, ...] * w[ky,kx]
 // One CTA owns a TH x TW patch of dx pixels; the dz patch that can contribute is staged by one TMA box (zero fill outside).
@@ -390,7 +409,7 @@ extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks
         if (eh != out->h || ew != out->w) return NASB_ERR_BAD_ARG;
     }
     TilePlan pl;
-    if (!plan_tiles(x->c, ks, stride, dil, (size_t)ks * ks * 4, 72 * 1024, pl)) return NASB_ERR_UNSUPPORTED;
+    if (!plan_tiles(x->c, ks, stride, dil, (size_t)ks * ks * 4, 48 * 1024, pl)) return NASB_ERR_UNSUPPORTED;  // x2 buffers
     if (npix(*out) == 0) return 0;
     DwT p{};
     p.N = x->n;
@@ -420,8 +439,16 @@ extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks
     p.stats = stats;
     CUtensorMap mx;
     if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH)) return NASB_ERR_UNSUPPORTED;
-    size_t smem = pl.smem + 256 + 2 * pl.CC * 4 + 16;
-    dim3 grid(p.tiles_x * p.tiles_y, p.nchunks, x->n);
+    const size_t tile_b = ((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127;
+    size_t smem = 2 * tile_b + (size_t)ks * ks * pl.CC * 4 + 16 + 256;
+    long long total = (long long)p.tiles_x * p.tiles_y * x->n;
+    int per_sm = (int)((200 * 1024) / smem);
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    long long gx = (long long)NASB_SM_COUNT * per_sm / p.nchunks;
+    if (gx < 1) gx = 1;
+    if (gx > total) gx = total;
+    dim3 grid((unsigned)gx, p.nchunks);
     static bool cfg3 = false, cfg5 = false;
     if (ks == 3) {
         if (!cfg3) {
@@ -449,7 +476,7 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     if ((ks != 3 && ks != 5) || !vec_ok(*x, 8) || !vec_ok(*dz, 8)) return NASB_ERR_UNSUPPORTED;
     TilePlan pl;
     // extra per channel: the dz patch (TH*TW <= 8*32 pixels) * 2 bytes
-    if (!plan_tiles(x->c, ks, stride, dil, (size_t)8 * 32 * 2, 88 * 1024, pl)) return NASB_ERR_UNSUPPORTED;
+    if (!plan_tiles(x->c, ks, stride, dil, (size_t)8 * 32 * 2, 48 * 1024, pl)) return NASB_ERR_UNSUPPORTED;  // x2 buffers
     const int pairs = ks * ks * (pl.CC / 8);
     if (pairs > 256) return NASB_ERR_UNSUPPORTED;
     if (npix(*dz) == 0) return 0;
@@ -474,10 +501,10 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     p.dw = dweight;
     CUtensorMap mx, mz;
     if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH) || !make_map4(&mz, dz, pl.CC, pl.TW, pl.TH)) return NASB_ERR_UNSUPPORTED;
-    size_t smem = pl.smem + 512;
+    size_t smem = 2 * ((((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127) + (((size_t)pl.TH * pl.TW * pl.CC * 2 + 127) & ~(size_t)127)) + 16 + 256;
     long long total = (long long)p.tiles_x * p.tiles_y * x->n;
     int per_sm = (int)((200 * 1024) / smem);
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 3) per_sm = 3;
     if (per_sm < 1) per_sm = 1;
     long long gx = (long long)NASB_SM_COUNT * per_sm / p.nchunks;
     if (gx < 1) gx = 1;
