@@ -54,8 +54,8 @@ def test_network_eval_logits(golden, tag):
         assert agree > 0.999
 
 
-def _oracle_train(tag, fx, dtype):
-    """fp64 / fp32 evaluation of the same training step in the CPU oracle."""
+def _oracle_train(tag, fx, dtype, x=None):
+    """fp64 / fp32 evaluation of the same training step in the CPU oracle (optionally on a perturbed input)."""
     from oracle import nas_oracle as O
     paper, cfg, ncls, agg, rep, aux = NETS[tag]
     sd = det_state_dict(keys_shapes(fx), seed=7)
@@ -65,7 +65,7 @@ def _oracle_train(tag, fx, dtype):
             v.requires_grad_(True)
     Pe, Pd = O.Params(sub_state(sd, "encoder."), dtype=dtype), O.Params(sub_state(sd, "decoder."), dtype=dtype)
     rl = (1, 2) if paper == "wacv" else (1, 2, 4, 6)
-    feats = O.mbv2_encoder(t(fx["x"]).to(dtype), Pe, rl, True)
+    feats = O.mbv2_encoder((t(fx["x"]) if x is None else x).to(dtype), Pe, rl, True)
     if paper == "wacv":
         out, auxs = O.template_decoder(feats, Pd, cfg, O.encoder_out_sizes(rl), ncls, agg, rep, training=True), []
     else:
@@ -76,6 +76,29 @@ def _oracle_train(tag, fx, dtype):
         loss = loss + 0.15 * O.segm_loss(a, y, y.shape[1:])
     loss.backward()
     return sd
+
+
+def _fp32_band(tag, fx, trials=4):
+    """How far the reference algorithm's OWN fp32 gradients sit from fp64 on this fixture: the largest (median relative
+    error, global relative L2 error) over `trials` evaluations whose inputs differ by 1e-6 relative.  On the 65x65 CVPR
+    fixtures that figure moves between 2e-3 and 3e-2 from one such evaluation to the next (tools/diag_grads.py, DESIGN.md
+    section 2): a ReLU or a 2-sample BatchNorm decides differently and every gradient upstream moves with it.  A single fp32
+    evaluation is therefore not a band; the maximum over a few is."""
+    g = torch.Generator().manual_seed(1)
+    x0 = t(fx["x"])
+    med, l2 = 0.0, 0.0
+    for i in range(trials):
+        x = x0 if i == 0 else (x0.double() * (1 + (torch.rand(x0.shape, generator=g, dtype=torch.float64) - 0.5) * 2e-6)).float()
+        s64, s32 = _oracle_train(tag, fx, torch.float64, x), _oracle_train(tag, fx, torch.float32, x)
+        es, num, den = [], 0.0, 0.0
+        for k, v in s64.items():
+            if v.grad is None or float(v.grad.abs().max()) < 1e-4:
+                continue
+            es.append(rel_err(s32[k].grad.numpy(), v.grad.numpy()))
+            num += float(((s32[k].grad.double() - v.grad) ** 2).sum())
+            den += float((v.grad ** 2).sum())
+        med, l2 = max(med, float(np.median(es))), max(l2, (num / den) ** 0.5)
+    return med, l2
 
 
 @pytest.mark.parametrize("tag", ["W0cv", "C0search", "C1search"])
@@ -132,8 +155,9 @@ def test_network_train_step(golden, tag):
         if e_cuda > max(0.35, 3.0 * e_cpu):
             bad.append((k, e_cuda, e_cpu))
     assert checked > 100 and not bad, bad[:20]
-    assert np.median(e_all) <= max(1e-3, 3.0 * np.median(e_cpu_all)), (np.median(e_all), np.median(e_cpu_all))
-    assert (num / den) ** 0.5 <= max(1e-2, 3.0 * (num_cpu / den) ** 0.5), ((num / den) ** 0.5, (num_cpu / den) ** 0.5)
+    band_med, band_l2 = _fp32_band(tag, fx)
+    assert np.median(e_all) <= max(1e-3, 3.0 * max(band_med, np.median(e_cpu_all))), (np.median(e_all), band_med)
+    assert (num / den) ** 0.5 <= max(1e-2, 3.0 * max(band_l2, (num_cpu / den) ** 0.5)), ((num / den) ** 0.5, band_l2)
     # the real reference's fixture gradients (fp32) must sit in the same error band around fp64
     for k in [k for k in fx.files if k.startswith("grad/")]:
         g64 = sd64[k[5:]].grad.numpy()

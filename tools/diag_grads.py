@@ -79,6 +79,12 @@ for tag in sys.argv[1:] or ["C0search", "C1search", "W0cv"]:
     print("  worst parameters (cuda-vs-fp64, cpu32-vs-fp64):")
     for r in rows[:12]:
         print("    %.2e  %.2e  %s" % r)
+    if os.environ.get("DIAG_ALL"):
+        print("  decoder parameters in module order:")
+        for k, p in named.items():
+            if k.startswith("decoder.") and sd64[k].grad is not None and p.grad is not None and float(sd64[k].grad.abs().max()) > 1e-4:
+                print("    %.2e  %.2e  %s" % (rel_err(p.grad.cpu().numpy(), sd64[k].grad.numpy()),
+                                              rel_err(sd32[k].grad.numpy(), sd64[k].grad.numpy()), k))
     enc_rows = [r for r in rows if r[2].startswith("encoder.")]
     print("  median over encoder params: cuda %.2e cpu32 %.2e ; decoder: cuda %.2e cpu32 %.2e" % (
         np.median([r[0] for r in enc_rows]), np.median([r[1] for r in enc_rows]),
