@@ -24,9 +24,9 @@ class _Config:
         self.use_tcgen05 = True  # bf16 pointwise convolutions on the tensor cores when shapes allow
         self.graph_warmup = 3  # eager iterations before an engine loop captures its CUDA graph
         self.cuda_graphs = False  # engine loops replay one captured CUDA graph per iteration (graphs.StepGraph)
-        # training-BN statistics inside the depthwise tile kernel: measured slower than the separate vectorised
-        # reduction on B200 (shared-memory atomics per strip cost more than the extra 16-byte/pixel read), so off
-        self.fuse_dw_stats = False
+        # training-BN statistics inside the depthwise tile kernel (per-thread register partials over the persistent loop,
+        # one shared-memory merge per CTA): +15-25 % on the kernel, cheaper than the separate pass that re-reads z
+        self.fuse_dw_stats = True
         self.use_tma_tiles = True  # bf16 depthwise convolutions on TMA-staged shared-memory tiles when shapes allow
 
 

@@ -60,19 +60,64 @@ struct DwT {
     double *stats;                // optional [2][C]: sum / sum of squares of the stored output (training-mode BN fused)
 };
 
-constexpr int DW_P = 4;  // output pixels per strip
+constexpr int DW_P = 4;  // output pixels per strip (a vertical strip: 4 consecutive rows of one column)
+
+// ---- packed helpers: 8 bf16 channels (one 16-byte LDS) -> four float2, and the Blackwell packed fp32 FMA (FFMA2)
+__device__ __forceinline__ void cvt8(const uint4 &r, float2 (&v)[4]) {
+    v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
+    v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
+}
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// explicit shared-space 16-byte loads on 32-bit shared addresses (a generic pointer derived through uintptr_t arithmetic
+// makes the compiler emit generic LD instead of LDS)
+__device__ __forceinline__ uint4 lds16(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void ldw8(uint32_t a, float2 (&w)[4]) {
+    const uint4 lo = lds16(a), hi = lds16(a + 16);
+    w[0] = make_float2(__uint_as_float(lo.x), __uint_as_float(lo.y));
+    w[1] = make_float2(__uint_as_float(lo.z), __uint_as_float(lo.w));
+    w[2] = make_float2(__uint_as_float(hi.x), __uint_as_float(hi.y));
+    w[3] = make_float2(__uint_as_float(hi.z), __uint_as_float(hi.w));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
 
 // Persistent: CTA (x, chunk) walks the patches x, x + gridDim.x, ... of its channel chunk with two shared-memory buffers; the
 // TMA box of the next patch is in flight while the current one is consumed.
-template <int K>
-__global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const DwT p) {
+//
+// Thread = (channel vector cv, lane): cv = tid % CVn is fixed for the thread's whole life (so the optional training-BN
+// statistics stay in registers until the end), lane = tid / CVn walks the patch's vertical strips -- DW_P consecutive
+// output rows of one column.  Consecutive lanes own consecutive columns: shared-memory reads and global stores of a warp
+// are contiguous.  With dilation 1 (template S = stride 1 or 2) every input pixel of the strip's column window is loaded
+// and converted once and feeds all the taps / output rows it belongs to out of registers; the weights of the current
+// kernel column sit in registers.  S == 0 is the general (dilated) path: one load per tap.
+// All arithmetic is packed fp32 (fma.rn.f32x2), accumulation in fp32.
+template <int K, int S, bool STATS>
+__global__ void __launch_bounds__(256, 2) dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const DwT p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
     const size_t tile_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
     const size_t tile_stride = (tile_bytes + 127) & ~(size_t)127;
     bf16 *tiles[2] = {reinterpret_cast<bf16 *>(base), reinterpret_cast<bf16 *>(base + tile_stride)};  // [ITH][ITW][CC] x 2
     float *wsm = reinterpret_cast<float *>(base + 2 * tile_stride);                                   // [K*K][CC]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + K * K * p.CC);                                 // [2]
+    float *ssm = wsm + K * K * p.CC;                                                                  // [2][CC] (STATS)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ssm + 2 * p.CC);                                     // [2]
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y, c_base = chunk * p.CC;
@@ -98,13 +143,24 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CU
         int src_tap = p.flip ? (K * K - 1 - tap) : tap;
         wsm[i] = p.w[(size_t)(c_base + c) * K * K + src_tap];
     }
+    if (STATS)
+        for (int i = tid; i < 2 * p.CC; i += blockDim.x) ssm[i] = 0.f;
     __syncthreads();  // barrier init + weights visible
     if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
 
     const int CVn = p.CC / 8;
-    const int strips_x = p.TW / DW_P;
-    const int items = p.TH * strips_x * CVn;
+    const int cv = tid % CVn, lane = tid / CVn, L = blockDim.x / CVn;  // host: blockDim.x is a multiple of CVn
+    const int nstrips = (p.TH / DW_P) * p.TW;
+    const int c0 = c_base + cv * 8;
     const bool epi = p.scale || p.shift || p.act;
+    float2 st1[4], st2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st1[j] = st2[j] = make_float2(0.f, 0.f);
+    const uint32_t wcv = dsmem_u32(wsm) + cv * 32;  // this thread's 8 weights of tap 0; next tap: + CC*4 bytes
+    const int CC = p.CC, ITW = p.ITW;
+    const uint32_t pxb = (uint32_t)CC * 2, rowb = (uint32_t)ITW * pxb, tapb = (uint32_t)CC * 4;  // byte pitches
+    const uint32_t tile_a[2] = {dsmem_u32(tiles[0]) + cv * 16, dsmem_u32(tiles[1]) + cv * 16};
+
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -112,105 +168,147 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const __grid_constant__ CU
         int n, oy0, ox0;
         origin(t, n, oy0, ox0);
         dmbar_wait(&bar[buf], (it >> 1) & 1);
-        const bf16 *tile = tiles[buf];
-        for (int item = tid; item < items; item += blockDim.x) {
-            const int cv = item % CVn;
-            const int sidx = item / CVn;
-            const int sx = sidx % strips_x, sy = sidx / strips_x;
-            const int oy = oy0 + sy, oxs = ox0 + sx * DW_P;
-            if (oy >= p.OH || oxs >= p.OW) continue;
-            float acc[DW_P][8];
+        const uint32_t tile = buf ? tile_a[1] : tile_a[0];
+        for (int s = lane; s < nstrips; s += L) {
+            const int sx = s % p.TW, sy = (s / p.TW) * DW_P;
+            const int ox = ox0 + sx, oy = oy0 + sy;
+            if (ox >= p.OW || oy >= p.OH) continue;
+            float2 acc[DW_P][4];
 #pragma unroll
             for (int q = 0; q < DW_P; ++q)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
-#pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                const int iy = sy * p.stride + ky * p.dil;
-                const bf16 *rowp = tile + ((size_t)iy * p.ITW) * p.CC + cv * 8;
-#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[q][j] = make_float2(0.f, 0.f);
+            if constexpr (S > 0) {
+                // column window: input rows sy*S .. sy*S + (DW_P-1)*S + K-1 of column sx*S + kx
+                constexpr int ROWS = (DW_P - 1) * S + K;
+#pragma unroll 1
                 for (int kx = 0; kx < K; ++kx) {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(wsm + (ky * K + kx) * p.CC + cv * 8 + 4);
-                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float2 wc[K][4];
 #pragma unroll
-                    for (int q = 0; q < DW_P; ++q) {
-                        const int ix = (sx * DW_P + q) * p.stride + kx * p.dil;
-                        float v[8];
-                        load_vec<bf16, 8>(rowp + (size_t)ix * p.CC, v);
+                    for (int ky = 0; ky < K; ++ky) ldw8(wcv + (uint32_t)(ky * K + kx) * tapb, wc[ky]);
+                    const uint32_t col = tile + (uint32_t)(sy * S) * rowb + (uint32_t)(sx * S + kx) * pxb;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(v[j], wv[j], acc[q][j]);
+                    for (int i = 0; i < ROWS; ++i) {
+                        float2 v[4];
+                        cvt8(lds16(col + (uint32_t)i * rowb), v);
+#pragma unroll
+                        for (int q = 0; q < DW_P; ++q) {
+                            const int ky = i - q * S;
+                            if (ky >= 0 && ky < K) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[q][j] = ffma2(v[j], wc[ky][j], acc[q][j]);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int ky = 0; ky < K; ++ky) {
+#pragma unroll 1
+                    for (int kx = 0; kx < K; ++kx) {
+                        float2 w[4];
+                        ldw8(wcv + (uint32_t)(ky * K + kx) * tapb, w);
+                        const uint32_t tp = tile + (uint32_t)(sy * p.stride + ky * p.dil) * rowb + (uint32_t)(sx * p.stride + kx * p.dil) * pxb;
+#pragma unroll
+                        for (int q = 0; q < DW_P; ++q) {
+                            float2 v[4];
+                            cvt8(lds16(tp + (uint32_t)(q * p.stride) * rowb), v);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[q][j] = ffma2(v[j], w[j], acc[q][j]);
+                        }
                     }
                 }
             }
-            const int c0 = c_base + cv * 8;
-            bf16 *orow = p.out + (((size_t)n * p.OH + oy) * p.OW + oxs) * p.out_cs + c0;
-            if (epi) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float sc = p.scale ? p.scale[c0 + j] : 1.f, sh = p.shift ? p.shift[c0 + j] : 0.f;
-#pragma unroll
-                    for (int q = 0; q < DW_P; ++q) acc[q][j] = apply_act(acc[q][j] * sc + sh, p.act);
-                }
-            }
+            bf16 *op = p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.out_cs + c0;
 #pragma unroll
             for (int q = 0; q < DW_P; ++q) {
-                if (oxs + q >= p.OW) break;
-                store_vec<bf16, 8>(orow + (size_t)q * p.out_cs, acc[q]);
-            }
-            if (p.stats) {  // optional fused statistics of the stored values (off by default, see __init__.py)
+                if (oy + q >= p.OH) break;
+                if (epi) {  // folded BN / activation (eval mode): constants come from L1
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float s1 = 0.f, s2 = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 sc = p.scale ? *reinterpret_cast<const float2 *>(p.scale + c0 + 2 * j) : make_float2(1.f, 1.f);
+                        const float2 sh = p.shift ? *reinterpret_cast<const float2 *>(p.shift + c0 + 2 * j) : make_float2(0.f, 0.f);
+                        const float2 e = ffma2(acc[q][j], sc, sh);
+                        acc[q][j] = make_float2(apply_act(e.x, p.act), apply_act(e.y, p.act));
+                    }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(acc[q][0].x, acc[q][0].y);
+                o.y = pack_bf16x2(acc[q][1].x, acc[q][1].y);
+                o.z = pack_bf16x2(acc[q][2].x, acc[q][2].y);
+                o.w = pack_bf16x2(acc[q][3].x, acc[q][3].y);
+                *reinterpret_cast<uint4 *>(op + (size_t)q * p.OW * p.out_cs) = o;
+                if (STATS) {  // statistics of the values as stored (bf16-rounded)
+                    float2 r[4];
+                    cvt8(o, r);
 #pragma unroll
-                    for (int q = 0; q < DW_P; ++q)
-                        if (oxs + q < p.OW) {
-                            const float v = __bfloat162float(__float2bfloat16_rn(acc[q][j]));
-                            s1 += v;
-                            s2 = fmaf(v, v, s2);
-                        }
-                    atomicAdd(&p.stats[c0 + j], (double)s1);
-                    atomicAdd(&p.stats[p.C + c0 + j], (double)s2);
+                    for (int j = 0; j < 4; ++j) {
+                        st1[j].x += r[j].x;
+                        st1[j].y += r[j].y;
+                        st2[j] = ffma2(r[j], r[j], st2[j]);
+                    }
                 }
             }
         }
         __syncthreads();  // everyone is done with tiles[buf]; it may be refilled two iterations from now
     }
+    if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&ssm[cv * 8 + 2 * j], st1[j].x);
+            atomicAdd(&ssm[cv * 8 + 2 * j + 1], st1[j].y);
+            atomicAdd(&ssm[CC + cv * 8 + 2 * j], st2[j].x);
+            atomicAdd(&ssm[CC + cv * 8 + 2 * j + 1], st2[j].y);
+        }
+        __syncthreads();
+        for (int i = tid; i < CC; i += blockDim.x) {
+            atomicAdd(&p.stats[c_base + i], (double)ssm[i]);
+            atomicAdd(&p.stats[p.C + c_base + i], (double)ssm[CC + i]);
+        }
+    }
 }
 
-// ---- weight gradient on tiles: thread = (tap, channel vector, pixel lane); persistent over the CTA's patches
+// ---- weight gradient on tiles.  Thread = (channel vector, kernel-column group, lane); lanes walk vertical strips of DW_P
+// dz rows.  KC = kernel columns per thread (1: one kernel column, K taps in registers).
+// dz and x patches arrive by TMA (zero fill outside the image => no bounds checks); partial sums stay in registers across
+// the CTA's patches, are merged through shared-memory atomics and flushed once with fp32 global atomics.
 struct DwW {
     int N, IH, IW, OH, OW, C;
     int CC, nchunks;
     int TH, TW, ITH, ITW;
     int stride, dil, pad;
     int tiles_x, tiles_y;
+    int lanes;  // lanes per (cv, column group); blockDim.x = lanes * CVn * (K / KC)
     float *dw;  // [C][k*k]
 };
 
-template <int K>
-__global__ void __launch_bounds__(256) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap map_x,
-                                                            const __grid_constant__ CUtensorMap map_dz, const DwW p) {
+template <int K, int S, int KC>
+__global__ void __launch_bounds__(256, 2) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                               const __grid_constant__ CUtensorMap map_dz, const DwW p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
     const size_t xt_bytes = (size_t)p.ITH * p.ITW * p.CC * 2, zt_bytes = (size_t)p.TH * p.TW * p.CC * 2;
     const size_t xs = (xt_bytes + 127) & ~(size_t)127, zs = (zt_bytes + 127) & ~(size_t)127;
     bf16 *xt[2] = {reinterpret_cast<bf16 *>(base), reinterpret_cast<bf16 *>(base + xs + zs)};            // [ITH][ITW][CC]
     bf16 *zt[2] = {reinterpret_cast<bf16 *>(base + xs), reinterpret_cast<bf16 *>(base + 2 * xs + zs)};   // [TH][TW][CC]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(base + 2 * (xs + zs));                                  // [2]
+    float *dsum = reinterpret_cast<float *>(base + 2 * (xs + zs));                                       // [CC][K*K]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(dsum + p.CC * K * K);                                   // [2]
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y, c_base = chunk * p.CC;
     const int CVn = p.CC / 8;
-    const int pairs = K * K * CVn;          // (tap, cv) pairs
-    const int PLn = blockDim.x / pairs;     // pixel lanes per pair (>= 1 guaranteed by the host)
-    const int pair = tid % pairs, pl = tid / pairs;
-    const int tap = pair / CVn, cv = pair - tap * CVn;
-    const int ky = tap / K, kx = tap - ky * K;
-    const bool active = pl < PLn;
-    float acc[8];
+    constexpr int NG = K / KC;                 // column groups
+    const int G = CVn * NG;
+    const int grp = tid % G, lane = tid / G;
+    const int cv = grp % CVn, kx0 = (grp / CVn) * KC;
+    const int L = p.lanes;
+    const int CC = p.CC, ITW = p.ITW, TW = p.TW;
+    const uint32_t pxb = (uint32_t)CC * 2, rowb = (uint32_t)ITW * pxb, zrowb = (uint32_t)TW * pxb;  // byte pitches
+    float2 acc[KC * K][4];  // [kxi * K + ky]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int i = 0; i < KC * K; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int total = tiles_per_img * p.N;
@@ -226,35 +324,73 @@ __global__ void __launch_bounds__(256) dw_wgrad_tile_kernel(const __grid_constan
         dmbar_init(&bar[0], 1);
         dmbar_init(&bar[1], 1);
     }
+    for (int i = tid; i < CC * K * K; i += blockDim.x) dsum[i] = 0.f;
     __syncthreads();
     if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+    const int nstrips = (p.TH / DW_P) * TW;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int buf = it & 1;
         if (tid == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
         dmbar_wait(&bar[buf], (it >> 1) & 1);
-        if (active) {
-            // out-of-image dz pixels are zero-filled by TMA, so the whole patch can be walked unconditionally
-            const bf16 *zb = zt[buf] + cv * 8;
-            const bf16 *xb = xt[buf] + ((size_t)(ky * p.dil) * p.ITW + kx * p.dil) * p.CC + cv * 8;
-            for (int sy = 0; sy < p.TH; ++sy) {
-                const bf16 *zr = zb + (size_t)sy * p.TW * p.CC;
-                const bf16 *xr = xb + (size_t)(sy * p.stride) * p.ITW * p.CC;
-                for (int sx = pl; sx < p.TW; sx += PLn) {
-                    float g[8], v[8];
-                    load_vec<bf16, 8>(zr + (size_t)sx * p.CC, g);
-                    load_vec<bf16, 8>(xr + (size_t)(sx * p.stride) * p.CC, v);
+        const uint32_t zb = dsmem_u32(buf ? zt[1] : zt[0]) + cv * 16;
+        const uint32_t xb = dsmem_u32(buf ? xt[1] : xt[0]) + cv * 16;
+        for (int s = lane; s < nstrips; s += L) {
+            const int sx = s % TW, sy = (s / TW) * DW_P;
+            float2 g[DW_P][4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], v[j], acc[j]);
+            for (int q = 0; q < DW_P; ++q) cvt8(lds16(zb + (uint32_t)(sy + q) * zrowb + (uint32_t)sx * pxb), g[q]);
+            if constexpr (S > 0) {
+                constexpr int ROWS = (DW_P - 1) * S + K;
+#pragma unroll
+                for (int kxi = 0; kxi < KC; ++kxi) {
+                    const uint32_t col = xb + (uint32_t)(sy * S) * rowb + (uint32_t)(sx * S + kx0 + kxi) * pxb;
+#pragma unroll
+                    for (int i = 0; i < ROWS; ++i) {
+                        float2 v[4];
+                        cvt8(lds16(col + (uint32_t)i * rowb), v);
+#pragma unroll
+                        for (int q = 0; q < DW_P; ++q) {
+                            const int ky = i - q * S;
+                            if (ky >= 0 && ky < K) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[kxi * K + ky][j] = ffma2(g[q][j], v[j], acc[kxi * K + ky][j]);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kxi = 0; kxi < KC; ++kxi) {
+#pragma unroll
+                    for (int ky = 0; ky < K; ++ky) {
+                        const uint32_t tp = xb + (uint32_t)(sy * p.stride + ky * p.dil) * rowb + (uint32_t)(sx * p.stride + (kx0 + kxi) * p.dil) * pxb;
+#pragma unroll
+                        for (int q = 0; q < DW_P; ++q) {
+                            float2 v[4];
+                            cvt8(lds16(tp + (uint32_t)(q * p.stride) * rowb), v);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[kxi * K + ky][j] = ffma2(g[q][j], v[j], acc[kxi * K + ky][j]);
+                        }
+                    }
                 }
             }
         }
         __syncthreads();  // everyone done with buffer `buf` before it is refilled
     }
-    if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&p.dw[(size_t)(c_base + cv * 8 + j) * K * K + tap], acc[j]);
-    }
+    for (int kxi = 0; kxi < KC; ++kxi)
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int tap = ky * K + kx0 + kxi;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&dsum[(cv * 8 + 2 * j) * K * K + tap], acc[kxi * K + ky][j].x);
+                atomicAdd(&dsum[(cv * 8 + 2 * j + 1) * K * K + tap], acc[kxi * K + ky][j].y);
+            }
+        }
+    __syncthreads();
+    for (int i = tid; i < CC * K * K; i += blockDim.x) atomicAdd(&p.dw[(size_t)c_base * K * K + i], dsum[i]);
 }
 
 // ---- strided data gradient on tiles: dx[iy,ix] = sum_{taps with (iy+pad-ky*dil) % s == 0 ...} dz[(iy+pad-ky*dil)/s, ...] * w[ky,kx]
@@ -372,10 +508,10 @@ struct TilePlan {
 static bool plan_tiles(int C, int ks, int stride, int dil, size_t extra_per_cc, size_t budget, TilePlan &pl) {
     int cc = pick_cc(C);
     if (!cc) return false;
-    const int th_opts[3] = {8, 4, 2}, tw = stride == 1 ? 32 : 16;
+    const int th_opts[2] = {8, 4}, tw = stride == 1 ? 32 : 16;  // multiples of DW_P
     for (int cci = cc; cci >= 8; cci -= 8) {
         if (C % cci) continue;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 2; ++i) {
             int th = th_opts[i];
             int ith = (th - 1) * stride + (ks - 1) * dil + 1, itw = (tw - 1) * stride + (ks - 1) * dil + 1;
             size_t bytes = (size_t)ith * itw * cci * 2 + extra_per_cc * cci + 1024;
@@ -440,31 +576,34 @@ extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks
     CUtensorMap mx;
     if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH)) return NASB_ERR_UNSUPPORTED;
     const size_t tile_b = ((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127;
-    size_t smem = 2 * tile_b + (size_t)ks * ks * pl.CC * 4 + 16 + 256;
+    size_t smem = 2 * tile_b + (size_t)ks * ks * pl.CC * 4 + (size_t)2 * pl.CC * 4 + 16 + 256;
+    const int CVn = pl.CC / 8, nstrips = (pl.TH / DW_P) * pl.TW;
+    int L = 64;
+    while (L * CVn > 256 || L > nstrips) L >>= 1;
+    const int threads = L * CVn;
+    typedef void (*Kern)(const CUtensorMap, const DwT);
+    static const Kern kerns[2][3][2] = {
+        {{dw_tile_kernel<3, 0, false>, dw_tile_kernel<3, 0, true>}, {dw_tile_kernel<3, 1, false>, dw_tile_kernel<3, 1, true>},
+         {dw_tile_kernel<3, 2, false>, dw_tile_kernel<3, 2, true>}},
+        {{dw_tile_kernel<5, 0, false>, dw_tile_kernel<5, 0, true>}, {dw_tile_kernel<5, 1, false>, dw_tile_kernel<5, 1, true>},
+         {dw_tile_kernel<5, 2, false>, dw_tile_kernel<5, 2, true>}}};
+    static bool cfg[2][3][2] = {};
+    const int ki = ks == 3 ? 0 : 1, si = (dil == 1 && stride <= 2) ? stride : 0, ti = stats ? 1 : 0;
+    Kern kern = kerns[ki][si][ti];
+    if (!cfg[ki][si][ti]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+            return NASB_ERR_UNSUPPORTED;
+        cfg[ki][si][ti] = true;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > 6) per_sm = 6;
     long long total = (long long)p.tiles_x * p.tiles_y * x->n;
-    int per_sm = (int)((200 * 1024) / smem);
-    if (per_sm > 3) per_sm = 3;
-    if (per_sm < 1) per_sm = 1;
     long long gx = (long long)NASB_SM_COUNT * per_sm / p.nchunks;
     if (gx < 1) gx = 1;
     if (gx > total) gx = total;
     dim3 grid((unsigned)gx, p.nchunks);
-    static bool cfg3 = false, cfg5 = false;
-    if (ks == 3) {
-        if (!cfg3) {
-            if (cudaFuncSetAttribute(dw_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
-                return NASB_ERR_UNSUPPORTED;
-            cfg3 = true;
-        }
-        dw_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, p);
-    } else {
-        if (!cfg5) {
-            if (cudaFuncSetAttribute(dw_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
-                return NASB_ERR_UNSUPPORTED;
-            cfg5 = true;
-        }
-        dw_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, p);
-    }
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(mx, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -477,8 +616,6 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     TilePlan pl;
     // extra per channel: the dz patch (TH*TW <= 8*32 pixels) * 2 bytes
     if (!plan_tiles(x->c, ks, stride, dil, (size_t)8 * 32 * 2, 48 * 1024, pl)) return NASB_ERR_UNSUPPORTED;  // x2 buffers
-    const int pairs = ks * ks * (pl.CC / 8);
-    if (pairs > 256) return NASB_ERR_UNSUPPORTED;
     if (npix(*dz) == 0) return 0;
     DwW p{};
     p.N = x->n;
@@ -501,31 +638,34 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     p.dw = dweight;
     CUtensorMap mx, mz;
     if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH) || !make_map4(&mz, dz, pl.CC, pl.TW, pl.TH)) return NASB_ERR_UNSUPPORTED;
-    size_t smem = 2 * ((((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127) + (((size_t)pl.TH * pl.TW * pl.CC * 2 + 127) & ~(size_t)127)) + 16 + 256;
+    size_t smem = 2 * ((((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127) + (((size_t)pl.TH * pl.TW * pl.CC * 2 + 127) & ~(size_t)127)) +
+                  (size_t)pl.CC * ks * ks * 4 + 16 + 256;
+    const int G = (pl.CC / 8) * ks, nstrips = (pl.TH / DW_P) * pl.TW;
+    int L = 64;
+    while (L * G > 256 || L > nstrips) L >>= 1;
+    if (L < 1) return NASB_ERR_UNSUPPORTED;
+    p.lanes = L;
+    const int threads = L * G;
+    typedef void (*Kern)(const CUtensorMap, const CUtensorMap, const DwW);
+    static const Kern kerns[2][3] = {{dw_wgrad_tile_kernel<3, 0, 1>, dw_wgrad_tile_kernel<3, 1, 1>, dw_wgrad_tile_kernel<3, 2, 1>},
+                                     {dw_wgrad_tile_kernel<5, 0, 1>, dw_wgrad_tile_kernel<5, 1, 1>, dw_wgrad_tile_kernel<5, 2, 1>}};
+    static bool cfg[2][3] = {};
+    const int ki = ks == 3 ? 0 : 1, si = (dil == 1 && stride <= 2) ? stride : 0;
+    Kern kern = kerns[ki][si];
+    if (!cfg[ki][si]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess)
+            return NASB_ERR_UNSUPPORTED;
+        cfg[ki][si] = true;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > 6) per_sm = 6;
     long long total = (long long)p.tiles_x * p.tiles_y * x->n;
-    int per_sm = (int)((200 * 1024) / smem);
-    if (per_sm > 3) per_sm = 3;
-    if (per_sm < 1) per_sm = 1;
     long long gx = (long long)NASB_SM_COUNT * per_sm / p.nchunks;
     if (gx < 1) gx = 1;
     if (gx > total) gx = total;
     dim3 grid((unsigned)gx, p.nchunks);
-    static bool cfg3 = false, cfg5 = false;
-    if (ks == 3) {
-        if (!cfg3) {
-            if (cudaFuncSetAttribute(dw_wgrad_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
-                return NASB_ERR_UNSUPPORTED;
-            cfg3 = true;
-        }
-        dw_wgrad_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, mz, p);
-    } else {
-        if (!cfg5) {
-            if (cudaFuncSetAttribute(dw_wgrad_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
-                return NASB_ERR_UNSUPPORTED;
-            cfg5 = true;
-        }
-        dw_wgrad_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mx, mz, p);
-    }
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(mx, mz, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
