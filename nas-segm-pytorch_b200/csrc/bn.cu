@@ -1,6 +1,7 @@
 // bn.cu -- BatchNorm2d pieces: eval-mode folding, training-mode batch statistics (+ running-stat update), the
 // affine+activation pass, and the backward of y = act(gamma*xhat + beta).  All reductions accumulate in fp64
 // (per-thread and across CTAs through fp64 atomics), so the fp32 results do not depend on summation order.
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -266,15 +267,25 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs
     }
 }
 
-// dgamma += sum g*xhat ; dbeta += sum g ; coef[0..C) = mean g ; coef[C..2C) = mean g*xhat  (fp32, aliased after ws)
-__global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, float *dgamma, float *dbeta, float *coef) {
+// dgamma += sum g*xhat ; dbeta += sum g ; coef[0..C) = mean g ; coef[C..2C) = mean g*xhat  (fp32, aliased after ws);
+// k (optional, [4][C]): the per-channel constants of bn_bwd_dz_bf16_kernel (mask scale, mask shift, A, B)
+__global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, float *dgamma, float *dbeta, float *coef,
+                                       const float *scale, const float *shift, const float *mean, const float *rstd, float *k) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s1 = ws[c], s2 = ws[C + c];
     if (dbeta) dbeta[c] += (float)s1;
     if (dgamma) dgamma[c] += (float)s2;
-    coef[c] = (float)(s1 / (double)P);
-    coef[C + c] = (float)(s2 / (double)P);
+    const float k1 = (float)(s1 / (double)P), k2 = (float)(s2 / (double)P);
+    coef[c] = k1;
+    coef[C + c] = k2;
+    if (k) {
+        const float s = scale ? scale[c] : 1.f, r = rstd[c];
+        k[c] = s;
+        k[C + c] = shift[c];
+        k[2 * C + c] = -s * k2 * r;
+        k[3 * C + c] = s * (k2 * r * mean[c] - k1);
+    }
 }
 
 template <typename T, int V>
@@ -402,6 +413,172 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_dz_fixed_kernel(const T *dy, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 streaming passes (speed mode).  Same thread layout as the *_fixed kernels (thread = fixed 8-channel vector, pixel
+// lane), but FOUR pixels are in flight per thread (raw 16-byte registers, converted after all loads were issued): with
+// ~1.6 us of loaded HBM latency the two-pixel versions ran at 58-70 % of the DRAM peak on long_scoreboard stalls (ncu,
+// profiles/r1_iter_sections_summary.txt).  Arithmetic is packed fp32 (FFMA2).  DESC walks the tensor from its last pixel
+// to its first: the pass that follows a producer which wrote the tensor front-to-back then starts on the part still in L2.
+constexpr int BN_PX = 4;
+
+__device__ __forceinline__ uint4 ldg16(const bf16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+
+__device__ __forceinline__ float2 act2(float2 v, int act) { return make_float2(apply_act(v.x, act), apply_act(v.y, act)); }
+// g where lo < ypre < hi, else 0
+__device__ __forceinline__ float2 gate2(float2 g, float2 ypre, float lo, float hi) {
+    return make_float2((ypre.x > lo && ypre.x < hi) ? g.x : 0.f, (ypre.y > lo && ypre.y < hi) ? g.y : 0.f);
+}
+__device__ __forceinline__ void ldc8(const float *p, int c0, float def, float2 (&o)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = p ? make_float2(p[c0 + 2 * j], p[c0 + 2 * j + 1]) : make_float2(def, def);
+}
+
+template <bool DESC>
+__global__ void __launch_bounds__(256, 4) affine_act_bf16_kernel(const bf16 *z, int z_cs, const float *scale, const float *shift,
+                                                                 int act, bf16 *y, int y_cs, long long P, int C) {
+    const int CV = C / 8, PL = blockDim.x / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
+    if (pl >= PL) return;
+    float2 s[4], b[4];
+    ldc8(scale, c0, 1.f, s);
+    ldc8(shift, c0, 0.f, b);
+    const long long G = (long long)gridDim.x * PL;
+    for (long long m0 = (long long)blockIdx.x * PL + pl; m0 < P; m0 += BN_PX * G) {
+        uint4 r[BN_PX];
+        long long m[BN_PX];
+#pragma unroll
+        for (int k = 0; k < BN_PX; ++k) {
+            const long long mm = m0 + k * G;
+            m[k] = mm < P ? (DESC ? P - 1 - mm : mm) : -1;
+            if (m[k] >= 0) r[k] = ldg16(z + m[k] * z_cs + c0);
+        }
+#pragma unroll
+        for (int k = 0; k < BN_PX; ++k) {
+            if (m[k] < 0) continue;
+            float2 v[4];
+            cvt8(r[k], v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = act2(ffma2(v[j], s[j], b[j]), act);
+            uint4 o;
+            o.x = pack_bf16x2(v[0].x, v[0].y);
+            o.y = pack_bf16x2(v[1].x, v[1].y);
+            o.z = pack_bf16x2(v[2].x, v[2].y);
+            o.w = pack_bf16x2(v[3].x, v[3].y);
+            *reinterpret_cast<uint4 *>(y + m[k] * y_cs + c0) = o;
+        }
+    }
+}
+
+// ws[0..C) += sum g ; ws[C..2C) += sum g*xhat, g = dy gated by lo < v*k_s + k_b < hi, xhat = (v - mu) * rs.
+// Per thread the raw moments sum g and sum g*v are accumulated (two constant vectors instead of four in registers); the
+// CTA converts its partial to the centred form in fp64 before the atomics.  Slabs are walked from the END of the tensor.
+__global__ void __launch_bounds__(256, 3) bn_bwd_sums_bf16_kernel(const bf16 *dy, int dy_cs, const bf16 *yz, int yz_cs,
+                                                                  const float *k_s, const float *k_b, const float *mu,
+                                                                  const float *rs, float lo, float hi, long long P, int C,
+                                                                  double *ws, long long rows_per_cta) {
+    extern __shared__ float red_sm[];  // [2][PL][C]
+    const long long e1 = P - (long long)blockIdx.x * rows_per_cta;  // this CTA's slab is [e0, e1), counted from the end
+    const long long e0 = e1 - rows_per_cta > 0 ? e1 - rows_per_cta : 0;
+    const int CV = C / 8, PL = blockDim.x / CV;
+    const int t = threadIdx.x, cv = t % CV, pl = t / CV, c0 = cv * 8;
+    float2 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = b[j] = make_float2(0.f, 0.f);
+    if (pl < PL) {
+        float2 ks[4], kb[4];
+        ldc8(k_s, c0, 1.f, ks);
+        ldc8(k_b, c0, 0.f, kb);
+        for (long long m0 = e1 - 1 - pl; m0 >= e0; m0 -= (long long)BN_PX * PL) {
+            uint4 rg[BN_PX], rv[BN_PX];
+            bool ok[BN_PX];
+#pragma unroll
+            for (int k = 0; k < BN_PX; ++k) {
+                const long long m = m0 - (long long)k * PL;
+                ok[k] = m >= e0;
+                if (ok[k]) {
+                    rg[k] = ldg16(dy + m * dy_cs + c0);
+                    rv[k] = ldg16(yz + m * yz_cs + c0);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BN_PX; ++k) {
+                if (!ok[k]) continue;
+                float2 g[4], v[4];
+                cvt8(rg[k], g);
+                cvt8(rv[k], v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 gm = gate2(g[j], ffma2(v[j], ks[j], kb[j]), lo, hi);
+                    a[j].x += gm.x;
+                    a[j].y += gm.y;
+                    b[j] = ffma2(gm, v[j], b[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red_sm[(size_t)pl * C + c0 + 2 * j] = a[j].x;
+            red_sm[(size_t)pl * C + c0 + 2 * j + 1] = a[j].y;
+            red_sm[(size_t)(PL + pl) * C + c0 + 2 * j] = b[j].x;
+            red_sm[(size_t)(PL + pl) * C + c0 + 2 * j + 1] = b[j].y;
+        }
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < PL; ++i) {
+            s1 += (double)red_sm[(size_t)i * C + c];
+            s2 += (double)red_sm[(size_t)(PL + i) * C + c];
+        }
+        atomicAdd(&ws[c], s1);
+        atomicAdd(&ws[C + c], (double)rs[c] * (s2 - (double)mu[c] * s1));
+    }
+}
+
+// dz = sg * gate(g) + A*v + B   (training mode only: sg = scale, A = -scale*k2*rstd, B = scale*(k2*rstd*mean - k1)).
+// The constants are prepared by bn_bwd_finalize_kernel, so the stream kernel holds 4 vectors in registers, not 7.
+__global__ void __launch_bounds__(256, 3) bn_bwd_dz_bf16_kernel(const bf16 *dy, int dy_cs, const bf16 *yz, int yz_cs,
+                                                                const float *k, float lo, float hi, bf16 *dz,
+                                                                int dz_cs, long long P, int C) {
+    const int CV = C / 8, PL = blockDim.x / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
+    if (pl >= PL) return;
+    float2 sg[4], mb[4], A[4], B[4];  // training mode: the mask's pre-activation is z*scale + shift, so its scale is sg
+    ldc8(k, c0, 1.f, sg);
+    ldc8(k + C, c0, 0.f, mb);
+    ldc8(k + 2 * C, c0, 0.f, A);
+    ldc8(k + 3 * C, c0, 0.f, B);
+    const long long G = (long long)gridDim.x * PL;
+    for (long long m0 = (long long)blockIdx.x * PL + pl; m0 < P; m0 += BN_PX * G) {
+        uint4 rg[BN_PX], rv[BN_PX];
+        bool ok[BN_PX];
+#pragma unroll
+        for (int kk = 0; kk < BN_PX; ++kk) {
+            const long long m = m0 + kk * G;
+            ok[kk] = m < P;
+            if (ok[kk]) {
+                rg[kk] = ldg16(dy + m * dy_cs + c0);
+                rv[kk] = ldg16(yz + m * yz_cs + c0);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < BN_PX; ++kk) {
+            if (!ok[kk]) continue;
+            float2 g[4], v[4];
+            cvt8(rg[kk], g);
+            cvt8(rv[kk], v);
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 gm = gate2(g[j], ffma2(v[j], sg[j], mb[j]), lo, hi);
+                const float2 r = ffma2(gm, sg[j], ffma2(A[j], v[j], B[j]));
+                o[j] = pack_bf16x2(r.x, r.y);
+            }
+            *reinterpret_cast<uint4 *>(dz + (m0 + kk * G) * dz_cs + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 static inline bool bn_safe() {
     static int v = -1;
     if (v < 0) v = getenv("NASB_BN_SAFE") ? atoi(getenv("NASB_BN_SAFE")) : 0;
@@ -463,8 +640,8 @@ extern "C" int nasb_bn_fold(const float *gamma, const float *beta, const float *
     return 0;
 }
 
-// 2*C doubles for the sums, then 2*C floats for the backward coefficients
-extern "C" long long nasb_bn_stats_workspace(int C) { return (long long)C * (2 * 8 + 2 * 4); }
+// 2*C doubles for the sums, 2*C floats for the backward coefficients, 4*C floats for the dz constants
+extern "C" long long nasb_bn_stats_workspace(int C) { return (long long)C * (2 * 8 + 2 * 4 + 4 * 4); }
 
 extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
                              float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
@@ -520,8 +697,9 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
     {
         int blocks;
         if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
-            affine_act_fixed_kernel<bf16, 8><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
-                                                                     (bf16 *)y->ptr, y->cstride, P, C);
+            // descending: z was just written front-to-back by the convolution, its tail is still in L2
+            affine_act_bf16_kernel<true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+                                                                 (bf16 *)y->ptr, y->cstride, P, C);
             NASB_CHECK_LAUNCH();
             return 0;
         }
@@ -572,7 +750,29 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
     int C = dy->c;
     double *ws = (double *)workspace;
     float *coef = (float *)(ws + 2 * C);
+    float *kdz = coef + 2 * C;
     bool need_sums = training || dgamma || dbeta;
+    const float lo = act == NASB_ACT_NONE ? -INFINITY : 0.f, hi = act == NASB_ACT_RELU6 ? 6.f : INFINITY;
+    {
+        // speed mode (bf16, training statistics): 4-pixel-in-flight packed kernels
+        int blocks, dzblocks;
+        long long rows;
+        size_t smem;
+        if (training && !(bn_safe() & 4) && dy->dtype == NASB_BF16 && vec_ok(*dy, 8) && vec_ok(*z, 8) && vec_ok(*dz, 8) &&
+            vec_reduce_cfg<8>(C, P, blocks, rows, smem) && fixed_cfg(C, 8, P, dzblocks)) {
+            cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST);
+            if (e != cudaSuccess) return (int)e;
+            bn_bwd_sums_bf16_kernel<<<blocks, 256, smem, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
+                                                               scale, shift, save_mean, save_rstd, lo, hi, P, C, ws, rows);
+            NASB_CHECK_LAUNCH();
+            bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef, scale, shift, save_mean, save_rstd, kdz);
+            NASB_CHECK_LAUNCH();
+            bn_bwd_dz_bf16_kernel<<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
+                                                            kdz, lo, hi, (bf16 *)dz->ptr, dz->cstride, P, C);
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     if (need_sums) {
         cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST);
         if (e != cudaSuccess) return (int)e;
@@ -602,7 +802,7 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
                                                                     gamma, beta, P, C, ws, rows);
         }
         NASB_CHECK_LAUNCH();
-        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef);
+        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef, nullptr, nullptr, nullptr, nullptr, nullptr);
         NASB_CHECK_LAUNCH();
     }
     {

@@ -126,6 +126,28 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
     return r;
 }
 
+// ---- packed helpers: 8 bf16 channels (one 16-byte LDS) -> four float2, and the Blackwell packed fp32 FMA (FFMA2)
+__device__ __forceinline__ void cvt8(const uint4 &r, float2 (&v)[4]) {
+    v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
+    v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
+}
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
 // block-wide sum of doubles through shared memory; result valid in thread 0.
 template <int NT>
 __device__ __forceinline__ double block_sum(double v, double *sm) {

@@ -62,23 +62,6 @@ struct DwT {
 
 constexpr int DW_P = 4;  // output pixels per strip (a vertical strip: 4 consecutive rows of one column)
 
-// ---- packed helpers: 8 bf16 channels (one 16-byte LDS) -> four float2, and the Blackwell packed fp32 FMA (FFMA2)
-__device__ __forceinline__ void cvt8(const uint4 &r, float2 (&v)[4]) {
-    v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
-    v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
-    v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
-    v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
-}
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
-    uint64_t ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
-}
 // explicit shared-space 16-byte loads on 32-bit shared addresses (a generic pointer derived through uintptr_t arithmetic
 // makes the compiler emit generic LD instead of LDS)
 __device__ __forceinline__ uint4 lds16(uint32_t a) {
@@ -92,10 +75,6 @@ __device__ __forceinline__ void ldw8(uint32_t a, float2 (&w)[4]) {
     w[1] = make_float2(__uint_as_float(lo.z), __uint_as_float(lo.w));
     w[2] = make_float2(__uint_as_float(hi.x), __uint_as_float(hi.y));
     w[3] = make_float2(__uint_as_float(hi.z), __uint_as_float(hi.w));
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&t);
 }
 
 // Persistent: CTA (x, chunk) walks the patches x, x + gridDim.x, ... of its channel chunk with two shared-memory buffers; the

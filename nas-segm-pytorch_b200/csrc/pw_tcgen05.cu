@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
     }
     const uint32_t idesc = make_idesc_bf16(npb);
     const int row = warp * 32 + lane;  // TMEM lane == row of the tile owned by this thread
+    const bool affine = p.scale || p.shift || p.act != NASB_ACT_NONE;
+    const int st_ch = tid & 7, st_rg = tid >> 3;  // statistics: this thread's 8-channel chunk and first row
+    const bool st_on = st_ch * 8 < nblk;
+    float2 st1[4], st2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st1[j] = st2[j] = make_float2(0.f, 0.f);
 
     uint32_t it = 0;
     for (int tile = tile0; tile < ntiles; tile += tstride, ++it) {
@@ -117,12 +123,15 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         // ---- epilogue: TMEM -> registers -> (BN fold / bias, activation, residual) -> bf16 -> swizzled smem
         const long long m = (long long)m0 + row;
         const bool row_ok = m < p.M;
+        uint8_t *orow = sO + (size_t)row * 128;
 #pragma unroll 1
         for (int c0 = 0; c0 < npb; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (affine) {  // uniform: raw accumulator goes out untouched for training-mode z and for data gradients
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+            }
             if (p.res && row_ok) {
                 const bf16 *rp = p.res + m * p.res_cs + n0 + c0;
                 if (c0 + 16 <= nblk) {
@@ -138,29 +147,20 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
                         if (c0 + j < nblk) v[j] += __bfloat162float(rp[j]);
                 }
             }
-            if (p.stats) {  // statistics of the value as stored (bf16-rounded), rows beyond M excluded
-                float q[16], q2[16];
+            if (p.stats && !row_ok) {  // rows beyond M must not count in the statistics read back from the tile
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    q[j] = row_ok ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
-                    q2[j] = q[j] * q[j];
-                }
-                int col;
-                float t1 = warp_colsum16(q, lane, col), t2 = warp_colsum16(q2, lane, col);
-                if (!(lane & 1) && c0 + col < nblk) {
-                    atomicAdd(&s_sum[c0 + col], t1);
-                    atomicAdd(&s_sq[c0 + col], t2);
-                }
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
             const int ch = c0 >> 3;  // first 16-byte chunk inside the 128-byte row
-            uint8_t *orow = sO + (size_t)row * 128;
             uint4 q0, q1;
-            bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                e0[j] = __float2bfloat16_rn(v[j]);
-                e1[j] = __float2bfloat16_rn(v[8 + j]);
-            }
+            q0.x = pack_bf16x2(v[0], v[1]);
+            q0.y = pack_bf16x2(v[2], v[3]);
+            q0.z = pack_bf16x2(v[4], v[5]);
+            q0.w = pack_bf16x2(v[6], v[7]);
+            q1.x = pack_bf16x2(v[8], v[9]);
+            q1.y = pack_bf16x2(v[10], v[11]);
+            q1.z = pack_bf16x2(v[12], v[13]);
+            q1.w = pack_bf16x2(v[14], v[15]);
             *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
             *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
         }
@@ -170,12 +170,48 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         if (tid == 0) {
             tma_store_2d(&map_o, sO, n0, m0);
             tma_store_commit();
-            tma_store_wait_read();  // smem tile may be overwritten once the bulk store has read it
         }
+        if (p.stats && st_on) {
+            // statistics of the tile AS STORED (bf16), read back from shared memory while the bulk store drains: thread =
+            // (16-byte channel chunk, row group), 8 rows per tile, partials stay in registers until the CTA is done
+#pragma unroll
+            for (int k = 0; k < TILE_M / 16; ++k) {
+                const int r = st_rg + 16 * k;
+                float2 q[4];
+                cvt8(*reinterpret_cast<const uint4 *>(sO + (size_t)r * 128 + ((st_ch ^ (r & 7)) << 4)), q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st1[j].x += q[j].x;
+                    st1[j].y += q[j].y;
+                    st2[j] = ffma2(q[j], q[j], st2[j]);
+                }
+            }
+        }
+        if (tid == 0) tma_store_wait_read();  // smem tile may be overwritten once the bulk store has read it
         __syncthreads();
     }
     if (tid == 0) tma_store_wait_all();
     if (p.stats) {
+        // merge the four row groups that share a chunk inside each warp (lanes c, c+8, c+16, c+24), then the warps
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int off = 8; off <= 16; off <<= 1) {
+                st1[j].x += __shfl_xor_sync(0xffffffffu, st1[j].x, off);
+                st1[j].y += __shfl_xor_sync(0xffffffffu, st1[j].y, off);
+                st2[j].x += __shfl_xor_sync(0xffffffffu, st2[j].x, off);
+                st2[j].y += __shfl_xor_sync(0xffffffffu, st2[j].y, off);
+            }
+        }
+        if (lane < 8 && st_on) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&s_sum[st_ch * 8 + 2 * j], st1[j].x);
+                atomicAdd(&s_sum[st_ch * 8 + 2 * j + 1], st1[j].y);
+                atomicAdd(&s_sq[st_ch * 8 + 2 * j], st2[j].x);
+                atomicAdd(&s_sq[st_ch * 8 + 2 * j + 1], st2[j].y);
+            }
+        }
         __syncthreads();
         for (int c = tid; c < nblk; c += TC_THREADS) {
             atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
