@@ -445,6 +445,141 @@ __global__ void __launch_bounds__(256) dw_dgrad_strided_tile_kernel(const __grid
     }
 }
 
+// ---- stride-2 3x3 (pad 1, dilation 1) data gradient, the MobileNet-v2 down-sampling case.  A 2x2 quad of dx pixels
+// (rows 2a, 2a+1; columns 2b, 2b+1) depends on the 2x2 dz neighbourhood (a..a+1, b..b+1) only:
+//   dx[2a  ,2b  ] = z00 w11                         dx[2a  ,2b+1] = z01 w10 + z00 w12
+//   dx[2a+1,2b  ] = z10 w01 + z00 w21               dx[2a+1,2b+1] = z11 w00 + z10 w02 + z01 w20 + z00 w22
+// so no tap needs a divisibility test.  Same persistent double-buffered TMA structure as dw_tile_kernel; thread = (channel
+// vector, lane), a lane walks vertical strips of QS quads of one quad column and slides its two dz rows down.
+struct DwQ {
+    int N, IH, IW, C;        // dx is IH x IW
+    int CC, nchunks;
+    int TH, TW, ZTH, ZTW;    // dx patch (multiples of 2*QS and 2), dz patch = TH/2+1 x TW/2+1
+    int tiles_x, tiles_y;
+    const float *w;
+    bf16 *dx;
+    int dx_cs;
+};
+constexpr int DQ_QS = 4;  // quads per strip
+
+__global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_constant__ CUtensorMap map_dz, const DwQ p) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
+    const size_t tile_bytes = (size_t)p.ZTH * p.ZTW * p.CC * 2;
+    const size_t tile_stride = (tile_bytes + 127) & ~(size_t)127;
+    bf16 *tiles[2] = {reinterpret_cast<bf16 *>(base), reinterpret_cast<bf16 *>(base + tile_stride)};
+    float *wsm = reinterpret_cast<float *>(base + 2 * tile_stride);  // [9][CC]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + 9 * p.CC);
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.y, c_base = chunk * p.CC;
+    const int tiles_img = p.tiles_x * p.tiles_y, total = tiles_img * p.N;
+    auto origin = [&](int t, int &n, int &iy0, int &ix0) {
+        n = t / tiles_img;
+        const int r = t - n * tiles_img, ty = r / p.tiles_x;
+        iy0 = ty * p.TH;
+        ix0 = (r - ty * p.tiles_x) * p.TW;
+    };
+    auto issue = [&](int t, int buf) {  // thread 0
+        int n, iy0, ix0;
+        origin(t, n, iy0, ix0);
+        dmbar_expect_tx(&bar[buf], (uint32_t)tile_bytes);
+        tma_load_4d(tiles[buf], &map_dz, &bar[buf], c_base, ix0 / 2, iy0 / 2, n);
+    };
+    if (tid == 0) {
+        dmbar_init(&bar[0], 1);
+        dmbar_init(&bar[1], 1);
+    }
+    for (int i = tid; i < 9 * p.CC; i += blockDim.x) {
+        int tap = i / p.CC, c = i - tap * p.CC;
+        wsm[i] = p.w[(size_t)(c_base + c) * 9 + tap];
+    }
+    __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+
+    const int CVn = p.CC / 8;
+    const int cv = tid % CVn, lane = tid / CVn, L = blockDim.x / CVn;
+    const int qcols = p.TW / 2, nstrips = (p.TH / (2 * DQ_QS)) * qcols;
+    const int c0 = c_base + cv * 8;
+    const uint32_t pxb = (uint32_t)p.CC * 2, rowb = (uint32_t)p.ZTW * pxb, tapb = (uint32_t)p.CC * 4;
+    const uint32_t wcv = dsmem_u32(wsm) + cv * 32;
+    const uint32_t tile_a[2] = {dsmem_u32(tiles[0]) + cv * 16, dsmem_u32(tiles[1]) + cv * 16};
+    const size_t orow = (size_t)p.IW * p.dx_cs;
+
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
+        int n, iy0, ix0;
+        origin(t, n, iy0, ix0);
+        dmbar_wait(&bar[buf], (it >> 1) & 1);
+        const uint32_t tile = buf ? tile_a[1] : tile_a[0];
+        for (int s = lane; s < nstrips; s += L) {
+            const int qb = s % qcols, qa0 = (s / qcols) * DQ_QS;
+            const int ix = ix0 + 2 * qb, iyb = iy0 + 2 * qa0;
+            if (ix >= p.IW || iyb >= p.IH) continue;
+            const bool x1ok = ix + 1 < p.IW;
+            float2 z0[2][4], z1[2][4];  // dz rows a and a+1, columns b and b+1
+            const uint32_t zp = tile + (uint32_t)qa0 * rowb + (uint32_t)qb * pxb;
+            cvt8(lds16(zp), z0[0]);
+            cvt8(lds16(zp + pxb), z0[1]);
+            bf16 *op = p.dx + (((size_t)n * p.IH + iyb) * p.IW + ix) * p.dx_cs + c0;
+#pragma unroll
+            for (int q = 0; q < DQ_QS; ++q) {
+                const int iy = iyb + 2 * q;
+                if (iy >= p.IH) break;
+                cvt8(lds16(zp + (uint32_t)(q + 1) * rowb), z1[0]);
+                cvt8(lds16(zp + (uint32_t)(q + 1) * rowb + pxb), z1[1]);
+                float2 w[4], o00[4], o01[4], o10[4], o11[4];
+                const float2 zero = make_float2(0.f, 0.f);
+                ldw8(wcv + 4 * tapb, w);  // w11
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o00[j] = ffma2(z0[0][j], w[j], zero);
+                ldw8(wcv + 3 * tapb, w);  // w10
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o01[j] = ffma2(z0[1][j], w[j], zero);
+                ldw8(wcv + 5 * tapb, w);  // w12
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o01[j] = ffma2(z0[0][j], w[j], o01[j]);
+                ldw8(wcv + 1 * tapb, w);  // w01
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o10[j] = ffma2(z1[0][j], w[j], zero);
+                ldw8(wcv + 7 * tapb, w);  // w21
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o10[j] = ffma2(z0[0][j], w[j], o10[j]);
+                ldw8(wcv + 0 * tapb, w);  // w00
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o11[j] = ffma2(z1[1][j], w[j], zero);
+                ldw8(wcv + 2 * tapb, w);  // w02
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o11[j] = ffma2(z1[0][j], w[j], o11[j]);
+                ldw8(wcv + 6 * tapb, w);  // w20
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o11[j] = ffma2(z0[1][j], w[j], o11[j]);
+                ldw8(wcv + 8 * tapb, w);  // w22
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o11[j] = ffma2(z0[0][j], w[j], o11[j]);
+                auto st = [&](bf16 *dst, const float2 (&o)[4]) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y),
+                                                                 pack_bf16x2(o[2].x, o[2].y), pack_bf16x2(o[3].x, o[3].y));
+                };
+                bf16 *r0 = op + (size_t)(2 * q) * orow;
+                st(r0, o00);
+                if (x1ok) st(r0 + p.dx_cs, o01);
+                if (iy + 1 < p.IH) {
+                    st(r0 + orow, o10);
+                    if (x1ok) st(r0 + orow + p.dx_cs, o11);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    z0[0][j] = z1[0][j];
+                    z0[1][j] = z1[1][j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 typedef CUresult (*DwEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -657,6 +792,51 @@ extern "C" int nasb_dwconv_dgrad_strided_tile(const NasbTensor *dz, const float 
     if ((ks != 3 && ks != 5) || stride < 2 || !vec_ok(*dz, 8) || !vec_ok(*dx, 8) || dx->n > 65535) return NASB_ERR_UNSUPPORTED;
     int cc = pick_cc(dx->c);
     if (!cc) return NASB_ERR_UNSUPPORTED;
+    if (ks == 3 && stride == 2 && dil == 1 && pad == 1 && dz->h == (dx->h - 1) / 2 + 1 && dz->w == (dx->w - 1) / 2 + 1) {
+        if (npix(*dx) == 0) return 0;
+        DwQ q{};
+        q.N = dx->n;
+        q.IH = dx->h;
+        q.IW = dx->w;
+        q.C = dx->c;
+        q.TH = 16;
+        q.TW = 64;
+        q.ZTH = q.TH / 2 + 1;
+        q.ZTW = q.TW / 2 + 1;
+        while (cc >= 8 && (dx->c % cc || (size_t)q.ZTH * q.ZTW * cc * 2 > 40 * 1024)) cc -= 8;
+        if (cc < 8) return NASB_ERR_UNSUPPORTED;
+        q.CC = cc;
+        q.nchunks = dx->c / cc;
+        q.tiles_x = cdiv(dx->w, q.TW);
+        q.tiles_y = cdiv(dx->h, q.TH);
+        q.w = weight;
+        q.dx = (bf16 *)dx->ptr;
+        q.dx_cs = dx->cstride;
+        CUtensorMap mq;
+        if (!make_map4(&mq, dz, cc, q.ZTW, q.ZTH)) return NASB_ERR_UNSUPPORTED;
+        const size_t tile_b = ((size_t)q.ZTH * q.ZTW * cc * 2 + 127) & ~(size_t)127;
+        const size_t smem = 2 * tile_b + (size_t)9 * cc * 4 + 16 + 256;
+        const int CVn = cc / 8, nstrips = (q.TH / (2 * DQ_QS)) * (q.TW / 2);
+        int L = 64;
+        while (L * CVn > 256 || L > nstrips) L >>= 1;
+        const int threads = L * CVn;
+        static bool cfgq = false;
+        if (!cfgq) {
+            if (cudaFuncSetAttribute(dw_dgrad_s2k3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+                return NASB_ERR_UNSUPPORTED;
+            cfgq = true;
+        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dw_dgrad_s2k3_kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (per_sm > 6) per_sm = 6;
+        long long total = (long long)q.tiles_x * q.tiles_y * dx->n;
+        long long gx = (long long)NASB_SM_COUNT * per_sm / q.nchunks;
+        if (gx < 1) gx = 1;
+        if (gx > total) gx = total;
+        dw_dgrad_s2k3_kernel<<<dim3((unsigned)gx, q.nchunks), threads, smem, (cudaStream_t)stream>>>(mq, q);
+        NASB_CHECK_LAUNCH();
+        return 0;
+    }
     const int TH = 16, TW = 32;
     DwG p{};
     // dz rows touched by TH dx rows: ((TH-1) + (ks-1)*dil) / stride + 2

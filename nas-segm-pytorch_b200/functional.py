@@ -393,8 +393,11 @@ class _ResizeAxpby(torch.autograd.Function):
         need = ctx.needs_input_grad
         dx = dyy = dsa = dsb = None
         if need[0]:
-            dx = lib.new_act(*x.shape, x.dtype, dev)
-            call("nasb_resize_bwd", ref(desc(dz)), ptr(sa), ref(desc(dx)))
+            if sa is None and tuple(dz.shape) == tuple(x.shape):
+                dx = dz  # same size, no per-channel scale: the adjoint of the identity (gradients are values, aliasing is safe)
+            else:
+                dx = lib.new_act(*x.shape, x.dtype, dev)
+                call("nasb_resize_bwd", ref(desc(dz)), ptr(sa), ref(desc(dx)))
         if y is not None and need[1]:
             if sb is None:
                 dyy = dz
