@@ -104,6 +104,10 @@ int nasb_stem_fwd(const NasbTensor *img, const float *weight, int ks, int stride
                   const float *out_shift, int act, const NasbTensor *out, void *stream);
 int nasb_stem_wgrad(const NasbTensor *img, const NasbTensor *dz, int ks, int stride, int dil, int pad, float *dweight,
                     void *stream);
+/* Speed mode: the same stem as a tensor-core GEMM.  nasb_stem_im2col writes the bf16 patch matrix [N, OH, OW, 32]
+ * (k = ci*9 + ky*3 + kx, zero for k >= 27); forward = nasb_pw_tc_fwd with the [32][27] weight packed to K = 32,
+ * weight gradient = nasb_pw_tc_wgrad on the same matrix (columns 27..31 of the result are zero). */
+int nasb_stem_im2col(const NasbTensor *img, int ks, int stride, int dil, int pad, const NasbTensor *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Tensor-core path of the pointwise (1x1, stride 1) convolution: bf16 activations, TMA-staged 128-byte-swizzled

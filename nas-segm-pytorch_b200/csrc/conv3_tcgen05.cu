@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant
     uint64_t *bar_b = (uint64_t *)(s_sq + C3_NB);
     uint64_t *bar_acc = bar_b + 1;
     uint64_t *full = bar_acc + 1;      // [stages]
-    uint64_t *done = full + 4;         // [stages]
-    uint32_t *s_tmem = (uint32_t *)(done + 4);
+    uint64_t *done = full + 8;         // [stages]
+    uint32_t *s_tmem = (uint32_t *)(done + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = (int)blockIdx.x % p.nnb, n0 = nb * C3_NB;
@@ -337,7 +337,7 @@ static void pick_patch(int H, int W, int &TH, int &TW) {
 }
 
 static size_t c3_smem(int nkb, int stages) {
-    return (size_t)9 * nkb * C3_NB * 128 + (size_t)stages * C3_TILE * 128 + (size_t)C3_TILE * 128 + 4 * C3_NB * 4 + 128 + 1024;
+    return (size_t)9 * nkb * C3_NB * 128 + (size_t)stages * C3_TILE * 128 + (size_t)C3_TILE * 128 + 4 * C3_NB * 4 + 256 + 1024;
 }
 
 }  // namespace nasb
@@ -387,7 +387,10 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     pick_patch(p.H, p.W, p.TH, p.TW);
     p.tiles_x = cdiv(p.W, p.TW);
     p.tiles_y = cdiv(p.H, p.TH);
-    p.stages = c3_smem(p.nkb, 4) <= 110 * 1024 ? 4 : (c3_smem(p.nkb, 3) <= 200 * 1024 ? 3 : 2);
+    // one CTA per SM (the nine weight tiles alone are 72 KB per K block): as deep a TMA ring as shared memory allows, so
+    // that most of the next patch is already in flight while the four warps run the epilogue
+    p.stages = 8;
+    while (p.stages > 2 && c3_smem(p.nkb, p.stages) > 216 * 1024) --p.stages;
     p.nr = (N + 63) / 64 * 64;
     p.scale = scale;
     p.shift = shift;
@@ -408,7 +411,7 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     size_t smem = c3_smem(p.nkb, p.stages);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(c3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048) != cudaSuccess)
+        if (cudaFuncSetAttribute(c3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return NASB_ERR_UNSUPPORTED;
         configured = true;
     }

@@ -88,6 +88,44 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemP p) {
     }
 }
 
+
+// ---- speed mode: the stem as a tensor-core GEMM.  One pass turns the planar fp32 image into the bf16 patch matrix
+// [N*OH*OW][32] (k = ci*9 + ky*3 + kx for k < 27, zero for k = 27..31 -- 64 bytes per output pixel); the 3x3x3 -> 32
+// convolution is then the pointwise tcgen05 kernel with K = 32 (fused BN statistics included) and its weight gradient is
+// nasb_pw_tc_wgrad on the same matrix.  Thread = output pixel: 27 loads (adjacent threads read adjacent columns),
+// four 16-byte stores.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const StemP p) {
+    const long long total = (long long)p.N * p.OH * p.OW;
+    const long long plane = (long long)p.IH * p.IW;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(pix % p.OW);
+        const long long t = pix / p.OW;
+        const int oy = (int)(t % p.OH);
+        const int n = (int)(t / p.OH);
+        const float *ib = p.img + (long long)n * 3 * plane;
+        float v[32];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = oy * p.stride - p.pad + ky * p.dil;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox * p.stride - p.pad + kx * p.dil;
+                    v[ci * 9 + ky * 3 + kx] =
+                        (iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW) ? ib[ci * plane + (long long)iy * p.IW + ix] : 0.f;
+                }
+            }
+#pragma unroll
+        for (int k = STEM_K; k < 32; ++k) v[k] = 0.f;
+        uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(p.out) + pix * p.out_cs);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            o[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                              pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+    }
+}
+
 constexpr int STEM_WP = 64;  // pixels staged per step of the weight gradient
 
 template <typename T>
@@ -205,6 +243,34 @@ extern "C" int nasb_stem_wgrad(const NasbTensor *img, const NasbTensor *dz, int 
         stem_wgrad_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, (const bf16 *)dz->ptr, dz->cstride, dweight, rows);
     else
         stem_wgrad_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, (const float *)dz->ptr, dz->cstride, dweight, rows);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// image [N][3][IH][IW] fp32 planar -> bf16 patch matrix `out` [N, OH, OW, 32] (see stem_im2col_kernel)
+extern "C" int nasb_stem_im2col(const NasbTensor *img, int ks, int stride, int dil, int pad, const NasbTensor *out, void *stream) {
+    if (!img || !out || img->dtype != NASB_F32_NCHW || img->c != 3 || ks != 3 || out->dtype != NASB_BF16 || out->c != 32 ||
+        out->n != img->n || !vec_ok(*out, 8))
+        return NASB_ERR_UNSUPPORTED;
+    int eh = (img->h + 2 * pad - dil * 2 - 1) / stride + 1, ew = (img->w + 2 * pad - dil * 2 - 1) / stride + 1;
+    if (eh != out->h || ew != out->w) return NASB_ERR_BAD_ARG;
+    StemP p{};
+    p.img = (const float *)img->ptr;
+    p.N = img->n;
+    p.IH = img->h;
+    p.IW = img->w;
+    p.OH = out->h;
+    p.OW = out->w;
+    p.stride = stride;
+    p.pad = pad;
+    p.dil = dil;
+    p.out = out->ptr;
+    p.out_cs = out->cstride;
+    long long total = npix(*out);
+    if (total == 0) return 0;
+    long long blocks = (total + 255) / 256, cap = (long long)NASB_SM_COUNT * 16;
+    if (blocks > cap) blocks = cap;
+    stem_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     NASB_CHECK_LAUNCH();
     return 0;
 }

@@ -59,6 +59,13 @@ def _tc_wgrad_ok(x, dz, cout):
     return bool(lib.load().nasb_pw_tc_wgrad_supported(int(cout), int(x.shape[1])))
 
 
+def _stem_tc_ok(cout):
+    from . import config
+    lb = lib.load()
+    return bool(config().use_tcgen05 and cout % 8 == 0 and lb.nasb_pw_tc_supported(32, int(cout))
+                and lb.nasb_pw_tc_wgrad_supported(int(cout), 32))
+
+
 def _c3_ok(x, cin, cout, ks, stride, dil, pad):
     """3x3 implicit GEMM on the tensor cores: bf16 input with a 16-byte pixel pitch, stride 1, 'same' geometry."""
     from . import config
@@ -123,6 +130,16 @@ class _ConvUnit(torch.autograd.Function):
         use_tc = (not dw and ks == 1 and stride == 1 and pad == 0 and x1 is None and not in_relu and not image
                   and _tc_ok(x0, x0.shape[1], cout, out_dtype))
         wpack = _pack_weight(weight, False) if use_tc else None
+        # speed mode stem: image -> bf16 patch matrix [n, 32, oh, ow] (k = ci*9 + ky*3 + kx), then the pointwise tensor-core
+        # kernel with K = 32; the patch matrix is what the backward pass keeps (weight gradient = nasb_pw_tc_wgrad)
+        stem_tc = (image and not dw and ks == 3 and x1 is None and not in_relu and res is None and x0.shape[1] == 3
+                   and out_dtype == torch.bfloat16 and not x0.requires_grad and _stem_tc_ok(cout))
+        if stem_tc:
+            xp = lib.new_act(n, 32, oh, ow, torch.bfloat16, dev)
+            call("nasb_stem_im2col", ref(dx0), ks, stride, dil, pad, ref(desc(xp)))
+            wpack = torch.empty(cout * 32, dtype=torch.bfloat16, device=dev)
+            call("nasb_pack_weight_bf16", ptr(weight), cout, 27, 0, ptr(wpack))
+            x0, dx0, use_tc = xp, desc(xp), True
         use_c3 = (not dw and x1 is None and not in_relu and not image and res is None
                   and out_dtype in (torch.bfloat16, torch.float32) and _c3_ok(x0, x0.shape[1], cout, ks, stride, dil, pad))
         wpack3 = _pack_conv3(weight, 0) if use_c3 else None
@@ -190,6 +207,7 @@ class _ConvUnit(torch.autograd.Function):
             call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
             if res is not None and not late_res:
                 call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
+        ctx.stem_tc = stem_tc
         ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
         ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
         ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
@@ -233,7 +251,11 @@ class _ConvUnit(torch.autograd.Function):
         if c3 and (dz.dtype != torch.bfloat16 or dz.data_ptr() % 16 or desc(dz).cstride % 8):
             dz = _bf16_padded_copy(dz)  # e.g. fp32 logit gradients with 19 channels
         ddz = desc(dz)
-        if need[2] and c3:
+        if need[2] and ctx.stem_tc:  # x0 is the saved bf16 patch matrix; columns 27..31 of the product are zero padding
+            dw32 = torch.zeros((cout, 32), dtype=torch.float32, device=dev)
+            call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dw32))
+            dweight = dw32[:, :27].reshape(weight.shape)
+        elif need[2] and c3:
             dweight = torch.zeros_like(weight, dtype=torch.float32)
             call("nasb_conv3_tc_wgrad", ref(desc(x0)), ref(ddz), dil, pad, ptr(dweight))
         elif need[2]:
@@ -253,7 +275,7 @@ class _ConvUnit(torch.autograd.Function):
                 call("nasb_conv_wgrad", ref(dsrc0), ref(desc(x1)) if has_x1 else None, None, None, in_relu, ref(ddz), ks,
                      stride, dil, pad, ptr(dweight))
         dx0 = dx1 = None
-        if need[0] or (has_x1 and need[1]):
+        if (need[0] or (has_x1 and need[1])) and not ctx.stem_tc:
             dx0 = lib.new_act(*x0.shape, x0.dtype, dev)
             if has_x1:
                 dx1 = lib.new_act(*x1.shape, x1.dtype, dev)

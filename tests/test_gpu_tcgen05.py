@@ -149,3 +149,30 @@ def test_tc_wgrad_mn_major():
     lib.call("nasb_pw_tc_wgrad", lib.ref(lib.desc(x.permute(0, 3, 1, 2))), lib.ref(lib.desc(dz.permute(0, 3, 1, 2))), lib.ptr(dw))
     ref = 1 + dz.float().reshape(-1, 48).t() @ x.float().reshape(-1, 32)
     assert float((dw - ref).abs().max() / ref.abs().max()) < 2e-3
+
+
+def test_stem_as_tensor_core_gemm():
+    """Speed-mode encoder stem (planar fp32 image -> bf16 patch matrix -> tcgen05 GEMM, K = 32) against torch fp32:
+    conv 3->32, stride 2, training-mode BN, ReLU6; output, weight / BN gradients, odd image sizes."""
+    import torch.nn.functional as F
+    from nas_segm_b200.nn.layer_factory import conv_bn_relu6
+    torch.manual_seed(3)
+    for (n, h, w) in [(2, 64, 96), (3, 37, 53), (1, 18, 130)]:
+        m = conv_bn_relu6(3, 32, 2).cuda().train()
+        x = torch.randn(n, 3, h, w, device="cuda")
+        nas_segm_b200.set_act_dtype(torch.bfloat16)
+        try:
+            y = m(x)
+            assert y.dtype == torch.bfloat16
+            gy = torch.randn(y.shape, device="cuda")
+            (y.float() * gy).sum().backward()
+        finally:
+            nas_segm_b200.set_act_dtype(torch.float32)
+        wr = m[0].weight.detach().clone().requires_grad_(True)
+        gr, br = m[1].weight.detach().clone().requires_grad_(True), m[1].bias.detach().clone().requires_grad_(True)
+        z = F.conv2d(x, wr, None, 2, 1)
+        yr = torch.clamp(F.batch_norm(z, None, None, gr, br, True, 0.1, 1e-5), 0, 6)
+        (yr * gy.to(torch.bfloat16).float()).sum().backward()
+        assert float((y.float() - yr).abs().max() / yr.abs().max()) < 2e-2, (n, h, w)
+        for a, b, tol in ((m[0].weight.grad, wr.grad, 5e-2), (m[1].weight.grad, gr.grad, 5e-2), (m[1].bias.grad, br.grad, 5e-2)):
+            assert float((a - b).abs().mean() / b.abs().mean()) < tol, (n, h, w, float((a - b).abs().mean() / b.abs().mean()))
