@@ -10,6 +10,8 @@
 //   weight gradient         : dW[:, :, tap] = x_tap^T dz.  Two taps share one M=128 instruction (rows 0-63 = tap 2j,
 //                             rows 64-127 = tap 2j+1, MN-major descriptors), 5 TMEM accumulators live across all the
 //                             CTA's patches, one atomic flush at the end.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace nasb {
@@ -25,6 +27,8 @@ struct C3Params {
     int dil, pad;
     int TH, TW, tiles_x, tiles_y;
     int stages;
+    int halo;            // 1: row-halo staging (TH == 1): three (TW + 2*dil)-pixel row boxes per (patch, K block) feed all nine taps
+    int rowbuf;          // bytes between the row buffers of one halo stage (multiple of 1024)
     int nr;              // rows per tap in the packed weight (N rounded up to 64)
     const float *scale, *shift;
     int act;
@@ -41,7 +45,8 @@ __global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant
     const int nb_items = 9 * p.nkb;
     uint8_t *sB = smem;                                        // 9*nkb x [64 x 128 B]
     uint8_t *sA = sB + (size_t)nb_items * C3_NB * 128;         // stages x [128 x 128 B]
-    uint8_t *sO = sA + (size_t)p.stages * C3_TILE * 128;       // [128 x 128 B]
+    const size_t stage_bytes = p.halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
+    uint8_t *sO = sA + (size_t)p.stages * stage_bytes;          // [128 x 128 B]
     float *s_scale = (float *)(sO + (size_t)C3_TILE * 128);
     float *s_shift = s_scale + C3_NB;
     float *s_sum = s_shift + C3_NB;
@@ -93,18 +98,30 @@ __global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant
         y0 = ty * p.TH;
         x0 = (r - ty * p.tiles_x) * p.TW;
     };
-    const long long total_items = (long long)my_patches * nb_items;
+    // pipeline item: (patch, tap, K block) in tap mode, (patch, K block) in row-halo mode
+    const int items_pp = p.halo ? p.nkb : nb_items;
+    const long long total_items = (long long)my_patches * items_pp;
     long long g_issued = 0;
-    auto issue = [&](long long g) {  // thread 0 only: TMA for pipeline item g = (patch, tap, k block)
+    auto issue = [&](long long g) {  // thread 0 only: TMA for pipeline item g
         const int s = (int)(g % S);
         if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
-        const int pi = (int)(g / nb_items), j = (int)(g % nb_items);
-        const int tap = j / p.nkb, kb = j - tap * p.nkb;
+        const int pi = (int)(g / items_pp), j = (int)(g % items_pp);
         int n, y0, x0;
         patch_origin(pi, n, y0, x0);
-        mbar_expect_tx(&full[s], C3_TILE * 128);
-        tma_load_4d_sw(sA + (size_t)s * C3_TILE * 128, &map_x, &full[s], kb * 64, x0 - p.pad + (tap % 3) * p.dil,
-                       y0 - p.pad + (tap / 3) * p.dil, n);
+        if (p.halo) {
+            // rows y0 - pad + {0, dil, 2 dil}, pixels x0 - pad .. x0 - pad + TW + 2 dil - 1: tap (ty, tx) is the 128 consecutive
+            // 128-byte rows of row buffer ty that start at pixel tx*dil (both TMA and UMMA swizzle on absolute address bits)
+            const uint32_t row_bytes = (uint32_t)(p.TW + 2 * p.dil) * 128;
+            mbar_expect_tx(&full[s], 3 * row_bytes);
+            for (int ty = 0; ty < 3; ++ty)
+                tma_load_4d_sw(sA + (size_t)s * stage_bytes + (size_t)ty * p.rowbuf, &map_x, &full[s], j * 64, x0 - p.pad,
+                               y0 - p.pad + ty * p.dil, n);
+        } else {
+            const int tap = j / p.nkb, kb = j - tap * p.nkb;
+            mbar_expect_tx(&full[s], C3_TILE * 128);
+            tma_load_4d_sw(sA + (size_t)s * C3_TILE * 128, &map_x, &full[s], kb * 64, x0 - p.pad + (tap % 3) * p.dil,
+                           y0 - p.pad + (tap / 3) * p.dil, n);
+        }
     };
     if (tid == 0 && my_patches > 0) {
         mbar_expect_tx(bar_b, (uint32_t)(nb_items * C3_NB * 128));
@@ -120,19 +137,30 @@ __global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant
         patch_origin(pi, n, y0, x0);
         if (tid == 0) {
             if (pi == 0) mbar_wait(bar_b, 0);
-            for (int j = 0; j < nb_items; ++j) {
-                const long long c = (long long)pi * nb_items + j;
+            for (int j = 0; j < items_pp; ++j) {
+                const long long c = (long long)pi * items_pp + j;
                 if (c >= 1 && g_issued < total_items) issue(g_issued++);  // refill the slot freed one item ago
                 const int s = (int)(c % S);
                 mbar_wait(&full[s], (uint32_t)(c / S) & 1);
                 tc_fence_after();
-                const int kb = j % p.nkb;
+                const int kb = p.halo ? j : j % p.nkb;
                 const int krem = p.K - kb * 64;
                 const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)s * C3_TILE * 128) + ks * 32);
-                    uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)j * C3_NB * 128) + ks * 32);
-                    umma_f16(tmem_base, ad, bd, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                if (p.halo) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a0 = smem_u32(sA + (size_t)s * stage_bytes + (size_t)(tap / 3) * p.rowbuf) +
+                                            (uint32_t)((tap % 3) * p.dil) * 128;
+                        const uint32_t b0 = smem_u32(sB + (size_t)(tap * p.nkb + kb) * C3_NB * 128);
+                        for (int ks = 0; ks < ksteps; ++ks)
+                            umma_f16(tmem_base, make_desc_sw128(a0 + ks * 32), make_desc_sw128(b0 + ks * 32), idesc,
+                                     (j > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                    }
+                } else {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)s * C3_TILE * 128) + ks * 32);
+                        uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)j * C3_NB * 128) + ks * 32);
+                        umma_f16(tmem_base, ad, bd, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&done[s]);
             }
@@ -336,8 +364,8 @@ static void pick_patch(int H, int W, int &TH, int &TW) {
     (void)H;
 }
 
-static size_t c3_smem(int nkb, int stages) {
-    return (size_t)9 * nkb * C3_NB * 128 + (size_t)stages * C3_TILE * 128 + (size_t)C3_TILE * 128 + 4 * C3_NB * 4 + 256 + 1024;
+static size_t c3_smem(int nkb, int stages, size_t stage_bytes = (size_t)C3_TILE * 128) {
+    return (size_t)9 * nkb * C3_NB * 128 + (size_t)stages * stage_bytes + (size_t)C3_TILE * 128 + 4 * C3_NB * 4 + 256 + 1024;
 }
 
 }  // namespace nasb
@@ -387,10 +415,21 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     pick_patch(p.H, p.W, p.TH, p.TW);
     p.tiles_x = cdiv(p.W, p.TW);
     p.tiles_y = cdiv(p.H, p.TH);
-    // one CTA per SM (the nine weight tiles alone are 72 KB per K block): as deep a TMA ring as shared memory allows, so
-    // that most of the next patch is already in flight while the four warps run the epilogue
-    p.stages = 8;
-    while (p.stages > 2 && c3_smem(p.nkb, p.stages) > 216 * 1024) --p.stages;
+    // Row-halo staging when a patch is one image row (TH == 1): 3 boxes per (patch, K block) instead of 9 -- the TMA unit
+    // moves ~one 16 KB box per L2 round trip per SM, which is what bounded the tap-per-box pipeline (12 us per patch).
+    static int halo_on = -1;
+    if (halo_on < 0) halo_on = getenv("NASB_C3_HALO") ? atoi(getenv("NASB_C3_HALO")) : 1;
+    p.halo = (halo_on && p.TH == 1 && p.TW + 2 * dil <= 256) ? 1 : 0;
+    p.rowbuf = (int)((((size_t)(p.TW + 2 * dil) * 128) + 1023) / 1024 * 1024);
+    size_t stage_bytes = p.halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
+    p.stages = p.halo ? 3 : 8;
+    while (p.stages > 2 && c3_smem(p.nkb, p.stages, stage_bytes) > 216 * 1024) --p.stages;
+    if (c3_smem(p.nkb, p.stages, stage_bytes) > 216 * 1024) {  // row buffers do not fit: tap-per-box pipeline
+        p.halo = 0;
+        stage_bytes = (size_t)C3_TILE * 128;
+        p.stages = 8;
+        while (p.stages > 2 && c3_smem(p.nkb, p.stages, stage_bytes) > 216 * 1024) --p.stages;
+    }
     p.nr = (N + 63) / 64 * 64;
     p.scale = scale;
     p.shift = shift;
@@ -401,14 +440,14 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     p.stats = stats;
     int Kp = (p.K + 7) / 8 * 8;
     CUtensorMap mx, mb, mo;
-    if (!tc_make_map4(&mx, x, p.TW, p.TH)) return NASB_ERR_UNSUPPORTED;
+    if (!tc_make_map4(&mx, x, p.halo ? p.TW + 2 * dil : p.TW, p.TH)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)9 * p.nr, (uint64_t)Kp, C3_NB)) return NASB_ERR_UNSUPPORTED;
     if (p.out_f32) {
         mo = mx;  // unused
     } else if (!tc_make_map4(&mo, out, p.TW, p.TH)) {
         return NASB_ERR_UNSUPPORTED;
     }
-    size_t smem = c3_smem(p.nkb, p.stages);
+    size_t smem = c3_smem(p.nkb, p.stages, stage_bytes);
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(c3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)

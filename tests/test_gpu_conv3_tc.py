@@ -18,6 +18,7 @@ def _nhwc(t):
 CASES = [  # Cin, Cout, dil, N, H, W
     (64, 19, 1, 2, 37, 53), (48, 48, 1, 2, 81, 81), (48, 48, 3, 2, 21, 21), (48, 48, 12, 2, 11, 11), (64, 64, 1, 1, 64, 128),
     (24, 40, 1, 3, 5, 200), (128, 64, 1, 1, 33, 47), (64, 21, 1, 4, 128, 256), (16, 8, 3, 1, 9, 9), (64, 1, 1, 2, 30, 40),
+    (48, 48, 3, 1, 20, 130), (128, 64, 1, 1, 12, 100), (64, 19, 12, 1, 30, 300),  # wide rows: the row-halo staging mode
 ]
 
 
