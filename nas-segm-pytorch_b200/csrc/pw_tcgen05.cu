@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap map_x, const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = WG_STAGE_A + p.nbb * TILE_M * 128;
+    // Co <= 64: only one 64-channel dz block is staged; the descriptor's second block (LBO) then aliases the first x block and
+    // produces accumulator rows 64..127 that the epilogue never reads
+    const int a_bytes = p.Co > 64 ? WG_STAGE_A : TILE_M * 128;
+    const int stage_bytes = a_bytes + p.nbb * TILE_M * 128;
     uint64_t *bars = (uint64_t *)(smem + 2 * (size_t)stage_bytes);  // full[2], done[2], final
     uint32_t *s_tmem = (uint32_t *)(bars + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -269,8 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE_M;
             mbar_expect_tx(&bars[s], (uint32_t)stage_bytes);
             tma_load_2d(st, &map_dz, &bars[s], 0, m0);
-            tma_load_2d(st + TILE_M * 128, &map_dz, &bars[s], 64, m0);
-            for (int b = 0; b < p.nbb; ++b) tma_load_2d(st + WG_STAGE_A + (size_t)b * TILE_M * 128, &map_x, &bars[s], b * 64, m0);
+            if (p.Co > 64) tma_load_2d(st + TILE_M * 128, &map_dz, &bars[s], 64, m0);
+            for (int b = 0; b < p.nbb; ++b) tma_load_2d(st + a_bytes + (size_t)b * TILE_M * 128, &map_x, &bars[s], b * 64, m0);
         };
         load(0);
         for (int i = 0; i < my_n; ++i) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
             }
             mbar_wait(&bars[s], (uint32_t)(i >> 1) & 1);
             tc_fence_after();
-            const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + WG_STAGE_A;
+            const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + a_bytes;
 #pragma unroll
             for (int ks = 0; ks < TILE_M / 16; ++ks) {
                 uint64_t ad = make_desc_mn_sw128(a0 + ks * 2048, TILE_M * 128);
@@ -424,7 +427,6 @@ extern "C" int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float
     p.ldw = Ci;
     CUtensorMap mx;
     if (!tc_make_map2(&mx, x->ptr, (uint64_t)Ci, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
-    size_t smem = 2 * ((size_t)WG_STAGE_A + (size_t)p.nbb * TILE_M * 128) + 64 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
@@ -432,18 +434,24 @@ extern "C" int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float
         configured = true;
     }
     int nchunks = (int)((M + TILE_M - 1) / TILE_M);
-    int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm > 3) per_sm = 3;
-    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
-    if (per_sm < 1) per_sm = 1;
-    int grid = NASB_SM_COUNT * per_sm;
-    if (grid > nchunks) grid = nchunks;
     for (int co0 = 0; co0 < Co; co0 += 128) {
         CUtensorMap mdz;
         const int cb = Co - co0 < 128 ? Co - co0 : 128;
         if (!tc_make_map2(&mdz, (const bf16 *)dz->ptr + co0, (uint64_t)cb, (uint64_t)M, (uint64_t)dz->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
         p.Co = cb;
         p.dw = dweight + (size_t)co0 * Ci;
+        const size_t smem = 2 * ((size_t)(cb > 64 ? WG_STAGE_A : TILE_M * 128) + (size_t)p.nbb * TILE_M * 128) + 64 + 1024;
+        int per_sm = (int)((220 * 1024) / smem);
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
+        if (per_sm < 1) per_sm = 1;
+        int grid = NASB_SM_COUNT * per_sm;
+        // every CTA ends with Co x Ci atomics onto the same addresses: at least 16 pixel chunks per CTA (but >= 32 CTAs) --
+        // measured on B200: 2048 chunks 49 -> 27 us, 128 chunks 24 -> 14 us, large M unchanged
+        int want = nchunks / 16 < 32 ? 32 : nchunks / 16;
+        if (grid > want) grid = want;
+        if (grid > nchunks) grid = nchunks;
+        if (grid < 1) grid = 1;
         pw_wgrad_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mdz, mx, p);
         NASB_CHECK_LAUNCH();
     }

@@ -203,9 +203,32 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
     if use_graph:
         make_capturable(optim_enc)
         make_capturable(optim_dec)
-    for i, sample in enumerate(train_loader):
-        image = sample["image"].float().cuda(non_blocking=True)
-        target = sample["mask"].cuda(non_blocking=True)
+    # Host batches are uploaded on a side stream one iteration ahead: the (pinned) host -> device copy of batch i+1 runs
+    # under the kernels of batch i instead of in front of them (201 MB of fp32 image per 8 x 2048x1024 batch).
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    batches = iter(train_loader)
+
+    def upload():
+        try:
+            sample = next(batches)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(copy_stream):
+            im = sample["image"].float().cuda(non_blocking=True)
+            tg = sample["mask"].cuda(non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return im, tg, ev
+
+    ahead, i = upload(), -1
+    while ahead is not None:
+        image, target, ready = ahead
+        i += 1
+        main_stream.wait_event(ready)
+        image.record_stream(main_stream)
+        target.record_stream(main_stream)
+        ahead = upload()
         if use_graph:
             sg = getattr(segmenter, "_nasb_step_graph", None)
             if sg is None or sg.key != (id(optim_enc), id(optim_dec)) or not sg.matches((image, target)):
