@@ -174,10 +174,10 @@ int nasb_bn_fold(const float *gamma, const float *beta, const float *mean, const
 long long nasb_bn_stats_workspace(int C);
 int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
                   float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
-                  float *shift, void *workspace, void *stream);
+                  float *shift, long long *num_batches_tracked, void *workspace, void *stream);
 int nasb_bn_finalize(const double *sums, long long P, int C, const float *gamma, const float *beta, float eps,
                      float momentum, float *running_mean, float *running_var, float *save_mean, float *save_rstd,
-                     float *scale, float *shift, void *stream);
+                     float *scale, float *shift, long long *num_batches_tracked, void *stream);
 int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift, int act, const NasbTensor *y,
                     void *stream);
 int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,

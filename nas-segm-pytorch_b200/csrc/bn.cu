@@ -189,9 +189,11 @@ __global__ void __launch_bounds__(256) bn_sums_kernel(const T *z, int cs, long l
 
 __global__ void bn_stats_finalize_kernel(const double *ws, long long P, int C, const float *gamma, const float *beta,
                                          float eps, float momentum, float *running_mean, float *running_var,
-                                         float *save_mean, float *save_rstd, float *scale, float *shift) {
+                                         float *save_mean, float *save_rstd, float *scale, float *shift,
+                                         long long *num_batches_tracked) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;  // nn.BatchNorm2d's step counter, no extra launch
     double mean = ws[c] / (double)P;
     double var = ws[C + c] / (double)P - mean * mean;  // biased
     if (var < 0.0) var = 0.0;
@@ -645,7 +647,7 @@ extern "C" long long nasb_bn_stats_workspace(int C) { return (long long)C * (2 *
 
 extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
                              float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
-                             float *shift, void *workspace, void *stream) {
+                             float *shift, long long *num_batches_tracked, void *workspace, void *stream) {
     if (!z || !scale || !shift || !workspace || (z->dtype != NASB_F32 && z->dtype != NASB_BF16)) return NASB_ERR_BAD_ARG;
     long long P = npix(*z);
     int C = z->c;
@@ -670,7 +672,7 @@ extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const floa
     }
     NASB_CHECK_LAUNCH();
     bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, gamma, beta, eps, momentum, running_mean, running_var,
-                                                           save_mean, save_rstd, scale, shift);
+                                                           save_mean, save_rstd, scale, shift, num_batches_tracked);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -678,10 +680,10 @@ extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const floa
 // finalize from externally accumulated fp64 sums (the tcgen05 pointwise kernel fuses the statistics into its epilogue)
 extern "C" int nasb_bn_finalize(const double *sums, long long P, int C, const float *gamma, const float *beta, float eps,
                                 float momentum, float *running_mean, float *running_var, float *save_mean, float *save_rstd,
-                                float *scale, float *shift, void *stream) {
+                                float *scale, float *shift, long long *num_batches_tracked, void *stream) {
     if (!sums || !scale || !shift || P <= 0 || C <= 0) return NASB_ERR_BAD_ARG;
     bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(sums, P, C, gamma, beta, eps, momentum, running_mean, running_var,
-                                                           save_mean, save_rstd, scale, shift);
+                                                           save_mean, save_rstd, scale, shift, num_batches_tracked);
     NASB_CHECK_LAUNCH();
     return 0;
 }

@@ -23,6 +23,7 @@ from torch import nn
 
 from .. import config as _config
 from .. import functional as Fn
+from .. import lib
 from ..graphs import StepGraph, make_capturable
 from ..helpers.utils import try_except
 
@@ -118,6 +119,13 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
     start = time.time()
 
     def iteration(idx):
+        lib.zero_arena.begin(dev)
+        try:
+            return _iteration(idx)
+        finally:
+            lib.zero_arena.end()
+
+    def _iteration(idx):
         encoder_outputs = [_gather(Xy_train[k], idx) for k in feat_keys]
         y = _gather(Xy_train["y"], idx)
         output = decoder(encoder_outputs)
@@ -164,6 +172,16 @@ def segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, en
                    aux_weight=-1, avg_param=None, polyak_decay=0.99):
     """One end-to-end iteration on device-resident tensors (the body of trainer.py:226-272): forward, nearest-resized
     target, CE (+ aux), backward, the two grad-norm clips, the two optimiser steps, Polyak.  Returns the loss tensor."""
+    lib.zero_arena.begin(image.device)
+    try:
+        return _segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
+                               do_polyak, aux_weight, avg_param, polyak_decay)
+    finally:
+        lib.zero_arena.end()
+
+
+def _segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip, do_polyak,
+                    aux_weight, avg_param, polyak_decay):
     output = segmenter(image)
     aux_outs = []
     if isinstance(output, tuple):

@@ -192,18 +192,18 @@ class _ConvUnit(torch.autograd.Function):
             fused_stats = use_tc or use_c3
             sums = None
             if fused_stats or (dw and not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and _dw_stats_on()):
-                sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+                sums = lib.zeros(2 * cout, torch.float64, dev)
                 fused_stats = bool(run_conv(z, None, None, ACT_NONE, None, sums)) or fused_stats
             if fused_stats:  # batch statistics were accumulated by the conv kernel's epilogue
                 call("nasb_bn_finalize", ptr(sums), C.c_longlong(n * oh * ow), cout, ptr(gamma), ptr(beta), float(bn.eps),
-                     mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]))
+                     mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]),
+                     ptr(bn.num_batches_tracked))
             else:
                 if sums is None:
                     run_conv(z, None, None, ACT_NONE, None)
                 call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
-                     ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, cout)))
-            if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)
+                     ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(bn.num_batches_tracked),
+                     ptr(_ws(dev, cout)))
             call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
             if res is not None and not late_res:
                 call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
@@ -228,8 +228,8 @@ class _ConvUnit(torch.autograd.Function):
         cout = weight.shape[0]
         dy = _grad_in(dy, y.dtype)
         need = ctx.needs_input_grad
-        dgamma = torch.zeros(cout, dtype=torch.float32, device=dev) if has_g else None
-        dbeta = torch.zeros(cout, dtype=torch.float32, device=dev) if has_b else None
+        dgamma = lib.zeros(cout, torch.float32, dev) if has_g else None
+        dbeta = lib.zeros(cout, torch.float32, dev) if has_b else None
         if ctx.bn_mode or act != ACT_NONE:
             dz = lib.new_act(*y.shape, y.dtype, dev)
             # training: the mask is recomputed from z, y is neither read nor passed
@@ -243,7 +243,7 @@ class _ConvUnit(torch.autograd.Function):
             dz = dy
         dbias = None
         if has_bias:
-            dbias = torch.zeros(cout, dtype=torch.float32, device=dev)
+            dbias = lib.zeros(cout, torch.float32, dev)
             call("nasb_channel_sum", ref(desc(dz)), ptr(dbias), None)
         dweight = None
         c3 = (not dw and not has_x1 and not in_relu and not image
@@ -252,14 +252,14 @@ class _ConvUnit(torch.autograd.Function):
             dz = _bf16_padded_copy(dz)  # e.g. fp32 logit gradients with 19 channels
         ddz = desc(dz)
         if need[2] and ctx.stem_tc:  # x0 is the saved bf16 patch matrix; columns 27..31 of the product are zero padding
-            dw32 = torch.zeros((cout, 32), dtype=torch.float32, device=dev)
+            dw32 = lib.zeros((cout, 32), torch.float32, dev)
             call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dw32))
             dweight = dw32[:, :27].reshape(weight.shape)
         elif need[2] and c3:
-            dweight = torch.zeros_like(weight, dtype=torch.float32)
+            dweight = lib.zeros(tuple(weight.shape), torch.float32, dev)
             call("nasb_conv3_tc_wgrad", ref(desc(x0)), ref(ddz), dil, pad, ptr(dweight))
         elif need[2]:
-            dweight = torch.zeros_like(weight, dtype=torch.float32)
+            dweight = lib.zeros(tuple(weight.shape), torch.float32, dev)
             if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image and not in_relu
                     and _tc_wgrad_ok(x0, dz, cout)):
                 call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dweight))
@@ -334,9 +334,8 @@ class _BnAct(torch.autograd.Function):
             sv = torch.empty((2, c), dtype=torch.float32, device=dev)
             mom = 0.1 if bn.momentum is None else float(bn.momentum)
             call("nasb_bn_stats", ref(desc(x)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
-                 ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(_ws(dev, c)))
-            if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)
+                 ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(bn.num_batches_tracked),
+                 ptr(_ws(dev, c)))
         else:
             call("nasb_bn_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), c,
                  ptr(ss[0]), ptr(ss[1]))
@@ -352,8 +351,8 @@ class _BnAct(torch.autograd.Function):
         x, gamma, beta, y, ss, sv = ctx.saved_tensors
         dev, c = y.device, y.shape[1]
         dy = _grad_in(dy, y.dtype)
-        dgamma = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[0] else None
-        dbeta = torch.zeros(c, dtype=torch.float32, device=dev) if ctx.has[1] else None
+        dgamma = lib.zeros(c, torch.float32, dev) if ctx.has[0] else None
+        dbeta = lib.zeros(c, torch.float32, dev) if ctx.has[1] else None
         dx = lib.new_act(*y.shape, y.dtype, dev)
         call("nasb_bn_act_bwd", ref(desc(dy)), None if ctx.training else ref(desc(y)), ref(desc(x)) if ctx.training else None,
              ctx.act, ptr(gamma),
@@ -428,8 +427,8 @@ class _ResizeAxpby(torch.autograd.Function):
                 call("nasb_scale_copy", ref(desc(dz)), ptr(sb), 0, ref(desc(dyy)))
         if (sa is not None and need[2]) or (sb is not None and need[3]):
             c = x.shape[1]
-            dsa = torch.zeros(c, dtype=torch.float32, device=dev) if sa is not None else None
-            dsb = torch.zeros(c, dtype=torch.float32, device=dev) if sb is not None else None
+            dsa = lib.zeros(c, torch.float32, dev) if sa is not None else None
+            dsb = lib.zeros(c, torch.float32, dev) if sb is not None else None
             call("nasb_axpby_bwd_params", ref(desc(dz)), ref(desc(x)), ref(desc(y)) if y is not None else None, ptr(dsa),
                  ptr(dsb), None)
         return dx, dyy, dsa, dsb, None

@@ -41,7 +41,7 @@ _SIG = {
     "nasb_pw_tc_wgrad_supported": [_I, _I],
     "nasb_pw_tc_wgrad": [_TP, _TP, _P, _P],
     "nasb_pw_tc_fwd": [_TP, _P, _I, _P, _P, _I, _TP, _TP, _P, _P],
-    "nasb_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    "nasb_bn_finalize": [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     "nasb_dwconv_fwd": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P],
     "nasb_dwconv_dgrad": [_TP, _P, _I, _I, _I, _I, _TP, _P],
     "nasb_dwconv_wgrad": [_TP, _I, _TP, _I, _I, _I, _I, _P, _P],
@@ -50,7 +50,7 @@ _SIG = {
     "nasb_dwconv_wgrad_tile": [_TP, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_bn_fold": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "nasb_bn_stats_workspace": [_I],
-    "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
+    "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "nasb_affine_act": [_TP, _P, _P, _I, _TP, _P],
     "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
     "nasb_pool3x3_fwd": [_TP, _I, _I, _TP, _P, _P],
@@ -270,6 +270,53 @@ def ref(d):
 
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _ZeroArena:
+    """Zero-initialised scratch for one training iteration (gradient accumulators of the atomically-reduced kernels,
+    fp64 statistics cells): one memset per iteration instead of ~300 two-microsecond fill kernels.  The engine's step
+    functions bracket an iteration with begin()/end(); outside of that take() is plain torch.zeros.  A tensor taken in
+    iteration i is zeroed again by begin() of iteration i+1, so only the engine loops (which drop gradients with
+    zero_grad() every iteration) switch it on."""
+
+    def __init__(self):
+        self.buf, self.off, self.active, self.need = None, 0, False, 0
+
+    def begin(self, device):
+        want = max(int(self.need * 1.25) + 4096, 1 << 20)
+        if self.buf is None or self.buf.device != device or self.buf.numel() < self.need:
+            if torch.cuda.is_current_stream_capturing():  # never (re)allocate inside a capture: fall back for this step
+                self.active = False
+                return
+            self.buf = torch.empty(want, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.off, self.active = 0, True
+
+    def end(self):
+        self.active = False
+
+    def take(self, shape, dtype, device):
+        if isinstance(shape, int):
+            shape = (shape,)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 15) // 16 * 16
+        if self.active:
+            self.need = max(self.need, self.off + nbytes)
+        if not self.active or self.buf is None or self.buf.device != torch.device(device) or self.off + nbytes > self.buf.numel():
+            return torch.zeros(shape, dtype=dtype, device=device)
+        t = self.buf[self.off:self.off + nbytes].view(dtype)[:n].view(shape)
+        self.off += nbytes
+        return t
+
+
+zero_arena = _ZeroArena()
+
+
+def zeros(shape, dtype, device):
+    """Zero-filled tensor: from the per-iteration arena inside an engine step, torch.zeros otherwise."""
+    return zero_arena.take(shape, dtype, device)
 
 
 _ws = {}

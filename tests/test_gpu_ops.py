@@ -201,7 +201,7 @@ def test_bf16_bn_affine_and_backward_vs_torch(act):
         rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
         sm, sr, sc, sh = (torch.empty(c, device="cuda") for _ in range(4))
         ws = lib.workspace(torch.device("cuda"), 1 << 20)
-        call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(sm), ptr(sr), ptr(sc), ptr(sh), ptr(ws))
+        call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(sm), ptr(sr), ptr(sc), ptr(sh), None, ptr(ws))
         y = lib.new_act(n, c, h, w, torch.bfloat16, "cuda")
         call("nasb_affine_act", ref(desc(z)), ptr(sc), ptr(sh), act, ref(desc(y)))
         dz = lib.new_act(n, c, h, w, torch.bfloat16, "cuda")

@@ -115,7 +115,7 @@ def _():
             rm, rv, sm, sr, sc, sh = (torch.zeros(c, device=DEV) for _ in range(6))
             ws = lib.workspace(DEV, 1 << 20)
             sets.append(lambda z=z, g=g, b=b, rm=rm, rv=rv, sm=sm, sr=sr, sc=sc, sh=sh, ws=ws: call(
-                "nasb_bn_stats", ref(desc(z)), ptr(g), ptr(b), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(sm), ptr(sr), ptr(sc), ptr(sh), ptr(ws)))
+                "nasb_bn_stats", ref(desc(z)), ptr(g), ptr(b), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(sm), ptr(sr), ptr(sc), ptr(sh), None, ptr(ws)))
         report("bn_stats[%dx%dx%dx%d]" % (n, h, w, c), timeit(sets), nb)
 
 
