@@ -269,25 +269,15 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs
     }
 }
 
-// dgamma += sum g*xhat ; dbeta += sum g ; coef[0..C) = mean g ; coef[C..2C) = mean g*xhat  (fp32, aliased after ws);
-// k (optional, [4][C]): the per-channel constants of bn_bwd_dz_bf16_kernel (mask scale, mask shift, A, B)
-__global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, float *dgamma, float *dbeta, float *coef,
-                                       const float *scale, const float *shift, const float *mean, const float *rstd, float *k) {
+// dgamma += sum g*xhat ; dbeta += sum g ; coef[0..C) = mean g ; coef[C..2C) = mean g*xhat  (fp32, aliased after ws)
+__global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, float *dgamma, float *dbeta, float *coef) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s1 = ws[c], s2 = ws[C + c];
     if (dbeta) dbeta[c] += (float)s1;
     if (dgamma) dgamma[c] += (float)s2;
-    const float k1 = (float)(s1 / (double)P), k2 = (float)(s2 / (double)P);
-    coef[c] = k1;
-    coef[C + c] = k2;
-    if (k) {
-        const float s = scale ? scale[c] : 1.f, r = rstd[c];
-        k[c] = s;
-        k[C + c] = shift[c];
-        k[2 * C + c] = -s * k2 * r;
-        k[3 * C + c] = s * (k2 * r * mean[c] - k1);
-    }
+    coef[c] = (float)(s1 / (double)P);
+    coef[C + c] = (float)(s2 / (double)P);
 }
 
 template <typename T, int V>
@@ -435,15 +425,60 @@ __device__ __forceinline__ void ldc8(const float *p, int c0, float def, float2 (
     for (int j = 0; j < 4; ++j) o[j] = p ? make_float2(p[c0 + 2 * j], p[c0 + 2 * j + 1]) : make_float2(def, def);
 }
 
+// Optional statistics finalisation folded into the pass (training mode with statistics accumulated by the conv kernel):
+// every thread derives scale / shift of ITS 8 channels from the fp64 sums with exactly the arithmetic of
+// bn_stats_finalize_kernel; block 0 additionally publishes save_mean / save_rstd / scale / shift, updates the running
+// statistics and the step counter.  Saves one launch (and one dependency bubble) per BatchNorm.
+struct BnFin {
+    const double *sums;  // [2][C] or null
+    long long P;
+    const float *gamma, *beta;
+    float eps, momentum;
+    float *running_mean, *running_var, *save_mean, *save_rstd, *scale, *shift;
+    long long *nbt;
+};
+
 template <bool DESC>
 __global__ void __launch_bounds__(256, 4) affine_act_bf16_kernel(const bf16 *z, int z_cs, const float *scale, const float *shift,
-                                                                 int act, bf16 *y, int y_cs, long long P, int C) {
+                                                                 int act, bf16 *y, int y_cs, long long P, int C, const BnFin fin) {
     const int CV = C / 8, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
     if (pl >= PL) return;
     float2 s[4], b[4];
-    ldc8(scale, c0, 1.f, s);
-    ldc8(shift, c0, 0.f, b);
+    if (fin.sums) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const double mean = fin.sums[c] / (double)fin.P;
+            double var = fin.sums[C + c] / (double)fin.P - mean * mean;  // biased
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)fin.eps));
+            const float g = fin.gamma ? fin.gamma[c] : 1.f, be = fin.beta ? fin.beta[c] : 0.f;
+            sc[j] = g * rstd;
+            sh[j] = be - (float)mean * sc[j];
+            if (blockIdx.x == 0 && pl == 0) {
+                if (fin.save_mean) fin.save_mean[c] = (float)mean;
+                if (fin.save_rstd) fin.save_rstd[c] = rstd;
+                if (fin.running_mean) fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mean;
+                if (fin.running_var) {
+                    const double unb = fin.P > 1 ? var * (double)fin.P / (double)(fin.P - 1) : var;
+                    fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unb;
+                }
+                fin.scale[c] = sc[j];
+                fin.shift[c] = sh[j];
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && fin.nbt) *fin.nbt += 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s[j] = make_float2(sc[2 * j], sc[2 * j + 1]);
+            b[j] = make_float2(sh[2 * j], sh[2 * j + 1]);
+        }
+    } else {
+        ldc8(scale, c0, 1.f, s);
+        ldc8(shift, c0, 0.f, b);
+    }
     const long long G = (long long)gridDim.x * PL;
     for (long long m0 = (long long)blockIdx.x * PL + pl; m0 < P; m0 += BN_PX * G) {
         uint4 r[BN_PX];
@@ -538,18 +573,43 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_sums_bf16_kernel(const bf16 *dy
 }
 
 // dz = sg * gate(g) + A*v + B   (training mode only: sg = scale, A = -scale*k2*rstd, B = scale*(k2*rstd*mean - k1)).
-// The constants are prepared by bn_bwd_finalize_kernel, so the stream kernel holds 4 vectors in registers, not 7.
 __global__ void __launch_bounds__(256, 3) bn_bwd_dz_bf16_kernel(const bf16 *dy, int dy_cs, const bf16 *yz, int yz_cs,
-                                                                const float *k, float lo, float hi, bf16 *dz,
-                                                                int dz_cs, long long P, int C) {
+                                                                const double *ws, const float *scale, const float *shift,
+                                                                const float *mean, const float *rstd, float *dgamma,
+                                                                float *dbeta, float lo, float hi, bf16 *dz, int dz_cs,
+                                                                long long P, int C) {
     const int CV = C / 8, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
     if (pl >= PL) return;
-    float2 sg[4], mb[4], A[4], B[4];  // training mode: the mask's pre-activation is z*scale + shift, so its scale is sg
-    ldc8(k, c0, 1.f, sg);
-    ldc8(k + C, c0, 0.f, mb);
-    ldc8(k + 2 * C, c0, 0.f, A);
-    ldc8(k + 3 * C, c0, 0.f, B);
+    // The reduction's finalisation is folded in: every thread turns the fp64 sums of ITS 8 channels into the constants of
+    // dz = sg * gate(g) + A*v + B; block 0 also accumulates dgamma / dbeta (what bn_bwd_finalize_kernel did in a launch of
+    // its own).  Training mode: the mask's pre-activation is z*scale + shift, so its scale is sg.
+    float2 sg[4], mb[4], A[4], B[4];
+    {
+        float t[4][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const double s1 = ws[c], s2 = ws[C + c];
+            const float k1 = (float)(s1 / (double)P), k2 = (float)(s2 / (double)P);
+            const float sc = scale ? scale[c] : 1.f, r = rstd[c];
+            t[0][j] = sc;
+            t[1][j] = shift[c];
+            t[2][j] = -sc * k2 * r;
+            t[3][j] = sc * (k2 * r * mean[c] - k1);
+            if (blockIdx.x == 0 && pl == 0) {
+                if (dbeta) dbeta[c] += (float)s1;
+                if (dgamma) dgamma[c] += (float)s2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sg[j] = make_float2(t[0][2 * j], t[0][2 * j + 1]);
+            mb[j] = make_float2(t[1][2 * j], t[1][2 * j + 1]);
+            A[j] = make_float2(t[2][2 * j], t[2][2 * j + 1]);
+            B[j] = make_float2(t[3][2 * j], t[3][2 * j + 1]);
+        }
+    }
     const long long G = (long long)gridDim.x * PL;
     for (long long m0 = (long long)blockIdx.x * PL + pl; m0 < P; m0 += BN_PX * G) {
         uint4 rg[BN_PX], rv[BN_PX];
@@ -642,8 +702,8 @@ extern "C" int nasb_bn_fold(const float *gamma, const float *beta, const float *
     return 0;
 }
 
-// 2*C doubles for the sums, 2*C floats for the backward coefficients, 4*C floats for the dz constants
-extern "C" long long nasb_bn_stats_workspace(int C) { return (long long)C * (2 * 8 + 2 * 4 + 4 * 4); }
+// 2*C doubles for the sums, then 2*C floats for the backward coefficients
+extern "C" long long nasb_bn_stats_workspace(int C) { return (long long)C * (2 * 8 + 2 * 4); }
 
 extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const float *beta, float eps, float momentum,
                              float *running_mean, float *running_var, float *save_mean, float *save_rstd, float *scale,
@@ -701,7 +761,7 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
         if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
             // descending: z was just written front-to-back by the convolution, its tail is still in L2
             affine_act_bf16_kernel<true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
-                                                                 (bf16 *)y->ptr, y->cstride, P, C);
+                                                                 (bf16 *)y->ptr, y->cstride, P, C, BnFin{});
             NASB_CHECK_LAUNCH();
             return 0;
         }
@@ -731,6 +791,29 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
     return 0;
 }
 
+// nasb_bn_finalize followed by nasb_affine_act in one launch where the layout allows (bf16, 16-byte channel vectors);
+// otherwise the two kernels run back to back.  Same results either way.
+extern "C" int nasb_bn_finalize_affine_act(const double *sums, long long P, const NasbTensor *z, const float *gamma,
+                                           const float *beta, float eps, float momentum, float *running_mean,
+                                           float *running_var, float *save_mean, float *save_rstd, float *scale, float *shift,
+                                           long long *num_batches_tracked, int act, const NasbTensor *y, void *stream) {
+    if (!sums || !z || !y || !scale || !shift || P <= 0 || npix(*z) != P || npix(*y) != P || z->c != y->c || z->dtype != y->dtype)
+        return NASB_ERR_BAD_ARG;
+    const int C = z->c;
+    int blocks;
+    if (!(bn_safe() & 8) && z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
+        BnFin f{sums, P, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift, num_batches_tracked};
+        affine_act_bf16_kernel<true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act, (bf16 *)y->ptr,
+                                                             y->cstride, P, C, f);
+        NASB_CHECK_LAUNCH();
+        return 0;
+    }
+    int rc = nasb_bn_finalize(sums, P, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift,
+                              num_batches_tracked, stream);
+    if (rc) return rc;
+    return nasb_affine_act(z, scale, shift, act, y, stream);
+}
+
 extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,
                                const float *beta, const float *scale, const float *shift, const float *save_mean,
                                const float *save_rstd, int training, float *dgamma, float *dbeta, const NasbTensor *dz,
@@ -752,7 +835,6 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
     int C = dy->c;
     double *ws = (double *)workspace;
     float *coef = (float *)(ws + 2 * C);
-    float *kdz = coef + 2 * C;
     bool need_sums = training || dgamma || dbeta;
     const float lo = act == NASB_ACT_NONE ? -INFINITY : 0.f, hi = act == NASB_ACT_RELU6 ? 6.f : INFINITY;
     {
@@ -767,10 +849,9 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
             bn_bwd_sums_bf16_kernel<<<blocks, 256, smem, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
                                                                scale, shift, save_mean, save_rstd, lo, hi, P, C, ws, rows);
             NASB_CHECK_LAUNCH();
-            bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef, scale, shift, save_mean, save_rstd, kdz);
-            NASB_CHECK_LAUNCH();
-            bn_bwd_dz_bf16_kernel<<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
-                                                            kdz, lo, hi, (bf16 *)dz->ptr, dz->cstride, P, C);
+            bn_bwd_dz_bf16_kernel<<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride, ws,
+                                                            scale, shift, save_mean, save_rstd, dgamma, dbeta, lo, hi,
+                                                            (bf16 *)dz->ptr, dz->cstride, P, C);
             NASB_CHECK_LAUNCH();
             return 0;
         }
@@ -804,7 +885,7 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
                                                                     gamma, beta, P, C, ws, rows);
         }
         NASB_CHECK_LAUNCH();
-        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef, nullptr, nullptr, nullptr, nullptr, nullptr);
+        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef);
         NASB_CHECK_LAUNCH();
     }
     {

@@ -194,17 +194,20 @@ class _ConvUnit(torch.autograd.Function):
             if fused_stats or (dw and not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and _dw_stats_on()):
                 sums = lib.zeros(2 * cout, torch.float64, dev)
                 fused_stats = bool(run_conv(z, None, None, ACT_NONE, None, sums)) or fused_stats
-            if fused_stats:  # batch statistics were accumulated by the conv kernel's epilogue
-                call("nasb_bn_finalize", ptr(sums), C.c_longlong(n * oh * ow), cout, ptr(gamma), ptr(beta), float(bn.eps),
-                     mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]),
-                     ptr(bn.num_batches_tracked))
+            applied = False
+            if fused_stats:  # batch statistics were accumulated by the conv kernel's epilogue: finalise + apply in one launch
+                call("nasb_bn_finalize_affine_act", ptr(sums), C.c_longlong(n * oh * ow), ref(desc(z)), ptr(gamma), ptr(beta),
+                     float(bn.eps), mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]),
+                     ptr(ss[1]), ptr(bn.num_batches_tracked), act, ref(desc(y)))
+                applied = True
             else:
                 if sums is None:
                     run_conv(z, None, None, ACT_NONE, None)
                 call("nasb_bn_stats", ref(desc(z)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
                      ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(bn.num_batches_tracked),
                      ptr(_ws(dev, cout)))
-            call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
+            if not applied:
+                call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
             if res is not None and not late_res:
                 call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
         ctx.stem_tc = stem_tc

@@ -52,6 +52,7 @@ _SIG = {
     "nasb_bn_stats_workspace": [_I],
     "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "nasb_affine_act": [_TP, _P, _P, _I, _TP, _P],
+    "nasb_bn_finalize_affine_act": [_P, _L, _TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _TP, _P],
     "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
     "nasb_pool3x3_fwd": [_TP, _I, _I, _TP, _P, _P],
     "nasb_pool3x3_bwd": [_TP, _I, _I, _P, _TP, _P],
@@ -85,7 +86,7 @@ EXPORTS = tuple(sorted(_SIG))
 _lib = None
 launches = 0  # kernels launched through the C ABI by this process (bench.py reports the delta over its timed region)
 # kernels (and async memsets) behind one call of each entry point; everything not listed launches exactly one
-_KERNELS_PER_CALL = {"nasb_bn_stats": 3, "nasb_bn_act_bwd": 4, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
+_KERNELS_PER_CALL = {"nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
                      "nasb_spatial_mean": 2, "nasb_spatial_sum": 2}
 _prof = None  # list of (key, bytes, ev0, ev1) while profiling
 
