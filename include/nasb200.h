@@ -182,11 +182,13 @@ int nasb_affine_act(const NasbTensor *z, const float *scale, const float *shift,
                     void *stream);
 /* nasb_bn_finalize + nasb_affine_act as ONE launch (training mode, statistics accumulated by the convolution kernel):
  * every thread derives scale/shift of its channels from the fp64 sums, block 0 publishes them with the saved / running
- * statistics and the step counter.  Falls back to the two kernels for layouts the fused pass does not cover. */
+ * statistics and the step counter; res (optional) is added after the activation (residual blocks: the block output is
+ * written directly, y = act(BN(z)) is never materialised -- the backward pass works from z).  Falls back to separate
+ * kernels for layouts the fused pass does not cover. */
 int nasb_bn_finalize_affine_act(const double *sums, long long P, const NasbTensor *z, const float *gamma, const float *beta,
                                 float eps, float momentum, float *running_mean, float *running_var, float *save_mean,
                                 float *save_rstd, float *scale, float *shift, long long *num_batches_tracked, int act,
-                                const NasbTensor *y, void *stream);
+                                const NasbTensor *res, const NasbTensor *y, void *stream);
 int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,
                     const float *beta, const float *scale, const float *shift, const float *save_mean,
                     const float *save_rstd, int training, float *dgamma, float *dbeta, const NasbTensor *dz,

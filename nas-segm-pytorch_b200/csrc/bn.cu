@@ -440,7 +440,8 @@ struct BnFin {
 
 template <bool DESC>
 __global__ void __launch_bounds__(256, 4) affine_act_bf16_kernel(const bf16 *z, int z_cs, const float *scale, const float *shift,
-                                                                 int act, bf16 *y, int y_cs, long long P, int C, const BnFin fin) {
+                                                                 int act, bf16 *y, int y_cs, long long P, int C, const BnFin fin,
+                                                                 const bf16 *res, int res_cs) {
     const int CV = C / 8, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
     if (pl >= PL) return;
@@ -481,13 +482,16 @@ __global__ void __launch_bounds__(256, 4) affine_act_bf16_kernel(const bf16 *z, 
     }
     const long long G = (long long)gridDim.x * PL;
     for (long long m0 = (long long)blockIdx.x * PL + pl; m0 < P; m0 += BN_PX * G) {
-        uint4 r[BN_PX];
+        uint4 r[BN_PX], rr[BN_PX];
         long long m[BN_PX];
 #pragma unroll
         for (int k = 0; k < BN_PX; ++k) {
             const long long mm = m0 + k * G;
             m[k] = mm < P ? (DESC ? P - 1 - mm : mm) : -1;
-            if (m[k] >= 0) r[k] = ldg16(z + m[k] * z_cs + c0);
+            if (m[k] >= 0) {
+                r[k] = ldg16(z + m[k] * z_cs + c0);
+                if (res) rr[k] = ldg16(res + m[k] * res_cs + c0);
+            }
         }
 #pragma unroll
         for (int k = 0; k < BN_PX; ++k) {
@@ -496,6 +500,15 @@ __global__ void __launch_bounds__(256, 4) affine_act_bf16_kernel(const bf16 *z, 
             cvt8(r[k], v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = act2(ffma2(v[j], s[j], b[j]), act);
+            if (res) {  // residual added AFTER the activation (InvertedResidual: x + conv(x)); the backward pass works from z
+                float2 q[4];
+                cvt8(rr[k], q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j].x += q[j].x;
+                    v[j].y += q[j].y;
+                }
+            }
             uint4 o;
             o.x = pack_bf16x2(v[0].x, v[0].y);
             o.y = pack_bf16x2(v[1].x, v[1].y);
@@ -761,7 +774,7 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
         if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
             // descending: z was just written front-to-back by the convolution, its tail is still in L2
             affine_act_bf16_kernel<true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
-                                                                 (bf16 *)y->ptr, y->cstride, P, C, BnFin{});
+                                                                 (bf16 *)y->ptr, y->cstride, P, C, BnFin{}, nullptr, 0);
             NASB_CHECK_LAUNCH();
             return 0;
         }
@@ -796,22 +809,28 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
 extern "C" int nasb_bn_finalize_affine_act(const double *sums, long long P, const NasbTensor *z, const float *gamma,
                                            const float *beta, float eps, float momentum, float *running_mean,
                                            float *running_var, float *save_mean, float *save_rstd, float *scale, float *shift,
-                                           long long *num_batches_tracked, int act, const NasbTensor *y, void *stream) {
+                                           long long *num_batches_tracked, int act, const NasbTensor *res, const NasbTensor *y,
+                                           void *stream) {
     if (!sums || !z || !y || !scale || !shift || P <= 0 || npix(*z) != P || npix(*y) != P || z->c != y->c || z->dtype != y->dtype)
         return NASB_ERR_BAD_ARG;
+    if (res && (res->dtype != y->dtype || res->c != y->c || npix(*res) != P)) return NASB_ERR_BAD_ARG;
     const int C = z->c;
     int blocks;
-    if (!(bn_safe() & 8) && z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
+    if (!(bn_safe() & 8) && z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && (!res || vec_ok(*res, 8)) &&
+        fixed_cfg(C, 8, P, blocks)) {
         BnFin f{sums, P, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift, num_batches_tracked};
         affine_act_bf16_kernel<true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act, (bf16 *)y->ptr,
-                                                             y->cstride, P, C, f);
+                                                             y->cstride, P, C, f, res ? (const bf16 *)res->ptr : nullptr,
+                                                             res ? res->cstride : 0);
         NASB_CHECK_LAUNCH();
         return 0;
     }
     int rc = nasb_bn_finalize(sums, P, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift,
                               num_batches_tracked, stream);
     if (rc) return rc;
-    return nasb_affine_act(z, scale, shift, act, y, stream);
+    rc = nasb_affine_act(z, scale, shift, act, y, stream);
+    if (rc || !res) return rc;
+    return nasb_resize_axpby(y, nullptr, res, nullptr, 0, y, stream);  // y += res
 }
 
 extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const NasbTensor *z, int act, const float *gamma,

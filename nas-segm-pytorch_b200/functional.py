@@ -169,6 +169,7 @@ class _ConvUnit(torch.autograd.Function):
                      ptr(scale), ptr(shift), a, ref(desc(r)) if r is not None else None, ref(desc(out)))
 
         z = ss = sv = None
+        res_done = False
         y = lib.new_act(n, cout, oh, ow, out_dtype, dev)
         # The residual add is fused into the conv epilogue only when no gradient is needed: the backward pass
         # rebuilds xhat / the activation mask from the unit's own output, which must then exclude the residual.
@@ -196,10 +197,12 @@ class _ConvUnit(torch.autograd.Function):
                 fused_stats = bool(run_conv(z, None, None, ACT_NONE, None, sums)) or fused_stats
             applied = False
             if fused_stats:  # batch statistics were accumulated by the conv kernel's epilogue: finalise + apply in one launch
+                # (+ the residual: training-mode backward rebuilds everything from z, so y itself is never needed)
                 call("nasb_bn_finalize_affine_act", ptr(sums), C.c_longlong(n * oh * ow), ref(desc(z)), ptr(gamma), ptr(beta),
                      float(bn.eps), mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]),
-                     ptr(ss[1]), ptr(bn.num_batches_tracked), act, ref(desc(y)))
+                     ptr(ss[1]), ptr(bn.num_batches_tracked), act, ref(desc(res)) if res is not None else None, ref(desc(y)))
                 applied = True
+                res_done = res is not None
             else:
                 if sums is None:
                     run_conv(z, None, None, ACT_NONE, None)
@@ -208,13 +211,13 @@ class _ConvUnit(torch.autograd.Function):
                      ptr(_ws(dev, cout)))
             if not applied:
                 call("nasb_affine_act", ref(desc(z)), ptr(ss[0]), ptr(ss[1]), act, ref(desc(y)))
-            if res is not None and not late_res:
+            if res is not None and not late_res and not res_done:
                 call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
         ctx.stem_tc = stem_tc
         ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
         ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
         ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
-        if late_res:
+        if late_res and not res_done:
             out = lib.new_act(n, cout, oh, ow, out_dtype, dev)
             call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(out)))
             return out

@@ -52,7 +52,7 @@ _SIG = {
     "nasb_bn_stats_workspace": [_I],
     "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "nasb_affine_act": [_TP, _P, _P, _I, _TP, _P],
-    "nasb_bn_finalize_affine_act": [_P, _L, _TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _TP, _P],
+    "nasb_bn_finalize_affine_act": [_P, _L, _TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I, _TP, _TP, _P],
     "nasb_bn_act_bwd": [_TP, _TP, _TP, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _TP, _P, _P],
     "nasb_pool3x3_fwd": [_TP, _I, _I, _TP, _P, _P],
     "nasb_pool3x3_bwd": [_TP, _I, _I, _P, _TP, _P],
