@@ -278,20 +278,36 @@ class _ZeroArena:
     fp64 statistics cells): one memset per iteration instead of ~300 two-microsecond fill kernels.  The engine's step
     functions bracket an iteration with begin()/end(); outside of that take() is plain torch.zeros.  A tensor taken in
     iteration i is zeroed again by begin() of iteration i+1, so only the engine loops (which drop gradients with
-    zero_grad() every iteration) switch it on."""
+    zero_grad() every iteration) switch it on.
+
+    The buffer of a device is allocated ONCE (CAPACITY bytes) and never replaced: a captured CUDA graph bakes in its
+    address (the memset and every view), and a graph of an earlier model may still be replayed after a larger model has
+    come along.  begin() clears only the prefix that earlier iterations were seen to need (the high-water mark, which
+    only grows); a take() that does not fit into the cleared prefix -- the first iteration of a model, or demand beyond
+    CAPACITY -- is served by torch.zeros."""
+
+    CAPACITY = 64 << 20
 
     def __init__(self):
-        self.buf, self.off, self.active, self.need = None, 0, False, 0
+        self.bufs, self.high = {}, {}
+        self.buf, self.off, self.cleared, self.active = None, 0, 0, False
+
+    @staticmethod
+    def _capturing(device):
+        return device.type == "cuda" and torch.cuda.is_current_stream_capturing()
 
     def begin(self, device):
-        want = max(int(self.need * 1.25) + 4096, 1 << 20)
-        if self.buf is None or self.buf.device != device or self.buf.numel() < self.need:
-            if torch.cuda.is_current_stream_capturing():  # never (re)allocate inside a capture: fall back for this step
+        device = torch.device(device)
+        buf = self.bufs.get(device)
+        if buf is None:
+            if self._capturing(device):  # never allocate the long-lived buffer from a graph's private pool
                 self.active = False
                 return
-            self.buf = torch.empty(want, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        self.off, self.active = 0, True
+            buf = self.bufs[device] = torch.empty(self.CAPACITY, dtype=torch.uint8, device=device)
+        n = min((self.high.get(device, 0) * 5 // 4 + 4095) // 4096 * 4096, self.CAPACITY)
+        if n:
+            buf[:n].zero_()
+        self.buf, self.off, self.cleared, self.active = buf, 0, n, True
 
     def end(self):
         self.active = False
@@ -302,14 +318,14 @@ class _ZeroArena:
         n = 1
         for d in shape:
             n *= int(d)
-        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 15) // 16 * 16
-        if self.active:
-            self.need = max(self.need, self.off + nbytes)
-        if not self.active or self.buf is None or self.buf.device != torch.device(device) or self.off + nbytes > self.buf.numel():
-            return torch.zeros(shape, dtype=dtype, device=device)
-        t = self.buf[self.off:self.off + nbytes].view(dtype)[:n].view(shape)
-        self.off += nbytes
-        return t
+        if self.active and self.buf is not None and self.buf.device == torch.device(device):
+            nbytes = (n * torch.empty((), dtype=dtype).element_size() + 15) // 16 * 16
+            start, self.off = self.off, self.off + nbytes
+            if self.off > self.high.get(self.buf.device, 0):
+                self.high[self.buf.device] = self.off
+            if self.off <= self.cleared:
+                return self.buf[start:start + nbytes].view(dtype)[:n].view(shape)
+        return torch.zeros(shape, dtype=dtype, device=device)
 
 
 zero_arena = _ZeroArena()

@@ -141,3 +141,45 @@ def test_try_except_convention():
     assert boom(RuntimeError) == 0
     with pytest.raises(ValueError):
         boom(ValueError)
+
+
+def test_zero_arena_host_logic():
+    """The per-iteration zero arena (lib.zero_arena): inactive outside begin()/end(); the first iteration of a model is
+    served by torch.zeros while the demand is recorded; later iterations hand out disjoint, 16-byte aligned, zeroed views of
+    ONE buffer that is never reallocated (captured graphs keep its address); begin() re-zeroes what the previous
+    iteration wrote; demand beyond the cleared prefix falls back to torch.zeros."""
+    import torch
+    from nas_segm_b200 import lib
+    ar = lib._ZeroArena()
+    ar.CAPACITY = 1 << 16
+    cpu = torch.device("cpu")
+    t = ar.take((3, 5), torch.float32, cpu)
+    assert t.shape == (3, 5) and float(t.abs().sum()) == 0 and not ar.active
+
+    def iteration(extra=0):
+        ar.begin(cpu)
+        outs = [ar.take((7,), torch.float32, cpu), ar.take(10, torch.float64, cpu), ar.take((4, 3, 1, 1), torch.float32, cpu)]
+        if extra:
+            outs.append(ar.take(extra, torch.float32, cpu))
+        for o in outs:
+            assert float(o.abs().sum()) == 0
+            o += 1.0  # what the kernels do: accumulate
+        ar.end()
+        return outs
+
+    first = iteration()
+    buf = ar.bufs[cpu]
+    base, size = buf.data_ptr(), buf.numel()
+    assert all(not (base <= o.data_ptr() < base + size) for o in first)      # demand was unknown: torch.zeros
+    second = iteration()
+    assert all(base <= o.data_ptr() < base + size and o.data_ptr() % 16 == 0 for o in second)
+    spans = sorted((o.data_ptr(), o.data_ptr() + o.numel() * o.element_size()) for o in second)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))               # disjoint
+    assert second[1].dtype == torch.float64 and second[2].shape == (4, 3, 1, 1)
+    third = iteration()
+    assert ar.bufs[cpu] is buf and [o.data_ptr() for o in third] == [o.data_ptr() for o in second]  # same addresses, re-zeroed
+    big = iteration(extra=1 << 20)                                           # more than CAPACITY: falls back, never reallocates
+    assert ar.bufs[cpu] is buf and not (base <= big[-1].data_ptr() < base + size) and float(big[-1].sum()) == (1 << 20)
+    again = iteration()
+    assert all(base <= o.data_ptr() < base + size for o in again)
+    assert float(ar.take(4, torch.float32, cpu).sum()) == 0 and not ar.active  # outside an iteration: plain zeros
