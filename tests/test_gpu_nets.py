@@ -1,5 +1,7 @@
 """GPU parity of whole networks (encoder + decoder) against fixtures from the real reference: logits within 1e-3
 relative (north_star) in fp32 mode -- in practice ~1e-5; one training step (loss + gradients); bf16 mode sanity."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -204,3 +206,48 @@ def test_cuda_graph_forward_matches_eager(golden):
             assert torch.equal(g(x2), ref2)
         finally:
             nas_segm_b200.set_act_dtype(torch.float32)
+
+
+@pytest.mark.skipif(not os.environ.get("NASB_FULLSIZE_TESTS"), reason="opt-in (NASB_FULLSIZE_TESTS=1): written after the "
+                    "round's GPU budget was spent; not yet run to completion on a B200")
+def test_full_size_properties_2048x1024():
+    """BASELINE size (2048x1024, WACV arch0, speed mode) through size-independent properties: images of a batch do not
+    interact in eval mode (batch of 2 == each image alone: exercises every tile / tail / persistent-loop path at full
+    size), the fused CE equals torch's CE on the same logits, and the fused upsample+argmax+histogram reward path counts
+    every valid pixel exactly once with the ground-truth marginals."""
+    from nas_segm_b200 import functional as Fn
+    torch.manual_seed(0)
+    from nas_segm_b200.nn.encoders import mbv2
+    from nas_segm_b200.nn.micro_decoders import TemplateDecoder
+    from golden_util import W0
+    nas_segm_b200.set_act_dtype(torch.bfloat16)
+    try:
+        enc = mbv2(return_layers=[1, 2])
+        dec = TemplateDecoder(list(enc.out_sizes), 19, W0, agg_size=64, repeats=2)
+        for m in list(enc.modules()) + list(dec.modules()):
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        enc, dec = enc.cuda().eval(), dec.cuda().eval()
+        g = torch.Generator().manual_seed(9314)
+        x = torch.randn(2, 3, 1024, 2048, generator=g).cuda()
+        with torch.no_grad():
+            out = dec(enc(x))
+            o0, o1 = dec(enc(x[0:1].contiguous())), dec(enc(x[1:2].contiguous()))
+        assert out.shape == (2, 19, 256, 512) and out.dtype == torch.float32
+        assert torch.isfinite(out).all()
+        scale = float(out.abs().max())
+        assert float((out[0:1] - o0).abs().max()) <= 1e-6 * scale and float((out[1:2] - o1).abs().max()) <= 1e-6 * scale
+        y = torch.randint(0, 19, (2, 256, 512), generator=g)
+        y[torch.rand(2, 256, 512, generator=g) < 0.05] = 255
+        y = y.cuda()
+        loss = Fn.cross_entropy2d(out, y, 255)
+        ref = torch.nn.functional.cross_entropy(out, y, ignore_index=255)
+        assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        gt = torch.randint(0, 21, (2, 1024, 2048), generator=g).to(torch.uint8).cuda()  # 19, 20 = out of range -> skipped
+        cm = Fn.confmat_logits(out, gt, 19).cpu().numpy()
+        gtn = gt.cpu().numpy()
+        assert cm.sum() == int((gtn < 19).sum())
+        assert (cm.sum(1) == np.bincount(gtn[gtn < 19].ravel(), minlength=19)).all()
+    finally:
+        nas_segm_b200.set_act_dtype(torch.float32)
