@@ -15,6 +15,12 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # A deadlocked kernel (mbarrier wait that never completes) would otherwise block the whole run: with pytest-timeout
+    # present every test gets a generous ceiling and a stack dump instead.
+    if config.pluginmanager.hasplugin("timeout"):
+        for it in items:
+            if it.get_closest_marker("timeout") is None:
+                it.add_marker(pytest.mark.timeout(600, method="thread"))
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
