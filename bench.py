@@ -174,16 +174,24 @@ def oracle_step_fn(h, w, batch):
         O.template_decoder(O.mbv2_encoder(torch.zeros(2, 3, 32, 32), Pe, (1, 2)), Pd, W0, [24, 32], NUM_CLASSES, 64, 2)
     for P in (Pe, Pd):
         P.requires_grad_()
-    params = [v for P in (Pe, Pd) for v in P.sd.values() if v.requires_grad]
+    p_enc = [v for v in Pe.sd.values() if v.requires_grad]
+    p_dec = [v for v in Pd.sd.values() if v.requires_grad]
+    # the same iteration as the CUDA arm: forward, CE, backward, the two grad-norm clips, SGD (encoder) + Adam (decoder)
+    optim_enc = torch.optim.SGD(p_enc, lr=1e-3, momentum=0.9, weight_decay=1e-5)
+    optim_dec = torch.optim.Adam(p_dec, lr=3e-3, weight_decay=1e-5)
 
     def step():
         out = O.template_decoder(O.mbv2_encoder(img, Pe, (1, 2), True), Pd, W0, [24, 32], NUM_CLASSES, 64, 2, training=True)
         y = O.nearest_labels(lab, out.shape[2:])
         loss = O.segm_loss(out, y)
-        for p in params:
-            p.grad = None
+        optim_enc.zero_grad()
+        optim_dec.zero_grad()
         loss.backward()
-        return float(loss)
+        nn.utils.clip_grad_norm_(p_enc, 3.0)
+        nn.utils.clip_grad_norm_(p_dec, 3.0)
+        optim_enc.step()
+        optim_dec.step()
+        return float(loss.detach())
     return step
 
 
