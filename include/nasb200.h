@@ -121,6 +121,8 @@ int nasb_stem_im2col(const NasbTensor *img, int ks, int stride, int dil, int pad
  *                         with x = dz and the transposed pack.
  * -------------------------------------------------------------------------------------------------------*/
 int nasb_pack_weight_bf16(const float *w, int rows, int cols, int transpose, void *out, void *stream);
+/* both packs in one launch: out = [rows][Kp(cols)] (forward), out_t = [cols][Kp(rows)] (data gradient) */
+int nasb_pack_weight_bf16_both(const float *w, int rows, int cols, void *out, void *out_t, void *stream);
 int nasb_pw_tc_supported(int K, int N);
 int nasb_pw_tc_wgrad_supported(int Co, int Ci);
 /* dweight[co][ci] += sum_pixels dz[.,co]*x[.,ci] on the tensor cores (MN-major operands, TMEM accumulation). */

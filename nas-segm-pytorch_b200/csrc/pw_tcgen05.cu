@@ -317,8 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
 }
 
 // weight [rows][cols] fp32 (row-major) -> bf16 [R][Kp]:  transpose=0: out[r][k] = w[r][k] ; transpose=1: out[r][k] = w[k][r]
-__global__ void pack_weight_kernel(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_one(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp, int i) {
     if (i >= R * Kp) return;
     int r = i / Kp, k = i - r * Kp;
     float v = 0.f;
@@ -328,6 +327,15 @@ __global__ void pack_weight_kernel(const float *w, int rows, int cols, int trans
         if (k < rows && r < cols) v = w[(long long)k * cols + r];
     }
     out[i] = __float2bfloat16_rn(v);
+}
+__global__ void pack_weight_kernel(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp) {
+    pack_one(w, rows, cols, transpose, out, R, Kp, blockIdx.x * blockDim.x + threadIdx.x);
+}
+// both operand layouts in one launch: the forward pack and the transposed pack the data gradient will want
+__global__ void pack_weight_both_kernel(const float *w, int rows, int cols, bf16 *out, int Kp, bf16 *out_t, int Kp_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pack_one(w, rows, cols, 0, out, rows, Kp, i);
+    pack_one(w, rows, cols, 1, out_t, cols, Kp_t, i);
 }
 
 }  // namespace nasb
@@ -339,6 +347,16 @@ extern "C" int nasb_pack_weight_bf16(const float *w, int rows, int cols, int tra
     int R = transpose ? cols : rows, K = transpose ? rows : cols;
     int Kp = (K + 7) / 8 * 8;
     pack_weight_kernel<<<cdiv((long long)R * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, transpose, (bf16 *)out, R, Kp);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}
+
+// out = pack(w, transpose=0) [rows][Kp(cols)], out_t = pack(w, transpose=1) [cols][Kp(rows)] in one launch
+extern "C" int nasb_pack_weight_bf16_both(const float *w, int rows, int cols, void *out, void *out_t, void *stream) {
+    if (!w || !out || !out_t || rows <= 0 || cols <= 0) return NASB_ERR_BAD_ARG;
+    const int Kp = (cols + 7) / 8 * 8, Kp_t = (rows + 7) / 8 * 8;
+    const long long n = (long long)rows * Kp > (long long)cols * Kp_t ? (long long)rows * Kp : (long long)cols * Kp_t;
+    pack_weight_both_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, (bf16 *)out, Kp, (bf16 *)out_t, Kp_t);
     NASB_CHECK_LAUNCH();
     return 0;
 }

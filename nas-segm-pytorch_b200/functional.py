@@ -35,6 +35,11 @@ def _dw_stats_on():
     return config().fuse_dw_stats
 
 
+def _dual_pack_on():
+    from . import config
+    return config().dual_pack
+
+
 def _tiles_on():
     from . import config
     return config().use_tma_tiles
@@ -129,7 +134,14 @@ class _ConvUnit(torch.autograd.Function):
 
         use_tc = (not dw and ks == 1 and stride == 1 and pad == 0 and x1 is None and not in_relu and not image
                   and _tc_ok(x0, x0.shape[1], cout, out_dtype))
-        wpack = _pack_weight(weight, False) if use_tc else None
+        wpack = wpack_t = None
+        if use_tc and _dual_pack_on() and weight.requires_grad and x0.requires_grad:  # dgrad wants the transposed pack: one launch
+            cin = x0.shape[1]
+            wpack = torch.empty(cout * ((cin + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+            wpack_t = torch.empty(cin * ((cout + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+            call("nasb_pack_weight_bf16_both", ptr(weight), cout, cin, ptr(wpack), ptr(wpack_t))
+        elif use_tc:
+            wpack = _pack_weight(weight, False)
         # speed mode stem: image -> bf16 patch matrix [n, 32, oh, ow] (k = ci*9 + ky*3 + kx), then the pointwise tensor-core
         # kernel with K = 32; the patch matrix is what the backward pass keeps (weight gradient = nasb_pw_tc_wgrad)
         stem_tc = (image and not dw and ks == 3 and x1 is None and not in_relu and res is None and x0.shape[1] == 3
@@ -214,6 +226,7 @@ class _ConvUnit(torch.autograd.Function):
             if res is not None and not late_res and not res_done:
                 call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
         ctx.stem_tc = stem_tc
+        ctx.wpack_t = wpack_t
         ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
         ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
         ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
@@ -290,7 +303,8 @@ class _ConvUnit(torch.autograd.Function):
                      ACT_NONE, ref(desc(dx0)), None)
             elif (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image
                     and _tc_ok(dz, cout, x0.shape[1], x0.dtype)):
-                call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
+                wpt = ctx.wpack_t if ctx.wpack_t is not None else _pack_weight(weight, True)
+                call("nasb_pw_tc_fwd", ref(ddz), ptr(wpt), x0.shape[1], None, None, ACT_NONE, None,
                      ref(desc(dx0)), None)
             elif dw:
                 tiled = False

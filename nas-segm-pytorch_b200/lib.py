@@ -37,6 +37,7 @@ _SIG = {
     "nasb_stem_wgrad": [_TP, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_stem_im2col": [_TP, _I, _I, _I, _I, _TP, _P],
     "nasb_pack_weight_bf16": [_P, _I, _I, _I, _P, _P],
+    "nasb_pack_weight_bf16_both": [_P, _I, _I, _P, _P, _P],
     "nasb_pw_tc_supported": [_I, _I],
     "nasb_pw_tc_wgrad_supported": [_I, _I],
     "nasb_pw_tc_wgrad": [_TP, _TP, _P, _P],
