@@ -183,3 +183,37 @@ def test_zero_arena_host_logic():
     again = iteration()
     assert all(base <= o.data_ptr() < base + size for o in again)
     assert float(ar.take(4, torch.float32, cpu).sum()) == 0 and not ar.active  # outside an iteration: plain zeros
+
+
+def test_abi_host_side_contracts_without_a_gpu():
+    """Entry points that are pure host functions (shape envelopes, workspace sizes) and the argument validation of the
+    launchers: bad arguments come back as NASB_ERR_BAD_ARG (10002) / NASB_ERR_UNSUPPORTED (10001) before any CUDA call, so
+    this runs on a box without a device (no compute calls)."""
+    import ctypes as C
+    h = lib.load()
+    BAD, UNS = 10002, 10001
+    # shape envelopes of the tensor-core paths (include/nasb200.h)
+    assert h.nasb_pw_tc_supported(32, 32) == 1 and h.nasb_pw_tc_supported(448, 320) == 1 and h.nasb_pw_tc_supported(960, 320) == 0
+    assert h.nasb_pw_tc_supported(7, 32) == 0 and h.nasb_pw_tc_supported(32, 12) == 0 and h.nasb_pw_tc_supported(32, 8192) == 0
+    assert h.nasb_pw_tc_wgrad_supported(192, 32) == 1 and h.nasb_pw_tc_wgrad_supported(32, 264) == 0
+    assert h.nasb_conv3_tc_supported(64, 19) == 1
+    assert h.nasb_pack_conv3_elems(19, 64, 0) > 0
+    assert h.nasb_bn_stats_workspace(64) == 64 * (2 * 8 + 2 * 4) and h.nasb_loss_workspace() > 0
+    # argument validation
+    t32 = lib.NasbTensor(0x1000, 1, 4, 4, 8, 8, lib.F32)
+    t16 = lib.NasbTensor(0x1000, 1, 4, 4, 8, 8, lib.BF16)
+    img = lib.NasbTensor(0x1000, 1, 8, 8, 3, 3, lib.F32_NCHW)
+    r = C.byref
+    assert h.nasb_stem_im2col(None, 3, 2, 1, 1, None, None) == UNS
+    assert h.nasb_stem_im2col(r(img), 3, 2, 1, 1, r(t16), None) == UNS            # patch matrix must have 32 channels
+    assert h.nasb_bn_finalize_affine_act(None, 16, r(t16), None, None, 1e-5, 0.1, None, None, None, None, None, None, None, 0,
+                                         None, r(t16), None) == BAD
+    assert h.nasb_dwconv_tile(r(t32), C.c_void_p(0x1000), 3, 1, 1, 1, 0, None, None, 0, r(t32), None, None) == UNS  # bf16 only
+    assert h.nasb_dwconv_tile(None, None, 3, 1, 1, 1, 0, None, None, 0, None, None, None) == BAD
+    assert h.nasb_dwconv_wgrad_tile(r(t16), r(t16), 7, 1, 1, 3, C.c_void_p(0x1000), None) == UNS                    # k in {3,5}
+    assert h.nasb_pw_tc_fwd(r(t32), C.c_void_p(0x1000), 8, None, None, 0, None, r(t32), None, None) == BAD          # bf16 only
+    assert h.nasb_pw_tc_wgrad(None, None, None, None) == BAD
+    assert h.nasb_conv3_tc_fwd(r(t32), C.c_void_p(0x1000), 8, 1, 1, None, None, 0, r(t32), None, None) == UNS
+    assert h.nasb_bn_act_bwd(None, None, None, 0, None, None, None, None, None, None, 1, None, None, None, None, None) == BAD
+    assert h.nasb_confmat_labels(None, None, 16, 300, None, None) == BAD                                            # C <= 256
+    assert h.nasb_affine_act(r(t16), None, None, 0, r(t32), None) == BAD                                            # dtype mismatch
