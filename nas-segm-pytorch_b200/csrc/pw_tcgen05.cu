@@ -15,6 +15,8 @@
 // The path is HBM-bound (C_in, C_out <= 256): the kernel is deliberately simple -- every CTA loops over its 128-pixel
 // tiles (load -> mma -> epilogue, serial per CTA) and latency is hidden by 2-5 co-resident CTAs per SM, each with its
 // own TMEM columns.  The same kernel computes the data gradient (A = dz, B = W^T packed by nasb_pack_weight_bf16).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace nasb {
@@ -224,6 +226,229 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 }
 
 
+// ------------------------------------------------------------------------------------------------ warp-specialised variant
+// OPT-IN (NASB_PW_WS=1): written after round 1's GPU budget was spent -- it compiles, its barrier protocol is argued below,
+// it has NOT yet run on a B200.  Same math, same epilogue, same statistics as pw_tc_kernel; what changes is the schedule:
+// pw_tc_kernel runs load -> MMA -> epilogue -> store serially per CTA and relies on 4-6 co-resident CTAs per SM for overlap
+// (small layers: 2-3 tiles per CTA, 11-17 us for 4-33 MB).  Here one CTA pipelines its own tiles:
+//   warp 4 (one lane)  producer : TMA of the weight block once, then the A tiles through a ring of WS_SA stages
+//   warp 5 (one lane)  MMA      : tcgen05.mma into one of TWO TMEM accumulators; tcgen05.commit releases the A stage and
+//                                 hands the accumulator to the epilogue
+//   warps 0-3          epilogue : tcgen05.ld (warp w owns TMEM lanes 32w..32w+31), math, bf16 tile into one of two shared
+//                                 tiles, TMA store, statistics read-back -- while the MMA warp already fills the other
+//                                 accumulator and the producer loads two tiles ahead.
+// Barriers (k = use count of the slot): a_full[s] (tx bytes, producer -> MMA), a_empty[s] (commit, MMA -> producer),
+// acc_full[a] (commit, MMA -> epilogue), acc_empty[a] (128 arrivals, epilogue -> MMA).  Every k-th completion of a barrier
+// requires the waiter of completion k-1 to have passed (producer item i+SA waits a_empty of item i, whose commit follows the
+// MMA's wait on a_full of item i; MMA item i+2 waits acc_empty of item i, which the epilogue arrives on after its wait on
+// acc_full of item i), so a parity wait can never be overtaken by two phases.
+constexpr int WS_THREADS = 192;
+constexpr int WS_SA = 2;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+__global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b,
+                                                              const __grid_constant__ CUtensorMap map_o, const PwParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;                                               // nkb x [64 x 128 B]
+    uint8_t *sA = sB + (size_t)p.nkb * TILE_N * 128;                  // WS_SA x nkb x [128 x 128 B]
+    uint8_t *sO = sA + (size_t)WS_SA * p.nkb * TILE_M * 128;          // 2 x [128 x 128 B]
+    float *s_scale = (float *)(sO + (size_t)2 * TILE_M * 128);
+    float *s_shift = s_scale + TILE_N;
+    float *s_sum = s_shift + TILE_N;
+    float *s_sq = s_sum + TILE_N;
+    uint64_t *b_full = (uint64_t *)(s_sq + TILE_N);
+    uint64_t *a_full = b_full + 1;          // [WS_SA]
+    uint64_t *a_empty = a_full + WS_SA;     // [WS_SA]
+    uint64_t *acc_full = a_empty + WS_SA;   // [2]
+    uint64_t *acc_empty = acc_full + 2;     // [2]
+    uint32_t *s_tmem = (uint32_t *)(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (p.M + TILE_M - 1) / TILE_M;
+    const int nb = (int)blockIdx.x % p.nnb, n0 = nb * TILE_N;
+    const int nblk = p.N - n0 < TILE_N ? p.N - n0 : TILE_N;
+    const int npb = (nblk + 15) / 16 * 16;
+    const int tile0 = (int)blockIdx.x / p.nnb, tstride = (int)gridDim.x / p.nnb;
+    const int my_n = tile0 < ntiles ? (ntiles - 1 - tile0) / tstride + 1 : 0;
+
+    if (tid == 0) {
+        mbar_init(b_full, 1);
+        for (int i = 0; i < WS_SA; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < TILE_N; i += WS_THREADS) {
+        s_scale[i] = (p.scale && i < nblk) ? p.scale[n0 + i] : 1.f;
+        s_shift[i] = (p.shift && i < nblk) ? p.shift[n0 + i] : 0.f;
+        s_sum[i] = 0.f;
+        s_sq[i] = 0.f;
+    }
+    if (warp == 5) tmem_alloc(s_tmem, 128);  // two 64-column accumulators
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 4) {
+        if (lane == 0 && my_n > 0) {  // ---- producer
+            mbar_expect_tx(b_full, (uint32_t)(p.nkb * TILE_N * 128));
+            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * TILE_N * 128, &map_b, b_full, kb * 64, n0);
+            for (int i = 0; i < my_n; ++i) {
+                const int s = i % WS_SA, tile = tile0 + i * tstride;
+                if (i >= WS_SA) mbar_wait(&a_empty[s], (uint32_t)((i / WS_SA) - 1) & 1);
+                mbar_expect_tx(&a_full[s], (uint32_t)(p.nkb * TILE_M * 128));
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    tma_load_2d(sA + ((size_t)s * p.nkb + kb) * TILE_M * 128, &map_a, &a_full[s], kb * 64, tile * TILE_M);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0 && my_n > 0) {  // ---- MMA issuer
+            const uint32_t idesc = make_idesc_bf16(npb);
+            const int ksteps = (p.K + 15) / 16;
+            mbar_wait(b_full, 0);
+            for (int i = 0; i < my_n; ++i) {
+                const int s = i % WS_SA, a = i & 1;
+                if (i >= 2) mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) - 1) & 1);
+                mbar_wait(&a_full[s], (uint32_t)(i / WS_SA) & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int kb = ks >> 2, kin = ks & 3;
+                    uint64_t ad = make_desc_sw128(smem_u32(sA + ((size_t)s * p.nkb + kb) * TILE_M * 128) + kin * 32);
+                    uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * TILE_N * 128) + kin * 32);
+                    umma_f16(tmem_base + (uint32_t)a * 64, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(&a_empty[s]);   // the A stage may be refilled once these MMAs have read it
+                umma_commit(&acc_full[a]);  // ... and the accumulator is complete
+            }
+        }
+    } else {
+        // ---- epilogue warps 0..3 (128 threads): thread = TMEM lane = pixel row of the tile
+        const int row = warp * 32 + lane;
+        const bool affine = p.scale || p.shift || p.act != NASB_ACT_NONE;
+        const int st_ch = tid & 7, st_rg = tid >> 3;
+        const bool st_on = st_ch * 8 < nblk;
+        float2 st1[4], st2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st1[j] = st2[j] = make_float2(0.f, 0.f);
+        for (int i = 0; i < my_n; ++i) {
+            const int a = i & 1, tile = tile0 + i * tstride, m0 = tile * TILE_M;
+            uint8_t *sOt = sO + (size_t)a * TILE_M * 128;
+            mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1);
+            tc_fence_after();
+            if (tid == 0 && i >= 2) tma_store_wait_read1();  // the bulk store of tile i-2 has finished reading this shared tile
+            epi_barrier();
+            const long long m = (long long)m0 + row;
+            const bool row_ok = m < p.M;
+            uint8_t *orow = sOt + (size_t)row * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < npb; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 64 + c0), v);
+                if (affine) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+                }
+                if (p.res && row_ok) {
+                    const bf16 *rp = p.res + m * p.res_cs + n0 + c0;
+                    if (c0 + 16 <= nblk) {
+                        float r[8];
+                        load_vec<bf16, 8>(rp, r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += r[j];
+                        load_vec<bf16, 8>(rp + 8, r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[8 + j] += r[j];
+                    } else {
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < nblk) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (p.stats && !row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+                const int ch = c0 >> 3;
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(v[0], v[1]);
+                q0.y = pack_bf16x2(v[2], v[3]);
+                q0.z = pack_bf16x2(v[4], v[5]);
+                q0.w = pack_bf16x2(v[6], v[7]);
+                q1.x = pack_bf16x2(v[8], v[9]);
+                q1.y = pack_bf16x2(v[10], v[11]);
+                q1.z = pack_bf16x2(v[12], v[13]);
+                q1.w = pack_bf16x2(v[14], v[15]);
+                *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
+                *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[a]);  // this thread is done with accumulator a
+            fence_proxy_async();
+            epi_barrier();               // tile complete in shared memory
+            if (tid == 0) {
+                tma_store_2d(&map_o, sOt, n0, m0);
+                tma_store_commit();
+            }
+            if (p.stats && st_on) {
+#pragma unroll
+                for (int k = 0; k < TILE_M / 16; ++k) {
+                    const int r = st_rg + 16 * k;
+                    float2 q[4];
+                    cvt8(*reinterpret_cast<const uint4 *>(sOt + (size_t)r * 128 + ((st_ch ^ (r & 7)) << 4)), q);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        st1[j].x += q[j].x;
+                        st1[j].y += q[j].y;
+                        st2[j] = ffma2(q[j], q[j], st2[j]);
+                    }
+                }
+            }
+        }
+        if (tid == 0) tma_store_wait_all();
+        if (p.stats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int off = 8; off <= 16; off <<= 1) {
+                    st1[j].x += __shfl_xor_sync(0xffffffffu, st1[j].x, off);
+                    st1[j].y += __shfl_xor_sync(0xffffffffu, st1[j].y, off);
+                    st2[j].x += __shfl_xor_sync(0xffffffffu, st2[j].x, off);
+                    st2[j].y += __shfl_xor_sync(0xffffffffu, st2[j].y, off);
+                }
+            }
+            if (lane < 8 && st_on) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&s_sum[st_ch * 8 + 2 * j], st1[j].x);
+                    atomicAdd(&s_sum[st_ch * 8 + 2 * j + 1], st1[j].y);
+                    atomicAdd(&s_sq[st_ch * 8 + 2 * j], st2[j].x);
+                    atomicAdd(&s_sq[st_ch * 8 + 2 * j + 1], st2[j].y);
+                }
+            }
+            epi_barrier();
+            for (int c = tid; c < nblk; c += 128) {
+                atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
+                atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 128);
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[co][ci] += sum_m dz[m][co] * x[m][ci].  Both operands are "MN-major" for this GEMM (the reduction index is the
 // pixel, the contiguous index is the channel), so the very same TMA boxes (64 channels x 128 pixels, 128-byte swizzle)
@@ -399,6 +624,30 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     if (!tc_make_map2(&ma, x->ptr, (uint64_t)p.K, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)N, (uint64_t)Kp, TILE_N)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mo, out->ptr, (uint64_t)N, (uint64_t)M, (uint64_t)out->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    static int ws_mode = -1;
+    if (ws_mode < 0) ws_mode = getenv("NASB_PW_WS") ? atoi(getenv("NASB_PW_WS")) : 0;
+    int ntiles = (int)((M + TILE_M - 1) / TILE_M);
+    if (ws_mode) {  // opt-in warp-specialised schedule (see pw_tc_ws_kernel)
+        const size_t smem_ws = (size_t)p.nkb * TILE_N * 128 + (size_t)WS_SA * p.nkb * TILE_M * 128 + (size_t)2 * TILE_M * 128 +
+                               4 * TILE_N * 4 + 128 + 1024;
+        if (smem_ws <= 200 * 1024) {
+            static bool configured_ws = false;
+            if (!configured_ws) {
+                cudaError_t e = cudaFuncSetAttribute(pw_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
+                if (e != cudaSuccess) return (int)e;
+                configured_ws = true;
+            }
+            int per_sm = (int)((220 * 1024) / smem_ws);
+            if (per_sm > 4) per_sm = 4;  // 128 TMEM columns per CTA
+            if (per_sm < 1) per_sm = 1;
+            long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;
+            if (grid < p.nnb) grid = p.nnb;
+            if (grid > (long long)ntiles * p.nnb) grid = (long long)ntiles * p.nnb;
+            pw_tc_ws_kernel<<<(int)grid, WS_THREADS, smem_ws, (cudaStream_t)stream>>>(ma, mb, mo, p);
+            NASB_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     size_t smem = pw_smem_bytes(p.nkb);
     static bool configured = false;
     if (!configured) {
@@ -406,7 +655,6 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    int ntiles = (int)((M + TILE_M - 1) / TILE_M);
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
