@@ -1,4 +1,4 @@
-"""Per-entry-point microbenchmark (GPU box): times individual C-ABI calls at the shapes that dominate the arch0 training
+"""Per-entry-point microbenchmark (GPU box; compare variants with the NASB_* switches listed in DESIGN.md section 4): times individual C-ABI calls at the shapes that dominate the arch0 training
 iteration (batch 8 @2048x1024, bf16) with CUDA events, rotating over enough buffer sets that the inputs never sit in L2.
 
     python tools/kbench.py [filter-substring ...]        # e.g.  python tools/kbench.py bn_act_bwd dwconv
@@ -117,6 +117,39 @@ def _():
             sets.append(lambda z=z, g=g, b=b, rm=rm, rv=rv, sm=sm, sr=sr, sc=sc, sh=sh, ws=ws: call(
                 "nasb_bn_stats", ref(desc(z)), ptr(g), ptr(b), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(sm), ptr(sr), ptr(sc), ptr(sh), None, ptr(ws)))
         report("bn_stats[%dx%dx%dx%d]" % (n, h, w, c), timeit(sets), nb)
+
+
+@case("bn_finalize_affine_act")
+def _():
+    for n, c, h, w, a in BN_SHAPES[:7]:
+        nb = 2 * n * c * h * w * 2
+        sets = []
+        for _ in range(nsets(nb)):
+            z, y = act(n, c, h, w), act(n, c, h, w, fill=None)
+            P = n * h * w
+            sums = torch.cat([torch.randn(c, dtype=torch.float64, device=DEV) * P * 0.1,
+                              (torch.rand(c, dtype=torch.float64, device=DEV) + 1.0) * P])
+            g, b = fvec(c), fvec(c, -0.5, 0.5)
+            rm, rv, sm, sr, sc, sh = (torch.zeros(c, device=DEV) for _ in range(6))
+            nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+            sets.append(lambda z=z, y=y, sums=sums, g=g, b=b, rm=rm, rv=rv, sm=sm, sr=sr, sc=sc, sh=sh, nbt=nbt, P=P: call(
+                "nasb_bn_finalize_affine_act", ptr(sums), P, ref(desc(z)), ptr(g), ptr(b), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(sm), ptr(sr),
+                ptr(sc), ptr(sh), ptr(nbt), a, None, ref(desc(y))))
+        report("bn_finalize_affine_act[%dx%dx%dx%d act%d]" % (n, h, w, c, a), timeit(sets), nb)
+
+
+@case("pool3x3")
+def _():
+    for n, c, h, w, stride in [(8, 32, 128, 256, 1), (8, 48, 256, 512, 2), (8, 24, 256, 512, 1), (8, 64, 32, 64, 1)]:
+        oh, ow = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        x, o = act(n, c, h, w), act(n, c, oh, ow, fill=None)
+        arg = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=DEV)
+        dy, dx = act(n, c, oh, ow), act(n, c, h, w, fill=None)
+        nb = n * c * (h * w + oh * ow) * 2
+        report("pool3x3_fwd[%dx%dx%dx%d s%d]" % (n, h, w, c, stride),
+               timeit([lambda: call("nasb_pool3x3_fwd", ref(desc(x)), 0, stride, ref(desc(o)), ptr(arg))]), nb)
+        report("pool3x3_bwd[%dx%dx%dx%d s%d]" % (n, h, w, c, stride),
+               timeit([lambda: call("nasb_pool3x3_bwd", ref(desc(dy)), 0, stride, ptr(arg), ref(desc(dx)))]), nb)
 
 
 # (n, c, h, w, ks, stride, dil, pad)
