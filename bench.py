@@ -55,6 +55,7 @@ def args_():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the training iteration as one CUDA graph (default on)")
     ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of one instrumented step")
+    ap.add_argument("--depth-head-only", action="store_true", help="(internal) print the BASELINE config-5 timings as JSON and exit")
     return ap.parse_args()
 
 
@@ -285,10 +286,64 @@ def fwd_latency(dev, genotype, h, w, dtype, iters=20, graph=False):
     return e0.elapsed_time(e1) / iters
 
 
+def depth_head_step(dev, batch=8, h=480, w=640, iters=10):
+    """BASELINE config 5: the CVPR arch0 genotype in its final settings as a depth head (MobileNet-v2 4-tap encoder +
+    MicroDecoder agg 64, repeats 2, ONE output channel), 640x480, reverse-Huber loss, forward + backward, bf16 activations,
+    synthetic depth targets in (0.5, 8) m with 5 % invalid (0) pixels.  Eager and as one CUDA graph."""
+    import nas_segm_b200
+    from nas_segm_b200 import functional as Fn
+    from nas_segm_b200.graphs import StepGraph
+    from nas_segm_b200.nn.encoders import mbv2
+    from nas_segm_b200.nn.micro_decoders import MicroDecoder
+    c0 = [[8, [0, 0, 5, 2], [0, 2, 8, 8], [0, 5, 1, 4]], [[3, 3], [3, 2], [3, 0]]]
+    nas_segm_b200.set_act_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    enc = mbv2()
+    dec = MicroDecoder(list(enc.out_sizes), 1, c0, agg_size=64, aux_cell=False, repeats=2)
+    net = Seg(enc, dec).to(dev).train()
+    params = [q for q in net.parameters() if q.requires_grad]
+    g = torch.Generator().manual_seed(9314)
+    x = torch.randn(batch, 3, h, w, generator=g).to(dev)
+
+    def step(im, tg):
+        out = net(im)
+        out = out[0] if isinstance(out, tuple) else out
+        loss = Fn.berhu_loss(out, tg)
+        for q in params:
+            q.grad = None
+        loss.backward()
+        return loss
+
+    with torch.no_grad():
+        o = net(x)
+        o = o[0] if isinstance(o, tuple) else o
+    tg = torch.empty(o.shape, dtype=torch.float32).uniform_(0.5, 8.0, generator=g)
+    tg[torch.rand(o.shape, generator=g) < 0.05] = 0.0
+    tg = tg.to(dev)
+    res = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, run in (("eager", step), ("cudagraph", StepGraph(step, [x.clone(), tg.clone()]))):
+        for _ in range(5):
+            loss = run(x, tg)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            loss = run(x, tg)
+        e1.record()
+        torch.cuda.synchronize()
+        res["d0_depth_berhu_fwdbwd_ms_b%d_%dx%d_bf16_%s" % (batch, w, h, name)] = e0.elapsed_time(e1) / iters
+    res["d0_depth_berhu_loss"] = float(loss.detach())
+    return res
+
+
 def main():
     a = args_()
     if a.impl == "reference":
         return run_reference(a)
+    if a.depth_head_only:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        print(json.dumps(depth_head_step(torch.device("cuda", torch.cuda.current_device()))))
+        return
     import nas_segm_b200
     from nas_segm_b200 import lib
     from nas_segm_b200.engine import trainer
@@ -437,6 +492,16 @@ def main():
                     for dn, dt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
                         extras["%s_fwd_ms_b1_%dx%d_%s" % (name, ww, hh, dn)] = fwd_latency(dev, g, hh, ww, dt)
                         extras["%s_fwd_ms_b1_%dx%d_%s_cudagraph" % (name, ww, hh, dn)] = fwd_latency(dev, g, hh, ww, dt, graph=True)
+            try:  # BASELINE config 5 (depth head) in a child process with a deadline: it can never cost the headline line
+                child = subprocess.run([sys.executable, os.path.abspath(__file__), "--depth-head-only"], capture_output=True,
+                                       text=True, timeout=240, env=dict(os.environ, LOCAL_RANK=str(local)))
+                line = [ln for ln in child.stdout.splitlines() if ln.startswith("{")]
+                if child.returncode == 0 and line:
+                    extras.update(json.loads(line[-1]))
+                else:
+                    extras["d0_depth_error"] = ("rc=%d " % child.returncode) + child.stderr[-300:]
+            except Exception as e:  # noqa: BLE001
+                extras["d0_depth_error"] = repr(e)[:300]
         finally:
             nas_segm_b200.set_act_dtype(dtype)
 
