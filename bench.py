@@ -502,6 +502,21 @@ def main():
                     extras["d0_depth_error"] = ("rc=%d " % child.returncode) + child.stderr[-300:]
             except Exception as e:  # noqa: BLE001
                 extras["d0_depth_error"] = repr(e)[:300]
+            try:  # BASELINE config 4 (NAS inner loop, candidates/hour on this GPU), same arrangement
+                child = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "search_bench.py"), "--candidates", "2"],
+                                       capture_output=True, text=True, timeout=300,
+                                       env={k: v for k, v in dict(os.environ, LOCAL_RANK=str(local)).items()
+                                            if k not in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")})
+                line = [ln for ln in child.stdout.splitlines() if ln.startswith("{")]
+                if child.returncode == 0 and line:
+                    sb = json.loads(line[-1])
+                    extras["search_loop_task0_candidates_per_hour_n1"] = sb.get("value")
+                    extras["search_loop_ms_per_task0_iteration"] = sb.get("ms_per_task0_iteration")
+                    extras["search_loop_per_candidate_s"] = sb.get("per_candidate_s")
+                else:
+                    extras["search_loop_error"] = ("rc=%d " % child.returncode) + child.stderr[-300:]
+            except Exception as e:  # noqa: BLE001
+                extras["search_loop_error"] = repr(e)[:300]
         finally:
             nas_segm_b200.set_act_dtype(dtype)
 
