@@ -46,7 +46,11 @@ def args_():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_b200"],
+                    help="b200: this repo's CUDA path; reference: the reference algorithm on the host cores; torch_b200: the "
+                         "same network through stock PyTorch (cuDNN / ATen) on this GPU, the re-baselined comparator")
+    ap.add_argument("--workload", default="train", choices=["train", "search"],
+                    help="train: BASELINE config 2 (arch0 training iteration); search: BASELINE config 4 (NAS candidates/hour)")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=2048)
@@ -56,6 +60,12 @@ def args_():
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the training iteration as one CUDA graph (default on)")
     ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of one instrumented step")
     ap.add_argument("--depth-head-only", action="store_true", help="(internal) print the BASELINE config-5 timings as JSON and exit")
+    ap.add_argument("--metric-only", action="store_true", help="(internal) print the confusion-matrix timings as JSON and exit")
+    ap.add_argument("--n-task0", type=int, default=4000, help="search workload: cached task0 crops per candidate")
+    ap.add_argument("--task1-iters", type=int, default=297, help="search workload: train_segmenter iterations of task 1 "
+                    "(297 = one epoch of batch 32 over the reference's 90 %% meta-train split of VOC train+)")
+    ap.add_argument("--val-images", type=int, default=1024, help="search workload: validation images per validate() call "
+                    "(the reference's 10 %% meta-val split is 1058)")
     return ap.parse_args()
 
 
@@ -242,17 +252,394 @@ def run_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, sample_batch=1),
+        "note": "CPU arm: ONE host process whatever --gpus is (rank 0 only); images/s normalises the 1-image sample",
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(a):
+def workload_config(a, sample_batch=None):
+    """`sample_batch`: the batch a bounded CPU sample actually ran (the reference arm times 1 image per step of the batch-8
+    workload; images/s is what makes the two arms comparable)."""
+    b = a.batch if sample_batch is None else sample_batch
     return {"workload": "WACV arch0 (mbv2 2-tap encoder + TemplateDecoder agg64 rep2, %d classes) training iteration "
-                        "fwd+CE+bwd+clip+SGD/Adam, BN train mode, batch %d @%dx%d" % (NUM_CLASSES, a.batch, a.width, a.height),
-            "global_batch_per_gpu": a.batch, "resolution": [a.width, a.height], "l2": "inputs_exceed_L2",
+                        "fwd+CE+bwd+clip+SGD/Adam, BN train mode, batch %d @%dx%d%s"
+                        % (NUM_CLASSES, b, a.width, a.height,
+                           "" if sample_batch is None else " (bounded sample of the batch-%d workload)" % a.batch),
+            "global_batch_per_gpu": b, "resolution": [a.width, a.height], "l2": "inputs_exceed_L2",
             "parallelism": "one candidate per GPU (replicas), 1 all-gather of 16 B per step",
             "cuda_graph": bool(getattr(a, "cuda_graph", 0))}
+
+
+
+# ------------------------------------------------------------------------------------------------------------ stock PyTorch on the B200
+def torch_b200_numbers(dev, a, budget_s=150.0):
+    """The same network and iteration through stock PyTorch (cuDNN / ATen kernels) on THIS GPU: the reference's own module
+    graph as restated by oracle/nas_oracle.py (the reference itself cannot travel to the GPU box), fp32 and bf16 autocast +
+    channels_last, eager and as a CUDA graph.  This is the "52.25 ms on a 1080Ti, re-baselined on 1xB200" comparator of the
+    north star (reference README.md:80-81).  Comparator only: nothing of the product path runs here."""
+    from oracle import nas_oracle as O
+    t_start = time.time()
+    res = {}
+
+    def params(seed_e=1, seed_d=2):
+        Pe, Pd = O.Params(seed=seed_e), O.Params(seed=seed_d)
+        with torch.no_grad():
+            O.template_decoder(O.mbv2_encoder(torch.zeros(2, 3, 32, 32), Pe, (1, 2)), Pd, W0, [24, 32], NUM_CLASSES, 64, 2)
+        for P in (Pe, Pd):
+            for k in list(P.sd):
+                v = P.sd[k].to(dev)
+                P.sd[k] = v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v
+        return Pe, Pd
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    # ---- eval forward, batch 1 (README table shapes)
+    for genotype, gname in ((W0, "arch0"), (W1, "arch1")):
+        Pe, Pd = O.Params(seed=1), O.Params(seed=2)
+        with torch.no_grad():
+            O.template_decoder(O.mbv2_encoder(torch.zeros(2, 3, 32, 32), Pe, (1, 2)), Pd, genotype, [24, 32], NUM_CLASSES, 64, 2)
+        for P in (Pe, Pd):
+            for k in list(P.sd):
+                v = P.sd[k].to(dev)
+                P.sd[k] = v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v
+        for (hh, ww) in ((1024, 2048), (360, 480)):
+            x = torch.randn(1, 3, hh, ww, device=dev).contiguous(memory_format=torch.channels_last)
+            for dn in ("f32", "bf16"):
+                if time.time() - t_start > budget_s:
+                    break
+
+                def fwd():
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dn == "bf16"):
+                        return O.template_decoder(O.mbv2_encoder(x, Pe, (1, 2)), Pd, genotype, [24, 32], NUM_CLASSES, 64, 2)
+                key = "%s_fwd_ms_b1_%dx%d_%s" % (gname, ww, hh, dn)
+                try:
+                    res[key] = timed(fwd, 10)
+                    s = torch.cuda.Stream()
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
+                        fwd()
+                    torch.cuda.current_stream().wait_stream(s)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fwd()
+                    res[key + "_cudagraph"] = timed(g.replay, 10)
+                    del g
+                except Exception as e:  # noqa: BLE001
+                    res[key + "_error"] = repr(e)[:200]
+        del Pe, Pd
+        torch.cuda.empty_cache()
+
+    # ---- training iteration, batch 8 @2048x1024 (the headline workload)
+    img, lab = synth(a.batch, a.height, a.width)
+    for dn in ("bf16", "f32"):
+        if time.time() - t_start > budget_s:
+            res["train_%s_skipped" % dn] = "time budget"
+            continue
+        try:
+            Pe, Pd = params()
+            for P in (Pe, Pd):
+                P.requires_grad_()
+            p_enc = [v for v in Pe.sd.values() if v.requires_grad]
+            p_dec = [v for v in Pd.sd.values() if v.requires_grad]
+            optim_enc = torch.optim.SGD(p_enc, lr=1e-3, momentum=0.9, weight_decay=1e-5)
+            optim_dec = torch.optim.Adam(p_dec, lr=3e-3, weight_decay=1e-5, capturable=True)
+            x = img.to(dev).contiguous(memory_format=torch.channels_last)
+            lab_d = lab.to(dev)
+
+            def step():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dn == "bf16"):
+                    out = O.template_decoder(O.mbv2_encoder(x, Pe, (1, 2), True), Pd, W0, [24, 32], NUM_CLASSES, 64, 2,
+                                             training=True)
+                y = O.nearest_labels(lab_d, out.shape[2:])
+                loss = O.segm_loss(out.float(), y)
+                optim_enc.zero_grad()
+                optim_dec.zero_grad()
+                loss.backward()
+                nn.utils.clip_grad_norm_(p_enc, 3.0)
+                nn.utils.clip_grad_norm_(p_dec, 3.0)
+                optim_enc.step()
+                optim_dec.step()
+                return loss
+            ms = timed(step, max(3, min(a.steps, 8)))
+            res["train_ms_per_step_b%d_%s_eager" % (a.batch, dn)] = ms
+            res["train_images_per_sec_%s_eager" % dn] = a.batch / ms * 1e3
+            res["train_peak_mem_gb_%s" % dn] = torch.cuda.max_memory_allocated() / 1e9
+            if dn == "bf16" and time.time() - t_start < budget_s:
+                try:
+                    s = torch.cuda.Stream()
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
+                        step()
+                    torch.cuda.current_stream().wait_stream(s)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        step()
+                    ms = timed(g.replay, max(3, min(a.steps, 8)))
+                    res["train_ms_per_step_b%d_bf16_cudagraph" % a.batch] = ms
+                    res["train_images_per_sec_bf16_cudagraph"] = a.batch / ms * 1e3
+                    del g
+                except Exception as e:  # noqa: BLE001
+                    res["train_bf16_cudagraph_error"] = repr(e)[:200]
+            del Pe, Pd, p_enc, p_dec, optim_enc, optim_dec, x
+        except Exception as e:  # noqa: BLE001
+            res["train_%s_error" % dn] = repr(e)[:300]
+        torch.cuda.empty_cache()
+    res["what"] = ("stock PyTorch %s (cuDNN/ATen; channels_last; bf16 = torch.autocast) running the reference's module graph "
+                   "(oracle/nas_oracle.py restatement) on this GPU" % torch.__version__)
+    return res
+
+
+def run_torch_b200(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    res = torch_b200_numbers(dev, a, budget_s=400.0)
+    best = max((v for k, v in res.items() if k.startswith("train_images_per_sec")), default=None)
+    ms = min((v for k, v in res.items() if k.startswith("train_ms_per_step")), default=None)
+    print(json.dumps({"impl": "torch_b200", "metric": METRIC, "value": best, "unit": "images/s", "n_gpus": 1, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "bf16", "data": "synthetic", "config": workload_config(a), "details": res}))
+
+
+# ------------------------------------------------------------------------------------------------------------ metric (fast_cm)
+def metric_numbers(dev):
+    """the confusion-matrix kernels against the HBM roofline (label path = 2 bytes per pixel; fused
+    upsample+argmax path = the bf16/fp32 logits + 1 label byte per full-resolution pixel) next to the reference's own Cython
+    fast_cm (oracle/_ref, built from src/helpers/miou_utils.pyx:7-30; single-threaded by construction) and the C
+    restatement on the same arrays."""
+    import nas_segm_b200  # noqa: F401
+    from nas_segm_b200 import functional as Fn
+    peak, peak_src = peaks()
+    res = {"peak_gbs": peak, "peak_source": peak_src}
+    g = torch.Generator().manual_seed(9314)
+    B, H, W, C = 8, 1024, 2048, NUM_CLASSES
+    n = B * H * W
+    # several label sets, rotated, so that no launch finds its input in the 126 MB L2
+    sets = []
+    for _ in range(6):
+        gt = torch.randint(0, C, (n,), generator=g, dtype=torch.int64).to(torch.uint8)
+        gt[torch.rand(n, generator=g) < 0.05] = 255
+        pr = torch.randint(0, C, (n,), generator=g, dtype=torch.int64).to(torch.uint8)
+        sets.append((pr.to(dev), gt.to(dev)))
+    cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+
+    def timed(fns, iters=30):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fns[i % len(fns)]()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    ms = timed([lambda p=p, q=q: Fn.confmat_labels(p, q, C, cm) for p, q in sets])
+    res["confmat_labels_ms_%dMpx_C%d" % (n >> 20, C)] = ms
+    res["confmat_labels_gbs"] = 2.0 * n / (ms * 1e-3) / 1e9
+    res["confmat_labels_frac_of_hbm_peak"] = res["confmat_labels_gbs"] / peak
+    res["confmat_labels_gpx_per_s"] = n / (ms * 1e-3) / 1e9
+    for dt, dn in ((torch.float32, "f32"),):
+        lsets = []
+        for i in range(4):
+            lg = torch.randn(B, H // 4, W // 4, C, generator=g).to(dev).to(dt).permute(0, 3, 1, 2)
+            lsets.append((lg, sets[i][1].view(B, H, W)))
+        ms = timed([lambda lg=lg, q=q: Fn.confmat_logits(lg, q, C, cm) for lg, q in lsets], iters=20)
+        nbytes = B * (H // 4) * (W // 4) * C * (4 if dt == torch.float32 else 2) + n
+        res["confmat_logits_ms_b8_19x256x512_to_2048x1024_%s" % dn] = ms
+        res["confmat_logits_gbs_%s" % dn] = nbytes / (ms * 1e-3) / 1e9
+        res["confmat_logits_frac_of_hbm_peak_%s" % dn] = res["confmat_logits_gbs_%s" % dn] / peak
+        res["confmat_logits_gpx_per_s_%s" % dn] = n / (ms * 1e-3) / 1e9
+    # CPU: the reference's Cython and the C restatement on ONE 2048x1024 image (2.1 Mpx), 1 core each
+    pr_h, gt_h = sets[0][0][:H * W].cpu().numpy(), sets[0][1][:H * W].cpu().numpy()
+    valid = gt_h < C  # inference.py:65: the reference caller pre-masks
+    pr_v, gt_v = np.ascontiguousarray(pr_h[valid]), np.ascontiguousarray(gt_h[valid])
+    try:
+        from oracle import build_ref, miou_oracle
+        ref = build_ref.load()
+        if ref is not None:
+            ref.fast_cm(pr_v, gt_v, C)
+            t0 = time.time()
+            for _ in range(5):
+                cm_ref = ref.fast_cm(pr_v, gt_v, C)
+            dt_ref = (time.time() - t0) / 5
+            res["cython_fast_cm_ms_2Mpx_1core"] = dt_ref * 1e3
+            res["cython_fast_cm_gpx_per_s_1core"] = pr_v.size / dt_ref / 1e9
+            cm_gpu = Fn.confmat_labels(sets[0][0][:H * W].contiguous(), sets[0][1][:H * W].contiguous(), C).cpu().numpy()
+            res["bit_exact_vs_cython"] = bool(np.array_equal(cm_gpu, np.asarray(cm_ref)))
+        else:
+            res["cython_fast_cm"] = "oracle/_ref not built on this box"
+        miou_oracle.fast_cm_c(pr_v, gt_v, C)
+        t0 = time.time()
+        for _ in range(5):
+            miou_oracle.fast_cm_c(pr_v, gt_v, C)
+        dt_c = (time.time() - t0) / 5
+        res["c_port_fast_cm_gpx_per_s_1core"] = pr_v.size / dt_c / 1e9
+    except Exception as e:  # noqa: BLE001
+        res["cpu_metric_error"] = repr(e)[:200]
+    return res
+
+
+
+# ------------------------------------------------------------------------------------------------------------ search loop (config 4)
+def search_numbers(a, dev, rank, world, rounds, warm_rounds, n_task0, task1_iters, val_images, deadline_s=None):
+    """BASELINE config 4 through the product's own outer loop: engine.search.search_rounds + evaluate_candidate, i.e. the
+    per-candidate recipe of the reference's main_search.py:548-680 -- a FRESH segmenter per candidate (MobileNet-v2 4-tap
+    encoder + sampled MicroDecoder, agg 48, aux cells, 21 classes; model build and CUDA-graph capture are inside the timed
+    region), task 0 = 5 epochs of train_task0 on n_task0 cached 256x256 crops (batch 64, KD-MSE + aux CE, Adam, clip,
+    Polyak) + validate, TaskPerformer decision, task 1 = one epoch of train_segmenter (batch 32 @350x350, host batches)
+    + validate, reward.  One candidate per rank per round; records are exchanged with the single all-gather
+    (sync_every = rounds: a rank stopped early moves on instead of idling; the synchronous figure is derived from the
+    per-candidate times of the same run).  Candidates come from search.uniform_sampler (the controller is outside the hot
+    path).  populate_task0 runs once, outside the timed region, and is reported separately."""
+    import types
+    import nas_segm_b200
+    from nas_segm_b200 import parallel
+    from nas_segm_b200.engine import search, trainer
+    from nas_segm_b200.nn.encoders import mbv2
+    from nas_segm_b200.nn.micro_decoders import MicroDecoder
+    nas_segm_b200.set_act_dtype(torch.bfloat16)
+    nas_segm_b200.config().cuda_graphs = True
+    np.random.seed(9314 + rank)
+    g = torch.Generator().manual_seed(9314 + rank)
+
+    class Loader(list):
+        class _DS:
+            def set_stage(self, s):
+                pass
+        dataset = _DS()
+        batch_sampler = types.SimpleNamespace(batch_size=1)
+
+    t0 = time.time()
+    enc0 = mbv2()
+    seg0 = Wrapper(Seg(enc0, nn.Identity()).to(dev))
+    n_real = min(n_task0, 64)
+    train0 = Loader({"image": torch.randn(1, 3, 256, 256, generator=g),
+                     "mask": torch.randint(0, 21, (1, 256, 256), generator=g).to(torch.uint8)} for _ in range(n_real))
+    Xy = trainer.populate_task0(seg0, train0, None, n_real, do_kd=False)
+    assert Xy != 0, "populate_task0 swallowed a RuntimeError"
+    torch.cuda.synchronize()
+    t_populate_per_image = (time.time() - t0) / n_real
+    reps = (n_task0 + n_real - 1) // n_real  # the cached block is tiled to n_task0 samples: content is irrelevant to timing
+    for k in list(Xy.keys()):
+        if k == "out_size":
+            continue
+        if k == "y":
+            Xy[k] = Xy[k].repeat(reps, 1, 1)[:n_task0].contiguous()
+        else:
+            Xy[k] = Xy[k].permute(0, 2, 3, 1).repeat(reps, 1, 1, 1)[:n_task0].contiguous().permute(0, 3, 1, 2)
+    Xy["kd_y"] = torch.randn(n_task0, 64, 64, 21, device=dev,
+                             generator=torch.Generator(device=dev).manual_seed(1)).permute(0, 3, 1, 2)
+    del seg0, enc0
+    pinned1 = [{"image": torch.randn(32, 3, 350, 350, generator=g).pin_memory(),
+                "mask": torch.randint(0, 21, (32, 350, 350), generator=g).to(torch.uint8).pin_memory()} for _ in range(2)]
+    train1 = Loader(pinned1[i % 2] for i in range(task1_iters))
+    pinned_v = [{"image": torch.randn(64, 3, 400, 400, generator=g).pin_memory(),
+                 "mask": torch.randint(0, 21, (64, 400, 400), generator=g).to(torch.uint8).pin_memory()} for _ in range(2)]
+    val = Loader(pinned_v[i % 2] for i in range(max(val_images // 64, 1)))
+    args = types.SimpleNamespace(
+        num_tasks=2, enc_optim="sgd", dec_optim="adam", enc_lr=[1e-3, 1e-3], dec_lr=[3e-3, 3e-3], enc_mom=[0.9] * 3,
+        dec_mom=[0.9] * 3, enc_wd=[1e-5] * 3, dec_wd=[1e-5] * 3, do_polyak=True, num_segm_epochs=[5, 1], val_every=[5, 1],
+        segm_crit=nn.NLLLoss(ignore_index=255), kd_crit=nn.MSELoss(), batch_size=[64, 32], freeze_bn=[False, False],
+        do_kd=True, kd_coeff=0.3, dec_grad_clip=3.0, enc_grad_clip=3.0, dec_aux_weight=0.15, print_every=20,
+        num_classes=[21, 21], val_omit_classes=[0])  # utils/default_args.py of the reference
+    task_ps = search.make_task_performers(args.num_segm_epochs, args.val_every)
+    sampler = search.uniform_sampler(seed=9314)
+    per_candidate, errors = [], []
+
+    def build(cfg):
+        torch.manual_seed(0)
+        enc = mbv2()
+        dec = MicroDecoder(list(enc.out_sizes), 21, cfg, agg_size=48, aux_cell=True, repeats=1)
+        return Wrapper(Seg(enc, dec).to(dev))
+
+    def evaluate(seg, cfg):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        try:
+            out = search.evaluate_candidate(seg, Xy, train1, val, args, task_ps)
+        except Exception as e:  # noqa: BLE001 -- keep the ranks' collectives matched whatever one candidate does
+            errors.append(repr(e)[:200])
+            out = (0.0, 1)
+        ev1.record()
+        torch.cuda.synchronize()
+        per_candidate.append((ev0.elapsed_time(ev1) / 1e3, int(out[1]), float(out[0])))
+        return out
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    if warm_rounds:
+        search.search_rounds(warm_rounds, lambda r, s: sampler(10000 + r, s), build, evaluate, sync_every=warm_rounds)
+    n_warm = len(per_candidate)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.time()
+    e0.record()
+    hist = search.search_rounds(rounds, sampler, build, evaluate, sync_every=rounds)
+    e1.record()
+    barrier()
+    t_wall = time.time() - t_wall
+    t_mine = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
+    times = torch.tensor([[c[0], float(c[1])] for c in per_candidate[n_warm:]], dtype=torch.float32, device=dev)  # [rounds, 2]
+    if world > 1:
+        import torch.distributed as td
+        td.all_reduce(t_mine, op=td.ReduceOp.MAX)
+        allt = torch.empty((world,) + tuple(times.shape), dtype=torch.float32, device=dev)
+        td.all_gather_into_tensor(allt, times)
+    else:
+        allt = times[None]
+    allt = allt.cpu().numpy()  # [world, rounds, 2]
+    t_block = float(t_mine.item())                          # max over ranks, device timeline, one exchange at the end
+    t_sync = float(allt[:, :, 0].max(axis=0).sum())         # what per-round all-gathers would have cost
+    n = world * rounds
+    return {"metric": "search_loop_candidates_per_hour", "value": n * 3600.0 / t_block, "unit": "candidates/h",
+            "n_gpus": world, "rounds": rounds, "warmup_rounds": warm_rounds, "candidates": n,
+            "seconds_per_round": t_block / rounds, "wall_s": t_wall,
+            "candidates_per_hour_synchronous_rounds": n * 3600.0 / t_sync,
+            "straggler_loss_of_synchronous_rounds": 1.0 - t_block / t_sync if t_sync > 0 else None,
+            "per_candidate_s": [[round(float(v), 3) for v in allt[r, :, 0]] for r in range(world)],
+            "epochs_run": [[int(v) for v in allt[r, :, 1]] for r in range(world)],
+            "rewards": [[round(float(t[s, 0]), 5) for s in range(world)] for t in hist],
+            "populate_task0_s_per_image": t_populate_per_image, "n_task0": n_task0, "task1_iterations": task1_iters,
+            "val_images": len(val) * 64, "errors": errors[:3],
+            "recipe": "task0: 5 epochs x %d it (batch 64, 64x64 feats, KD+aux, Adam, clip, Polyak) + validate; TaskPerformer; "
+                      "task1: %d it of train_segmenter (batch 32 @350x350, host batches) + validate; fresh model + CUDA-graph "
+                      "capture per candidate inside the timed region; bf16" % (n_task0 // 64, task1_iters)}
+
+
+def run_search(a):
+    from nas_segm_b200 import parallel
+    rank, world, dev = parallel.init()
+    res = search_numbers(a, dev, rank, world, rounds=max(a.steps, 1), warm_rounds=min(max(a.warmup, 0), 1),
+                         n_task0=a.n_task0, task1_iters=a.task1_iters, val_images=a.val_images)
+    if rank == 0:
+        res.update({"steps": a.steps, "warmup": a.warmup, "ms_per_step": res["seconds_per_round"] * 1e3, "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": "CVPR search loop (BASELINE config 4): " + res.pop("recipe"),
+                               "parallelism": "one candidate per GPU per round, 1 all-gather of 16 B per candidate"}})
+        print(json.dumps(res))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------------ CUDA arm
@@ -340,6 +727,14 @@ def main():
     a = args_()
     if a.impl == "reference":
         return run_reference(a)
+    if a.impl == "torch_b200":
+        return run_torch_b200(a)
+    if a.metric_only:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        print(json.dumps(metric_numbers(torch.device("cuda", torch.cuda.current_device()))))
+        return
+    if a.workload == "search":
+        return run_search(a)
     if a.depth_head_only:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         print(json.dumps(depth_head_step(torch.device("cuda", torch.cuda.current_device()))))
@@ -502,21 +897,44 @@ def main():
                     extras["d0_depth_error"] = ("rc=%d " % child.returncode) + child.stderr[-300:]
             except Exception as e:  # noqa: BLE001
                 extras["d0_depth_error"] = repr(e)[:300]
-            try:  # BASELINE config 4 (NAS inner loop, candidates/hour on this GPU), same arrangement
-                child = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "search_bench.py"), "--candidates", "2"],
-                                       capture_output=True, text=True, timeout=300,
-                                       env={k: v for k, v in dict(os.environ, LOCAL_RANK=str(local)).items()
-                                            if k not in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")})
-                line = [ln for ln in child.stdout.splitlines() if ln.startswith("{")]
-                if child.returncode == 0 and line:
-                    sb = json.loads(line[-1])
-                    extras["search_loop_task0_candidates_per_hour_n1"] = sb.get("value")
-                    extras["search_loop_ms_per_task0_iteration"] = sb.get("ms_per_task0_iteration")
-                    extras["search_loop_per_candidate_s"] = sb.get("per_candidate_s")
-                else:
-                    extras["search_loop_error"] = ("rc=%d " % child.returncode) + child.stderr[-300:]
-            except Exception as e:  # noqa: BLE001
-                extras["search_loop_error"] = repr(e)[:300]
+            def child(argv, timeout):
+                """A measurement in a child process with a deadline: it can never cost the headline line."""
+                env = {k: v for k, v in dict(os.environ, LOCAL_RANK=str(local)).items()
+                       if k not in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+                try:
+                    c = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True,
+                                       timeout=timeout, env=env)
+                    line = [ln for ln in c.stdout.splitlines() if ln.startswith("{")]
+                    if c.returncode == 0 and line:
+                        return json.loads(line[-1])
+                    return {"error": ("rc=%d " % c.returncode) + c.stderr[-300:]}
+                except Exception as e:  # noqa: BLE001
+                    return {"error": repr(e)[:300]}
+            # the same network through stock PyTorch on this GPU (north star: "re-baselined on 1xB200")
+            tb = child(["--impl", "torch_b200", "--steps", str(min(a.steps, 8)), "--warmup", "3"], 420)
+            extras["torch_b200"] = tb.get("details", tb)
+            # SURVEY 8(d): confusion-matrix kernels vs HBM roofline, Cython fast_cm beside them
+            extras["metric"] = child(["--metric-only"], 180)
+            # BASELINE config 4 through engine.search (task0 + task1, TaskPerformer, per-candidate rebuild + capture)
+            sb = child(["--workload", "search", "--steps", "2", "--warmup", "1"], 420)
+            sb.pop("config", None)
+            extras["search_loop"] = sb
+        finally:
+            nas_segm_b200.set_act_dtype(dtype)
+
+    if dist and not a.no_extras:
+        # candidates/hour at this N through the same outer loop (one candidate per rank per round); every rank takes part.
+        # Errors inside a candidate are recorded, not raised, so the ranks' collectives stay matched.
+        del img_d, lab_d
+        seg = optim_enc = optim_dec = graphed = None
+        torch.cuda.empty_cache()
+        try:
+            sb = search_numbers(a, dev, rank, world, rounds=2, warm_rounds=1, n_task0=a.n_task0, task1_iters=a.task1_iters,
+                                val_images=a.val_images)
+            sb.pop("recipe", None)
+            extras["search_loop"] = sb
+        except Exception as e:  # noqa: BLE001
+            extras["search_loop"] = {"error": repr(e)[:300]}
         finally:
             nas_segm_b200.set_act_dtype(dtype)
 

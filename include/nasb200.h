@@ -121,8 +121,6 @@ int nasb_stem_im2col(const NasbTensor *img, int ks, int stride, int dil, int pad
  *                         with x = dz and the transposed pack.
  * -------------------------------------------------------------------------------------------------------*/
 int nasb_pack_weight_bf16(const float *w, int rows, int cols, int transpose, void *out, void *stream);
-/* both packs in one launch: out = [rows][Kp(cols)] (forward), out_t = [cols][Kp(rows)] (data gradient) */
-int nasb_pack_weight_bf16_both(const float *w, int rows, int cols, void *out, void *out_t, void *stream);
 int nasb_pw_tc_supported(int K, int N);
 int nasb_pw_tc_wgrad_supported(int Co, int Ci);
 /* dweight[co][ci] += sum_pixels dz[.,co]*x[.,ci] on the tensor cores (MN-major operands, TMEM accumulation). */
@@ -282,10 +280,57 @@ int nasb_confmat_logits(const NasbTensor *logits, const uint8_t *gt, int H, int 
 int nasb_ius_accs(const long long *cm, int n_classes, double *iu, long long *n_pixels, double *accs, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Optimiser-side fused passes over a flat fp32 buffer (trainer.py:163-169; "next" row f2 of the scope table).
- * nasb_sumsq : out[0] += sum x^2   (global grad-norm for clip_grad_norm_)
+ * Tail of a training iteration as multi-tensor kernels (scope row f2): torch.nn.utils.clip_grad_norm_ +
+ * optimiser.step() + the Polyak average of trainer.py:163-169,258-272 over the ~490 small parameter tensors of a
+ * candidate (optimisers built by src/utils/solvers.py:35-52: torch.optim.SGD / torch.optim.Adam).
+ * `tensors` / `groups` / `max_norm` are HOST arrays (the table travels by value in the kernel parameters, so a captured
+ * CUDA graph bakes it in); every pointer inside a NasbOptTensor is a DEVICE pointer to contiguous fp32.
+ *   NasbOptTensor : param; grad (NULL = no update, Polyak only); state1 = SGD momentum buffer / Adam exp_avg;
+ *                   state2 = Adam exp_avg_sq; avg = Polyak average (NULL = none); step = Adam's per-parameter step
+ *                   counter (fp32 scalar on the device, torch's state["step"]); group = index into groups (-1 = none);
+ *                   clip = index of the gradient-norm cell this tensor belongs to (-1 = not clipped).
+ *   NasbOptGroup  : kind NASB_OPT_SGD  : beta1 = momentum, beta2 = dampening, first = 1 on the step that creates the
+ *                                        momentum buffers (buf = grad), nesterov
+ *                   kind NASB_OPT_ADAM : beta1, beta2, eps (amsgrad / maximize / decoupled decay are not supported)
+ * nasb_mt_grad_sumsq : cells[c] = sum over the tensors of clip cell c of grad^2 (fp64; cells are zeroed first), and
+ *                      step += 1 for every tensor with a step counter.  Must precede nasb_mt_optim_step.
+ * nasb_mt_optim_step : grad *= min(1, max_norm[c] / (sqrt(cells[c]) + 1e-6)) (written back, like clip_grad_norm_);
+ *                      the optimiser update; avg = avg*polyak_decay + (1 - polyak_decay)*param.
+ * nasb_sumsq         : out[0] += sum x^2 over one flat buffer.
  * -------------------------------------------------------------------------------------------------------*/
+#define NASB_OPT_NONE 0
+#define NASB_OPT_SGD 1
+#define NASB_OPT_ADAM 2
+typedef struct NasbOptTensor {
+    float *param, *grad, *state1, *state2, *avg, *step;
+    long long numel;
+    int32_t group, clip;
+} NasbOptTensor;
+typedef struct NasbOptGroup {
+    int32_t kind, first, nesterov;
+    float lr, beta1, beta2, eps, weight_decay;
+} NasbOptGroup;
+int nasb_mt_grad_sumsq(const NasbOptTensor *tensors, int n, double *cells, int n_cells, void *stream);
+int nasb_mt_optim_step(const NasbOptTensor *tensors, int n, const NasbOptGroup *groups, int n_groups,
+                       const float *max_norm, int n_cells, const double *cells, float polyak_decay, void *stream);
 int nasb_sumsq(const float *x, long long n, float *out1, void *stream);
+
+/* Every tensor-core weight operand of a model re-packed from the fp32 master weights in ONE launch (the per-call
+ * nasb_pack_weight_bf16 / nasb_pack_conv3_bf16 launches were 135 per arch0 iteration).  jobs is a HOST array.
+ *   kind NASB_PACK_PW / _PW_T : nasb_pack_weight_bf16 with transpose 0 / 1 (src [c_out][c_in])
+ *   kind NASB_PACK_C3 / _C3_T : nasb_pack_conv3_bf16 with mode 0 / 1       (src [c_out][c_in][3][3])
+ * nasb_pack_elems gives the bf16 element count of one packed operand. */
+#define NASB_PACK_PW 0
+#define NASB_PACK_PW_T 1
+#define NASB_PACK_C3 2
+#define NASB_PACK_C3_T 3
+typedef struct NasbPackJob {
+    const float *src;
+    void *dst;
+    int32_t c_out, c_in, kind, reserved;
+} NasbPackJob;
+long long nasb_pack_elems(int kind, int c_out, int c_in);
+int nasb_mt_pack_bf16(const NasbPackJob *jobs, int n, void *stream);
 
 #ifdef __cplusplus
 }

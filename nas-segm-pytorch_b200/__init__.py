@@ -28,9 +28,9 @@ class _Config:
         # one shared-memory merge per CTA): +15-25 % on the kernel, cheaper than the separate pass that re-reads z
         self.fuse_dw_stats = True
         self.use_tma_tiles = True  # bf16 depthwise convolutions on TMA-staged shared-memory tiles when shapes allow
-        # forward and transposed bf16 weight packs of a pointwise conv in ONE launch (67 launches fewer per arch0 iteration).
-        # Off: written after the round's GPU budget was spent, not yet validated on a B200.
-        self.dual_pack = False
+        # clip + optimiser step + Polyak of an engine iteration as two multi-tensor launches (optim.FusedStep) when the
+        # caller's optimisers are plain torch.optim.SGD / Adam; off = the caller's own optim.step() (torch kernels)
+        self.fused_optim = True
 
 
 _config = None

@@ -438,7 +438,7 @@ struct BnFin {
     long long *nbt;
 };
 
-// COOP (opt-in, NASB_BN_COOP=1; written after the round's GPU budget was spent, not yet validated on a B200): the CTA
+// COOP (validated on a B200 in round 2; chosen by bn_coop() for tensors up to ~100 MB): the CTA
 // derives the constants cooperatively -- thread c handles channel c (coalesced loads, one L2 round trip, one fp64 chain)
 // and publishes them through shared memory -- instead of every thread walking its 8 channels one dependent load after the
 // other (SASS: 8 serial LDG.64 + fp64 division chains, ~3 us before the first streaming load of every CTA; measured as
@@ -724,10 +724,14 @@ static inline bool bn_safe() {
     if (v < 0) v = getenv("NASB_BN_SAFE") ? atoi(getenv("NASB_BN_SAFE")) : 0;
     return v;
 }
-static inline bool bn_coop() {
+// Cooperative finalise prologue (thread c -> channel c, constants through shared memory) or every thread deriving its own
+// eight channels: measured on a B200 (profiles/r2_switches_kbench.txt) the cooperative form wins 8-22 % up to ~100 MB
+// tensors and loses 6-10 % on the 270-800 MB ones (its __syncthreads delays the first streaming loads of every CTA).
+// NASB_BN_COOP=0 / 1 forces one form.
+static inline bool bn_coop(long long P, int C) {
     static int v = -1;
-    if (v < 0) v = getenv("NASB_BN_COOP") ? atoi(getenv("NASB_BN_COOP")) : 0;
-    return v != 0;
+    if (v < 0) v = getenv("NASB_BN_COOP") ? atoi(getenv("NASB_BN_COOP")) : 2;
+    return v == 1 || (v == 2 && P * C <= (56LL << 20));
 }
 static inline bool fixed_cfg(int C, int V, long long P, int &blocks) {
     if (bn_safe() & 1) return false;
@@ -889,7 +893,7 @@ extern "C" int nasb_bn_finalize_affine_act(const double *sums, long long P, cons
     if (!(bn_safe() & 8) && z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && (!res || vec_ok(*res, 8)) &&
         fixed_cfg(C, 8, P, blocks)) {
         BnFin f{sums, P, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift, num_batches_tracked};
-        if (bn_coop())
+        if (bn_coop(P, C))
             affine_act_bf16_kernel<true, true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act,
                                                                        (bf16 *)y->ptr, y->cstride, P, C, f,
                                                                        res ? (const bf16 *)res->ptr : nullptr, res ? res->cstride : 0);
@@ -943,7 +947,7 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
             bn_bwd_sums_bf16_kernel<<<blocks, 256, smem, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
                                                                scale, shift, save_mean, save_rstd, lo, hi, P, C, ws, rows);
             NASB_CHECK_LAUNCH();
-            if (bn_coop())
+            if (bn_coop(P, C))
                 bn_bwd_dz_bf16_kernel<true><<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
                                                                       ws, scale, shift, save_mean, save_rstd, dgamma, dbeta, lo, hi,
                                                                       (bf16 *)dz->ptr, dz->cstride, P, C);

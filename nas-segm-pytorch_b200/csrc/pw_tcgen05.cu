@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 
 
 // ------------------------------------------------------------------------------------------------ warp-specialised variant
-// OPT-IN (NASB_PW_WS=1): written after round 1's GPU budget was spent -- it compiles, its barrier protocol is argued below,
-// it has NOT yet run on a B200.  Same math, same epilogue, same statistics as pw_tc_kernel; what changes is the schedule:
+// Validated on a B200 in round 2 (full GPU suite + kbench with NASB_PW_WS=1; chosen by nasb_pw_tc_fwd for M <= 2^20 pixels).
+// Same math, same epilogue, same statistics as pw_tc_kernel; what changes is the schedule:
 // pw_tc_kernel runs load -> MMA -> epilogue -> store serially per CTA and relies on 4-6 co-resident CTAs per SM for overlap
 // (small layers: 2-3 tiles per CTA, 11-17 us for 4-33 MB).  Here one CTA pipelines its own tiles:
 //   warp 4 (one lane)  producer : TMA of the weight block once, then the A tiles through a ring of WS_SA stages
@@ -556,13 +556,6 @@ __device__ __forceinline__ void pack_one(const float *w, int rows, int cols, int
 __global__ void pack_weight_kernel(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp) {
     pack_one(w, rows, cols, transpose, out, R, Kp, blockIdx.x * blockDim.x + threadIdx.x);
 }
-// both operand layouts in one launch: the forward pack and the transposed pack the data gradient will want
-__global__ void pack_weight_both_kernel(const float *w, int rows, int cols, bf16 *out, int Kp, bf16 *out_t, int Kp_t) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    pack_one(w, rows, cols, 0, out, rows, Kp, i);
-    pack_one(w, rows, cols, 1, out_t, cols, Kp_t, i);
-}
-
 }  // namespace nasb
 
 using namespace nasb;
@@ -572,16 +565,6 @@ extern "C" int nasb_pack_weight_bf16(const float *w, int rows, int cols, int tra
     int R = transpose ? cols : rows, K = transpose ? rows : cols;
     int Kp = (K + 7) / 8 * 8;
     pack_weight_kernel<<<cdiv((long long)R * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, transpose, (bf16 *)out, R, Kp);
-    NASB_CHECK_LAUNCH();
-    return 0;
-}
-
-// out = pack(w, transpose=0) [rows][Kp(cols)], out_t = pack(w, transpose=1) [cols][Kp(rows)] in one launch
-extern "C" int nasb_pack_weight_bf16_both(const float *w, int rows, int cols, void *out, void *out_t, void *stream) {
-    if (!w || !out || !out_t || rows <= 0 || cols <= 0) return NASB_ERR_BAD_ARG;
-    const int Kp = (cols + 7) / 8 * 8, Kp_t = (rows + 7) / 8 * 8;
-    const long long n = (long long)rows * Kp > (long long)cols * Kp_t ? (long long)rows * Kp : (long long)cols * Kp_t;
-    pack_weight_both_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, (bf16 *)out, Kp, (bf16 *)out_t, Kp_t);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -624,10 +607,13 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     if (!tc_make_map2(&ma, x->ptr, (uint64_t)p.K, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)N, (uint64_t)Kp, TILE_N)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mo, out->ptr, (uint64_t)N, (uint64_t)M, (uint64_t)out->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    // Schedule choice (measured on a B200, profiles/r2_switches_kbench.txt): the warp-specialised kernel wins 5-30 % up to
+    // 2^20 pixels (8 x 256 x 512) and loses 5-20 % on the 512 x 1024 maps, where its second output tile costs occupancy.
+    // NASB_PW_WS=0 / 1 forces one schedule (kernel comparisons in tools/kbench.py).
     static int ws_mode = -1;
-    if (ws_mode < 0) ws_mode = getenv("NASB_PW_WS") ? atoi(getenv("NASB_PW_WS")) : 0;
+    if (ws_mode < 0) ws_mode = getenv("NASB_PW_WS") ? atoi(getenv("NASB_PW_WS")) : 2;
     int ntiles = (int)((M + TILE_M - 1) / TILE_M);
-    if (ws_mode) {  // opt-in warp-specialised schedule (see pw_tc_ws_kernel)
+    if (ws_mode == 1 || (ws_mode == 2 && M <= (1LL << 20))) {  // warp-specialised schedule (see pw_tc_ws_kernel)
         const size_t smem_ws = (size_t)p.nkb * TILE_N * 128 + (size_t)WS_SA * p.nkb * TILE_M * 128 + (size_t)2 * TILE_M * 128 +
                                4 * TILE_N * 4 + 128 + 1024;
         if (smem_ws <= 200 * 1024) {

@@ -19,10 +19,9 @@ static inline int grid_for(long long total, int threads = 256) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (total); idx += (long long)gridDim.x * blockDim.x)
 
 // ------------------------------------------------------------------------------------------------ pooling
-// PACK (opt-in, NASB_POOL_PACK=1, bf16 V = 8 only; not yet validated on a B200): the eight arg-max bytes of a channel vector
-// travel as ONE 8-byte store / load instead of eight byte accesses (the byte loads are 72 of the backward kernel's ~100
-// memory instructions per thread).  The arg-max layout in memory is unchanged.
-template <typename T, int V, bool PACK = false>
+// (A variant moving the eight arg-max bytes of a channel vector as one 8-byte access was measured on a B200 in round 2:
+// forward unchanged, backward 4-9 % SLOWER -- the compiler already merges the byte accesses -- and was removed.)
+template <typename T, int V>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const T *x, int x_cs, T *out, int out_cs, uint8_t *argmax, int N,
                                                        int IH, int IW, int OH, int OW, int C, int stride, int mode) {
     const int CV = C / V;
@@ -73,20 +72,13 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const T *x, int x_cs, T *
         }
         store_vec<T, V>(out + pix * out_cs + cv * V, acc);
         if (argmax) {
-            if constexpr (PACK && V == 8) {
-                uint2 pk;
-                pk.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
-                pk.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
-                *reinterpret_cast<uint2 *>(argmax + pix * C + cv * V) = pk;
-            } else {
 #pragma unroll
-                for (int j = 0; j < V; ++j) argmax[pix * C + cv * V + j] = (uint8_t)arg[j];
-            }
+            for (int j = 0; j < V; ++j) argmax[pix * C + cv * V + j] = (uint8_t)arg[j];
         }
     }
 }
 
-template <typename T, int V, bool PACK = false>
+template <typename T, int V>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const T *dy, int dy_cs, T *dx, int dx_cs, const uint8_t *argmax,
                                                        int N, int IH, int IW, int OH, int OW, int C, int stride, int mode) {
     const int CV = C / V;
@@ -115,17 +107,9 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const T *dy, int dy_cs, T
                 float g[V];
                 load_vec<T, V>(dy + opix * dy_cs + cv * V, g);
                 if (mode == NASB_POOL_MAX) {
-                    if constexpr (PACK && V == 8) {
-                        const uint2 pk = *reinterpret_cast<const uint2 *>(argmax + opix * C + cv * V);
-                        const uint32_t tap = (uint32_t)(ky * 3 + kx);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if ((((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xffu) == tap) acc[j] += g[j];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < V; ++j)
-                            if (argmax[opix * C + cv * V + j] == ky * 3 + kx) acc[j] += g[j];
-                    }
+                    for (int j = 0; j < V; ++j)
+                        if (argmax[opix * C + cv * V + j] == ky * 3 + kx) acc[j] += g[j];
                 } else {
                     int y0 = oy * stride - 1, x0 = ox * stride - 1;
                     int cy = min(y0 + 3, IH) - max(y0, 0), cx = min(x0 + 3, IW) - max(x0, 0);
@@ -460,11 +444,6 @@ using namespace nasb;
     } while (0)
 
 static inline int vfor(int dtype) { return dtype == NASB_BF16 ? 8 : 4; }
-static inline bool pool_pack() {
-    static int v = -1;
-    if (v < 0) v = getenv("NASB_POOL_PACK") ? atoi(getenv("NASB_POOL_PACK")) : 0;
-    return v != 0;
-}
 static inline bool same_nhw(const NasbTensor *a, const NasbTensor *b) { return a->n == b->n && a->h == b->h && a->w == b->w; }
 static inline bool act_dtype(const NasbTensor *a) { return a->dtype == NASB_F32 || a->dtype == NASB_BF16; }
 
@@ -476,12 +455,6 @@ extern "C" int nasb_pool3x3_fwd(const NasbTensor *x, int mode, int stride, const
     long long rows = npix(*out);
     if (rows == 0) return 0;
     bool ok = vec_ok(*x, vfor(x->dtype)) && vec_ok(*out, vfor(x->dtype));
-    if (pool_pack() && ok && x->dtype == NASB_BF16 && argmax && ((uintptr_t)argmax % 8) == 0) {
-        pool_fwd_kernel<bf16, 8, true><<<grid_for(rows * (x->c / 8)), 256, 0, ST>>>(
-            (const bf16 *)x->ptr, x->cstride, (bf16 *)out->ptr, out->cstride, argmax, x->n, x->h, x->w, out->h, out->w, x->c, stride, mode);
-        NASB_CHECK_LAUNCH();
-        return 0;
-    }
     NASB_DISPATCH(x->dtype, ok, (pool_fwd_kernel<T, V><<<grid_for(rows * (x->c / V)), 256, 0, ST>>>(
                                     (const T *)x->ptr, x->cstride, (T *)out->ptr, out->cstride, argmax, x->n, x->h, x->w,
                                     out->h, out->w, x->c, stride, mode)));
@@ -496,12 +469,6 @@ extern "C" int nasb_pool3x3_bwd(const NasbTensor *dy, int mode, int stride, cons
     long long rows = npix(*dx);
     if (rows == 0) return 0;
     bool ok = vec_ok(*dy, vfor(dy->dtype)) && vec_ok(*dx, vfor(dy->dtype));
-    if (pool_pack() && ok && dy->dtype == NASB_BF16 && mode == NASB_POOL_MAX && ((uintptr_t)argmax % 8) == 0) {
-        pool_bwd_kernel<bf16, 8, true><<<grid_for(rows * (dx->c / 8)), 256, 0, ST>>>(
-            (const bf16 *)dy->ptr, dy->cstride, (bf16 *)dx->ptr, dx->cstride, argmax, dx->n, dx->h, dx->w, dy->h, dy->w, dx->c, stride, mode);
-        NASB_CHECK_LAUNCH();
-        return 0;
-    }
     NASB_DISPATCH(dy->dtype, ok, (pool_bwd_kernel<T, V><<<grid_for(rows * (dx->c / V)), 256, 0, ST>>>(
                                      (const T *)dy->ptr, dy->cstride, (T *)dx->ptr, dx->cstride, argmax, dx->n, dx->h, dx->w,
                                      dy->h, dy->w, dx->c, stride, mode)));

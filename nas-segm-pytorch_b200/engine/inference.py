@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from .. import functional as Fn
+from .. import packs
 from ..helpers.utils import try_except
 
 logger = logging.getLogger(__name__)
@@ -42,7 +43,7 @@ def validate(segmenter, val_loader, epoch, epoch2, num_classes=-1, print_every=1
             pass
     segmenter.eval()
     cm = None
-    with torch.no_grad():
+    with torch.no_grad(), packs.scope(segmenter):  # weights are constant here: one multi-tensor operand pack
         for i, sample in enumerate(val_loader):
             image, target = sample["image"], sample["mask"]
             output = segmenter(image.float().cuda(non_blocking=True))

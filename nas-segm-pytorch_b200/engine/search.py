@@ -141,11 +141,41 @@ def evaluate_candidate(segmenter, Xy_train, train_loader, val_loader, args, task
     return reward, epochs_run
 
 
-def search_rounds(n_rounds, sample_fn, build_fn, evaluate_fn, update_fn=None, log=None, first_epoch=0):
+def uniform_sampler(seed=9314, enc_num_layers=4, dec_num_cells=3, cell_num_layers=4, num_ops=11):
+    """`sample_fn` over the CVPR search space of the reference controller (src/rl/micro_controllers.py:94-120,180-262:
+    decoder block i draws two inputs from enc_num_layers + i candidates; cell layer 0 draws one op, layer l >= 1 draws two
+    positions from 1 + 3(l-1) candidates and two ops), uniform instead of LSTM-parametrised -- the controller itself is
+    outside the hot path and its freshly initialised policy (weights in +-0.1) is within a few percent
+    of uniform.  Deterministic in (seed, round, slot), identical on every rank.  Entropy / log-prob of the uniform policy
+    are returned so that `update_fn` sees the controller's tuple shape."""
+    def sample(rnd, slot):
+        rs = np.random.RandomState([seed & 0x7fffffff, int(rnd), int(slot)])
+        logp = 0.0
+        conns = []
+        for i in range(dec_num_cells):
+            n = enc_num_layers + i
+            conns.append([int(rs.randint(n)), int(rs.randint(n))])
+            logp -= 2 * np.log(n)
+        ctx = [int(rs.randint(num_ops))]
+        logp -= np.log(num_ops)
+        for layer in range(1, cell_num_layers):
+            n = 1 + 3 * (layer - 1)
+            ctx.append([int(rs.randint(n)), int(rs.randint(n)), int(rs.randint(num_ops)), int(rs.randint(num_ops))])
+            logp -= 2 * np.log(n) + 2 * np.log(num_ops)
+        return [ctx, conns], float(-logp), float(logp)
+    return sample
+
+
+def search_rounds(n_rounds, sample_fn, build_fn, evaluate_fn, update_fn=None, log=None, first_epoch=0, sync_every=1):
     """Rank-parallel search: every round, slot s of the round (s = 0 .. world-1) is sampled by `sample_fn(round, s)` -- on
     EVERY rank, so that all ranks hold identical controller inputs -- rank r builds and evaluates slot r only, one
     all-gather exchanges the rewards, and `update_fn` receives the round's samples in slot order on every rank.  Rank 0
     appends one genotype line per candidate to `log`.  Returns the list of per-round reward tensors [world, RECORD].
+
+    `sync_every` = k > 1 exchanges the records of k consecutive rounds with ONE all-gather (k samples per rank from one
+    policy snapshot): a rank whose candidate was stopped early by its TaskPerformer moves on to its next candidate instead
+    of idling until the slowest rank of the round is done (SURVEY 8e "stragglers").  Controller updates and log lines are
+    then replayed in (round, slot) order after the exchange; k = 1 is the synchronous schedule.
 
     `evaluate_fn(segmenter, decoder_config) -> reward | (reward, miou, macc, fwiou) | (reward, n_epochs)` as returned by
     `evaluate_candidate`; an engine function that swallowed a RuntimeError returns 0, which is recorded as reward 0
@@ -153,7 +183,23 @@ def search_rounds(n_rounds, sample_fn, build_fn, evaluate_fn, update_fn=None, lo
     reference (main_search.py:666-668)."""
     rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
     world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-    history = []
+    history, pending = [], []
+    sync_every = max(int(sync_every), 1)
+
+    def exchange():
+        if not pending:
+            return
+        tables = parallel.gather_records([m for _, _, m in pending])  # [world, k, RECORD]: the single collective of the block
+        for j, (rnd, samples, _) in enumerate(pending):
+            table = tables[:, j, :]
+            history.append(table)
+            if update_fn is not None:
+                update_fn([(samples[s][0], float(table[s, 0]), samples[s][1], samples[s][2]) for s in range(world)])
+            if log is not None and rank == 0:
+                for s in range(world):
+                    log.write(float(table[s, 0]), first_epoch + rnd * world + s, int(table[s, 3]), float(table[s, 2]), samples[s][0])
+        del pending[:]
+
     for rnd in range(n_rounds):
         samples = [sample_fn(rnd, s) for s in range(world)]
         t0 = time.time()
@@ -167,11 +213,8 @@ def search_rounds(n_rounds, sample_fn, build_fn, evaluate_fn, update_fn=None, lo
         mine = list(out) if isinstance(out, (tuple, list)) else [float(out), 0.0, 0.0, 0.0]
         # record = (reward, miou, time per epoch, #params): the last two fields feed the genotype log
         mine = [float(mine[0]), float(mine[1]) if len(mine) > 1 else 0.0, (time.time() - t0) / n_epochs, float(n_params)]
-        table = parallel.gather_records([mine])[:, 0, :]  # [world, RECORD], the single collective of the round
-        history.append(table)
-        if update_fn is not None:
-            update_fn([(samples[s][0], float(table[s, 0]), samples[s][1], samples[s][2]) for s in range(world)])
-        if log is not None and rank == 0:
-            for s in range(world):
-                log.write(float(table[s, 0]), first_epoch + rnd * world + s, int(table[s, 3]), float(table[s, 2]), samples[s][0])
+        pending.append((rnd, samples, mine))
+        if len(pending) == sync_every:
+            exchange()
+    exchange()
     return history

@@ -23,8 +23,9 @@ from torch import nn
 
 from .. import config as _config
 from .. import functional as Fn
-from .. import lib
+from .. import lib, packs
 from ..graphs import StepGraph, make_capturable
+from ..optim import FusedStep
 from ..helpers.utils import try_except
 
 logger = logging.getLogger(__name__)
@@ -41,6 +42,38 @@ def _segm_loss(crit, logits, target, size=None):
     if crit is None or isinstance(crit, (nn.NLLLoss,)) or hasattr(crit, "ignore_index"):
         return Fn.cross_entropy2d(logits, target, _ignore_index(crit) if crit is not None else 255)
     return crit(nn.functional.log_softmax(logits.float(), dim=1), target)
+
+
+def _finish_step(owner, entries, polyak_params, avg_param, polyak_decay):
+    """clip_grad_norm_ + optimiser.step() for every (optim, clip_params, max_norm) entry, then the Polyak average
+    (trainer.py:163-169,258-272).  Plain SGD / Adam run as two multi-tensor launches (optim.FusedStep, cached on `owner`
+    with strong references to everything its key names); anything else keeps the caller's own torch calls."""
+    do_polyak = avg_param is not None and polyak_params is not None
+    if _config().fused_optim and FusedStep.supported(entries):
+        key = tuple(id(o) for o, _, _ in entries) + tuple(float(mn) for _, _, mn in entries) + (id(avg_param) if do_polyak else 0,)
+        cached = getattr(owner, "_nasb_fused_step", None)
+        if cached is None or cached[0] != key:
+            plist = list(polyak_params) if do_polyak else None
+            cached = (key, FusedStep([(o, list(cp), mn) for o, cp, mn in entries], plist, avg_param if do_polyak else None))
+            owner._nasb_fused_step = cached
+        cached[1].step(polyak_decay if do_polyak else 0.0)
+        return
+    for o, clip_params, max_norm in entries:
+        if max_norm > 0:
+            nn.utils.clip_grad_norm_(clip_params, max_norm)
+        o.step()
+    if do_polyak:
+        for p, avg_p in zip(polyak_params, avg_param):
+            avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+
+
+def _hyper_key(*optims):
+    """Hyper-parameters a captured iteration bakes in (kernel arguments of the fused step / torch's own scalars)."""
+    key = []
+    for o in optims:
+        for g in o.param_groups:
+            key.append(tuple((k, v) for k, v in sorted(g.items()) if k != "params" and isinstance(v, (int, float, bool, tuple, type(None)))))
+    return tuple(key)
 
 
 def _set_stage(loader, stage):
@@ -63,7 +96,8 @@ def populate_task0(segmenter, train_loader, kd_net, n_train, do_kd=False):
         train_loader.batch_sampler.batch_size = 1  # reference: batch 1 "to not run out of memory"
     except AttributeError:
         pass
-    with torch.no_grad():
+    # weights are constant over the whole loop: one multi-tensor pack of the encoder's tensor-core operands
+    with torch.no_grad(), packs.scope(segmenter.module.encoder):
         n_curr = 0
         for sample in train_loader:
             image = sample["image"].float().cuda()
@@ -120,9 +154,11 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
 
     def iteration(idx):
         lib.zero_arena.begin(dev)
+        packs.begin(decoder)
         try:
             return _iteration(idx)
         finally:
+            packs.end()
             lib.zero_arena.end()
 
     def _iteration(idx):
@@ -141,22 +177,28 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
                 loss = loss + _segm_loss(segm_crit, aux_out, y, out_size) * aux_weight
         optim_dec.zero_grad()
         loss.backward()
-        nn.utils.clip_grad_norm_(decoder.parameters(), dec_grad_clip)
-        optim_dec.step()
-        if do_polyak:
-            for p, avg_p in zip(decoder.parameters(), avg_param):
-                avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+        if dec_grad_clip > 0:
+            _finish_step(decoder, [(optim_dec, dec_params, dec_grad_clip)], dec_params if do_polyak else None,
+                         avg_param if do_polyak else None, polyak_decay)
+        else:  # the reference clips unconditionally (trainer.py:163); a non-positive norm keeps torch's own arithmetic
+            nn.utils.clip_grad_norm_(dec_params, dec_grad_clip)
+            _finish_step(decoder, [(optim_dec, (), 0.0)], dec_params if do_polyak else None,
+                         avg_param if do_polyak else None, polyak_decay)
         return loss
+
+    dec_params = list(decoder.parameters())
 
     step = iteration
     if _config().cuda_graphs:
         make_capturable(optim_dec)
         sg = getattr(decoder, "_nasb_task0_graph", None)
         key = (id(optim_dec), id(Xy_train), id(avg_param), batch_size, bool(do_kd), float(kd_coeff), float(aux_weight),
-               bool(do_polyak), float(polyak_decay), bool(freeze_bn), float(dec_grad_clip))
+               bool(do_polyak), float(polyak_decay), bool(freeze_bn), float(dec_grad_clip), _ignore_index(segm_crit),
+               _hyper_key(optim_dec), _config().act_dtype)
         if sg is None or sg.key != key:
             sg = StepGraph(iteration, [torch.zeros(batch_size, dtype=torch.int64, device=dev)])
             sg.key = key
+            sg.keep = (optim_dec, Xy_train, avg_param)  # the ids in the key stay unique while the graph is cached
             decoder._nasb_task0_graph = sg
         step = sg
     for i in range(n_passes):
@@ -173,10 +215,12 @@ def segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, en
     """One end-to-end iteration on device-resident tensors (the body of trainer.py:226-272): forward, nearest-resized
     target, CE (+ aux), backward, the two grad-norm clips, the two optimiser steps, Polyak.  Returns the loss tensor."""
     lib.zero_arena.begin(image.device)
+    packs.begin(segmenter)
     try:
         return _segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
                                do_polyak, aux_weight, avg_param, polyak_decay)
     finally:
+        packs.end()
         lib.zero_arena.end()
 
 
@@ -194,15 +238,9 @@ def _segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, e
     optim_enc.zero_grad()
     optim_dec.zero_grad()
     loss.backward()
-    if enc_grad_clip > 0:
-        nn.utils.clip_grad_norm_(segmenter.module.encoder.parameters(), enc_grad_clip)
-    if dec_grad_clip > 0:
-        nn.utils.clip_grad_norm_(segmenter.module.decoder.parameters(), dec_grad_clip)
-    optim_enc.step()
-    optim_dec.step()
-    if do_polyak:
-        for p, avg_p in zip(segmenter.parameters(), avg_param):
-            avg_p.mul_(polyak_decay).add_(p.data, alpha=1.0 - polyak_decay)
+    _finish_step(segmenter, [(optim_enc, segmenter.module.encoder.parameters(), enc_grad_clip),
+                             (optim_dec, segmenter.module.decoder.parameters(), dec_grad_clip)],
+                 segmenter.parameters() if do_polyak else None, avg_param if do_polyak else None, polyak_decay)
     return loss
 
 
@@ -249,11 +287,17 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
         ahead = upload()
         if use_graph:
             sg = getattr(segmenter, "_nasb_step_graph", None)
-            if sg is None or sg.key != (id(optim_enc), id(optim_dec)) or not sg.matches((image, target)):
+            # everything the captured iteration bakes in (the same discipline as train_task0's key); `keep` holds strong
+            # references so that no id() in the key can be recycled by a new object while the graph is cached
+            key = (id(optim_enc), id(optim_dec), id(avg_param), bool(freeze_bn), float(enc_grad_clip), float(dec_grad_clip),
+                   float(aux_weight), bool(do_polyak), float(polyak_decay), _ignore_index(segm_crit),
+                   _hyper_key(optim_enc, optim_dec), _config().act_dtype)
+            if sg is None or sg.key != key or not sg.matches((image, target)):
                 sg = StepGraph(lambda im, tg: segmenter_step(segmenter, im, tg, optim_enc, optim_dec, segm_crit, enc_grad_clip,
                                                              dec_grad_clip, do_polyak, aux_weight, avg_param, polyak_decay),
                                [torch.empty_like(image), torch.empty_like(target)])
-                sg.key = (id(optim_enc), id(optim_dec))
+                sg.key = key
+                sg.keep = (optim_enc, optim_dec, avg_param)
                 segmenter._nasb_step_graph = sg
             loss = sg(image, target)
         else:

@@ -8,7 +8,7 @@ import ctypes as C
 
 import torch
 
-from . import lib
+from . import lib, packs
 from .lib import ACT_NONE, ACT_RELU, ACT_RELU6, POOL_AVG, POOL_MAX, call, desc, ptr, ref, try_call  # noqa: F401
 
 
@@ -35,9 +35,12 @@ def _dw_stats_on():
     return config().fuse_dw_stats
 
 
-def _dual_pack_on():
-    from . import config
-    return config().dual_pack
+def _bn_momentum(bn):
+    """nn.BatchNorm2d's update factor: `momentum`, or 1 / num_batches_tracked (cumulative moving average) when momentum is
+    None -- that reads the device counter (a host sync, and an error under CUDA-graph capture, which cannot bake it in)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    return 1.0 / (int(bn.num_batches_tracked.item()) + 1)
 
 
 def _tiles_on():
@@ -82,6 +85,9 @@ def _c3_ok(x, cin, cout, ks, stride, dil, pad):
 
 
 def _pack_conv3(weight, mode):
+    wp = packs.get(weight, packs.C3_T if mode else packs.C3)
+    if wp is not None:
+        return wp
     cout, cin = weight.shape[0], weight.shape[1]
     n = int(lib.load().nasb_pack_conv3_elems(cout, cin, mode))
     wp = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
@@ -101,8 +107,11 @@ def _bf16_padded_copy(t):
 
 
 def _pack_weight(weight, transpose):
-    """fp32 [C_out, C_in, 1, 1] -> bf16 [R][Kp] operand of the tensor-core kernel (a few KB; repacked per call because the
-    optimiser rewrites the fp32 master weights every step)."""
+    """fp32 [C_out, C_in, 1, 1] -> bf16 [R][Kp] operand of the tensor-core kernel.  Inside an engine iteration the operand
+    comes from the model's persistent packs (packs.begin: one launch for the whole model); otherwise it is packed here."""
+    wp = packs.get(weight, packs.PW_T if transpose else packs.PW)
+    if wp is not None:
+        return wp
     cout, cin = weight.shape[0], weight.shape[1]
     r, k = (cin, cout) if transpose else (cout, cin)
     wp = torch.empty(r * ((k + 7) // 8 * 8), dtype=torch.bfloat16, device=weight.device)
@@ -134,14 +143,7 @@ class _ConvUnit(torch.autograd.Function):
 
         use_tc = (not dw and ks == 1 and stride == 1 and pad == 0 and x1 is None and not in_relu and not image
                   and _tc_ok(x0, x0.shape[1], cout, out_dtype))
-        wpack = wpack_t = None
-        if use_tc and _dual_pack_on() and weight.requires_grad and x0.requires_grad:  # dgrad wants the transposed pack: one launch
-            cin = x0.shape[1]
-            wpack = torch.empty(cout * ((cin + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
-            wpack_t = torch.empty(cin * ((cout + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
-            call("nasb_pack_weight_bf16_both", ptr(weight), cout, cin, ptr(wpack), ptr(wpack_t))
-        elif use_tc:
-            wpack = _pack_weight(weight, False)
+        wpack = _pack_weight(weight, False) if use_tc else None
         # speed mode stem: image -> bf16 patch matrix [n, 32, oh, ow] (k = ci*9 + ky*3 + kx), then the pointwise tensor-core
         # kernel with K = 32; the patch matrix is what the backward pass keeps (weight gradient = nasb_pw_tc_wgrad)
         stem_tc = (image and not dw and ks == 3 and x1 is None and not in_relu and res is None and x0.shape[1] == 3
@@ -149,8 +151,10 @@ class _ConvUnit(torch.autograd.Function):
         if stem_tc:
             xp = lib.new_act(n, 32, oh, ow, torch.bfloat16, dev)
             call("nasb_stem_im2col", ref(dx0), ks, stride, dil, pad, ref(desc(xp)))
-            wpack = torch.empty(cout * 32, dtype=torch.bfloat16, device=dev)
-            call("nasb_pack_weight_bf16", ptr(weight), cout, 27, 0, ptr(wpack))
+            wpack = packs.get(weight, packs.PW)
+            if wpack is None:
+                wpack = torch.empty(cout * 32, dtype=torch.bfloat16, device=dev)
+                call("nasb_pack_weight_bf16", ptr(weight), cout, 27, 0, ptr(wpack))
             x0, dx0, use_tc = xp, desc(xp), True
         use_c3 = (not dw and x1 is None and not in_relu and not image and res is None
                   and out_dtype in (torch.bfloat16, torch.float32) and _c3_ok(x0, x0.shape[1], cout, ks, stride, dil, pad))
@@ -201,7 +205,7 @@ class _ConvUnit(torch.autograd.Function):
             z = lib.new_act(n, cout, oh, ow, out_dtype, dev)
             ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
             sv = torch.empty((2, cout), dtype=torch.float32, device=dev)
-            mom = 0.1 if bn.momentum is None else float(bn.momentum)
+            mom = _bn_momentum(bn)
             fused_stats = use_tc or use_c3
             sums = None
             if fused_stats or (dw and not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and _dw_stats_on()):
@@ -226,7 +230,6 @@ class _ConvUnit(torch.autograd.Function):
             if res is not None and not late_res and not res_done:
                 call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(y)))
         ctx.stem_tc = stem_tc
-        ctx.wpack_t = wpack_t
         ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
         ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
         ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
@@ -303,8 +306,7 @@ class _ConvUnit(torch.autograd.Function):
                      ACT_NONE, ref(desc(dx0)), None)
             elif (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image
                     and _tc_ok(dz, cout, x0.shape[1], x0.dtype)):
-                wpt = ctx.wpack_t if ctx.wpack_t is not None else _pack_weight(weight, True)
-                call("nasb_pw_tc_fwd", ref(ddz), ptr(wpt), x0.shape[1], None, None, ACT_NONE, None,
+                call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
                      ref(desc(dx0)), None)
             elif dw:
                 tiled = False
@@ -352,7 +354,7 @@ class _BnAct(torch.autograd.Function):
                 raise ValueError("Expected more than 1 value per channel when training, got input size {}".format(
                     list(x.shape)))
             sv = torch.empty((2, c), dtype=torch.float32, device=dev)
-            mom = 0.1 if bn.momentum is None else float(bn.momentum)
+            mom = _bn_momentum(bn)
             call("nasb_bn_stats", ref(desc(x)), ptr(gamma), ptr(beta), float(bn.eps), mom, ptr(bn.running_mean),
                  ptr(bn.running_var), ptr(sv[0]), ptr(sv[1]), ptr(ss[0]), ptr(ss[1]), ptr(bn.num_batches_tracked),
                  ptr(_ws(dev, c)))

@@ -37,7 +37,6 @@ _SIG = {
     "nasb_stem_wgrad": [_TP, _TP, _I, _I, _I, _I, _P, _P],
     "nasb_stem_im2col": [_TP, _I, _I, _I, _I, _TP, _P],
     "nasb_pack_weight_bf16": [_P, _I, _I, _I, _P, _P],
-    "nasb_pack_weight_bf16_both": [_P, _I, _I, _P, _P, _P],
     "nasb_pw_tc_supported": [_I, _I],
     "nasb_pw_tc_wgrad_supported": [_I, _I],
     "nasb_pw_tc_wgrad": [_TP, _TP, _P, _P],
@@ -79,15 +78,20 @@ _SIG = {
     "nasb_confmat_logits": [_TP, _P, _I, _I, _I, _P, _P],
     "nasb_ius_accs": [_P, _I, _P, _P, _P, _P],
     "nasb_sumsq": [_P, _L, _P, _P],
+    "nasb_mt_grad_sumsq": [_P, _I, _P, _I, _P],
+    "nasb_mt_optim_step": [_P, _I, _P, _I, _P, _I, _P, _F, _P],
+    "nasb_pack_elems": [_I, _I, _I],
+    "nasb_mt_pack_bf16": [_P, _I, _P],
     "nasb_version": [],
 }
-_RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L}
+_RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L,
+        "nasb_pack_elems": _L}
 EXPORTS = tuple(sorted(_SIG))
 
 _lib = None
 launches = 0  # kernels launched through the C ABI by this process (bench.py reports the delta over its timed region)
 # kernels (and async memsets) behind one call of each entry point; everything not listed launches exactly one
-_KERNELS_PER_CALL = {"nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
+_KERNELS_PER_CALL = {"nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
                      "nasb_spatial_mean": 2, "nasb_spatial_sum": 2}
 _prof = None  # list of (key, bytes, ev0, ev1) while profiling
 

@@ -212,6 +212,28 @@ class Zero(nn.Module):
         return Fn.channel_tile(x, self.repeats[1], self.stride, 0.0)
 
 
+class FactorizedReduce(nn.Module):
+    """ReLU -> two stride-2 1x1 convolutions on the even / odd pixel grids -> cat -> BN (layer_factory.py:300-313).  Not
+    reachable from any genotype (it is in no name table); kept for registry completeness on the general kernels."""
+
+    def __init__(self, C_in, C_out, affine=True):
+        super().__init__()
+        assert C_out % 2 == 0
+        self.relu = nn.ReLU(inplace=False)
+        self.conv_1 = nn.Conv2d(C_in, C_out // 2, 1, stride=2, padding=0, bias=False)
+        self.conv_2 = nn.Conv2d(C_in, C_out // 2, 1, stride=2, padding=0, bias=False)
+        self.bn = nn.BatchNorm2d(C_out, affine=affine)
+
+    def forward(self, x):
+        x = _entry(x)
+        x = Fn.concat_resize([x], x.shape[2:], relu=True)
+        a = Fn.conv_unit(x, self.conv_1.weight, None, ks=1, stride=2)
+        b = Fn.conv_unit(_entry(x[:, :, 1:, 1:]), self.conv_2.weight, None, ks=1, stride=2)
+        if a.shape[2:] != b.shape[2:]:  # odd input sizes: torch.cat fails in the reference as well
+            raise RuntimeError("Sizes of tensors must match except in dimension 1")
+        return Fn.bn_act(Fn.concat_resize([a, b], a.shape[2:]), self.bn, ACT_NONE)
+
+
 OPS = {
     "none": lambda C_in, C_out, stride, affine, repeats=1: Zero(C_in, C_out, stride),
     "avg_pool_3x3": lambda C_in, C_out, stride, affine, repeats=1: Pool(C_in, C_out, stride, repeats, ksize=3, mode="avg"),

@@ -237,6 +237,15 @@ class TemplateDecoder(nn.Module):
         self.num_classes = num_classes
         self.agg_size = agg_size
 
+    def _reset_clf(self, num_classes):
+        """Replace the classifier for another label set (micro_decoders.py:367-373; the reference reads self.agg_size there
+        without ever setting it -- here it is set, so the call the inference notebooks make works)."""
+        if num_classes != self.num_classes:
+            dev = self.conv_clf.weight.device
+            del self.conv_clf
+            self.conv_clf = conv3x3(self.agg_size, num_classes, stride=1, bias=True).to(dev)
+            self.num_classes = num_classes
+
     def prettify(self, n_params):
         return "#PARAMS\n\n {:3.2f}M".format(n_params / 1e6) + "\n\n#Connections:\n" + self.info
 

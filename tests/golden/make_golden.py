@@ -245,6 +245,58 @@ def gen_task0():
     save("task0_step", **out)
 
 
+# ------------------------------------------------------------------------------ engine: train_segmenter
+def gen_segmenter():
+    """The UNMODIFIED reference train_segmenter (engine/trainer.py:179-283) on the CPU (Tensor.cuda aliased away): two
+    epochs x two iterations, SGD encoder + Adam decoder, both clips, Polyak 0.99, aux heads, BatchNorm in training mode."""
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.manual_seed(0)
+    enc = mbv2(pretrained=False)
+    dec = MicroDecoder(list(enc.out_sizes), 21, C0, agg_size=16, aux_cell=True, repeats=1)
+    net = EncDec(enc, dec)
+    ks_e, ks_d = fill(enc, seed=21), fill(dec, seed=22)
+    seg = nn.Module()
+    seg.module = net
+    seg.forward = lambda x: net(x)
+    B, H, W, n_it = 2, 128, 128, 2
+    loader = ListLoader()
+    out = {}
+    for i in range(n_it):
+        img = det_array("seg/img%d" % i, (B, 3, H, W)).astype(np.float64)
+        msk = det_array("seg/msk%d" % i, (B, H, W), kind="int", lo=0, hi=21).astype(np.uint8)
+        msk[:, ::5, ::3] = 255
+        loader.append({"image": torch.from_numpy(img), "mask": torch.from_numpy(msk)})
+    optim_enc = torch.optim.SGD(enc.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-5)
+    optim_dec = torch.optim.Adam(dec.parameters(), lr=3e-3, weight_decay=1e-5)
+    avg = [p.data.clone() for p in seg.parameters()]
+    losses = []
+    orig_info = ref_trainer.logger.info
+    ref_trainer.logger.info = lambda msg, *a: losses.append(float(msg.split("Avg. Loss:")[1].split()[0]))
+    for epoch in range(2):
+        r = ref_trainer.train_segmenter(seg, loader, optim_enc, optim_dec, epoch, nn.NLLLoss2d(ignore_index=255), False,
+                                        3.0, 3.0, True, print_every=1, aux_weight=0.15, avg_param=avg, polyak_decay=0.99)
+        assert r is None
+    ref_trainer.logger.info = orig_info
+    out.update({"enc_keys": ks_arrays(ks_e)["keys"], "enc_shapes": ks_arrays(ks_e)["shapes"],
+                "dec_keys": ks_arrays(ks_d)["keys"], "dec_shapes": ks_arrays(ks_d)["shapes"],
+                "logged_avg_loss": np.array(losses)})
+    # the 1.8 M encoder parameters would make a 14 MB fixture: tensors above 4096 elements are pinned by a strided sample of
+    # 512 elements plus their sum and sum of squares (float64), everything smaller is stored whole
+    def put(key, arr):
+        arr = np.asarray(arr)
+        if arr.size <= 4096 or arr.dtype.kind != "f":
+            out[key] = arr
+        else:
+            flat = arr.reshape(-1)
+            out[key + "@sample"] = flat[:: max(flat.size // 512, 1)][:512].copy()
+            out[key + "@sums"] = np.array([flat.astype(np.float64).sum(), (flat.astype(np.float64) ** 2).sum()])
+    for k, v in net.state_dict().items():
+        put("post/" + k, n(v))
+    for (pn, _), a in zip(seg.named_parameters(), avg):
+        put("avg/" + pn, n(a))
+    save("segmenter_step", **out)
+
+
 # ------------------------------------------------------------------------------ engine: validate / metric
 class TableSegmenter(nn.Module):
     """Returns pre-computed logits batch by batch -- pins inference.py:58-91 without a network."""
@@ -308,12 +360,14 @@ def gen_validate():
 
 if __name__ == "__main__":
     logging.basicConfig(level=logging.WARNING)
-    which = sys.argv[1:] or ["ops", "nets", "task0", "validate"]
+    which = sys.argv[1:] or ["ops", "nets", "task0", "segmenter", "validate"]
     if "ops" in which:
         gen_ops()
     if "nets" in which:
         gen_nets()
     if "task0" in which:
         gen_task0()
+    if "segmenter" in which:
+        gen_segmenter()
     if "validate" in which:
         gen_validate()
