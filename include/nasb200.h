@@ -332,6 +332,28 @@ typedef struct NasbPackJob {
 long long nasb_pack_elems(int kind, int c_out, int c_in);
 int nasb_mt_pack_bf16(const NasbPackJob *jobs, int n, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Inference: one call per nn.Conv2d -> nn.BatchNorm2d.eval() -> nn.ReLU / nn.ReLU6 (-> + residual) unit
+ * (layer_factory.py:94-114,125-158,225-265 with BN in eval mode).  Folds the running statistics, packs the bf16
+ * tensor-core operand when the shape allows and picks the kernel (tcgen05 pointwise / dense 3x3, TMA-tiled depthwise,
+ * general implicit GEMM) -- what the Python host does with several calls on the training path.
+ *   u->gamma / beta may be NULL (affine=False); running_mean == NULL means "no BatchNorm" (bias is then the shift).
+ *   scratch: >= nasb_conv_unit_scratch(c_out, c_in) bytes of device memory owned by the caller, rewritten by every call.
+ *   flags  : NASB_UNIT_TENSOR_CORES | NASB_UNIT_TMA_TILES enable the specialised kernels.
+ * -------------------------------------------------------------------------------------------------------*/
+#define NASB_UNIT_TENSOR_CORES 1
+#define NASB_UNIT_TMA_TILES 2
+typedef struct NasbConvUnit {
+    const float *weight;                                      /* [c_out][c_in / groups][ks][ks] */
+    const float *gamma, *beta, *running_mean, *running_var;   /* BatchNorm2d (eval) or NULL */
+    const float *bias;                                        /* conv bias (only without BatchNorm) or NULL */
+    float eps;
+    int32_t c_out, ks, stride, dil, pad, dw, in_relu, act;
+} NasbConvUnit;
+long long nasb_conv_unit_scratch(int c_out, int c_in);
+int nasb_conv_unit_infer(const NasbTensor *x, const NasbConvUnit *u, const NasbTensor *res, const NasbTensor *out,
+                         void *scratch, long long scratch_bytes, int flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,17 +212,51 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const T *dz, int dz_cs,
             int ylo, yhi, xlo, xhi;
             adj_range(iy, rh, OH, ylo, yhi);
             adj_range(ix, rw, OW, xlo, xhi);
-            for (int oy = ylo; oy <= yhi; ++oy) {
-                float wy = adj_weight(oy, iy, rh, IH);
-                if (wy == 0.f) continue;
-                for (int ox = xlo; ox <= xhi; ++ox) {
-                    float wx = adj_weight(ox, ix, rw, IW);
-                    if (wx == 0.f) continue;
-                    float g[V];
-                    load_vec<T, V>(dz + (((long long)n * OH + oy) * OW + ox) * dz_cs + c0, g);
-                    float w = wy * wx;
+            // The tent weights are separable: the column weights of this thread's window are computed once (<= RB_MAXT
+            // candidates for up-sampling factors up to 8) instead of once per (row, column) pair -- the x8 gradient was
+            // bound by that arithmetic (0.8 TB/s), not by its loads.
+            constexpr int RB_MAXT = 24;
+            const int nx = xhi - xlo + 1;
+            if (nx <= RB_MAXT) {
+                float wxs[RB_MAXT];
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = fmaf(w, g[j], acc[j]);
+                for (int k = 0; k < RB_MAXT; ++k) wxs[k] = k < nx ? adj_weight(xlo + k, ix, rw, IW) : 0.f;
+                int k0 = 0, k1 = nx - 1;  // trim the zero-weight fringe of the candidate range
+                while (k0 < k1 && wxs[k0] == 0.f) ++k0;
+                while (k1 > k0 && wxs[k1] == 0.f) --k1;
+                // Four taps per step with unconditional (clamped) loads: a thread keeps four 16-byte loads in flight instead
+                // of one -- with one load per iteration the x8 gradient was bound by 256 serialised L2 round trips per thread.
+                for (int oy = ylo; oy <= yhi; ++oy) {
+                    const float wy = adj_weight(oy, iy, rh, IH);
+                    if (wy == 0.f) continue;
+                    const T *rowp = dz + (((long long)n * OH + oy) * OW + xlo) * dz_cs + c0;
+                    for (int k = k0; k <= k1; k += 4) {
+                        float g[4][V], w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int kk = k + u <= k1 ? k + u : k1;
+                            w[u] = k + u <= k1 ? wy * wxs[kk] : 0.f;
+                            load_vec<T, V>(rowp + (long long)kk * dz_cs, g[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int j = 0; j < V; ++j) acc[j] = fmaf(w[u], g[u][j], acc[j]);
+                    }
+                }
+            } else {
+                for (int oy = ylo; oy <= yhi; ++oy) {
+                    float wy = adj_weight(oy, iy, rh, IH);
+                    if (wy == 0.f) continue;
+                    for (int ox = xlo; ox <= xhi; ++ox) {
+                        float wx = adj_weight(ox, ix, rw, IW);
+                        if (wx == 0.f) continue;
+                        float g[V];
+                        load_vec<T, V>(dz + (((long long)n * OH + oy) * OW + ox) * dz_cs + c0, g);
+                        float w = wy * wx;
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = fmaf(w, g[j], acc[j]);
+                    }
                 }
             }
         }

@@ -13,8 +13,33 @@ from .lib import ACT_NONE, ACT_RELU, ACT_RELU6, POOL_AVG, POOL_MAX, call, desc, 
 
 
 def act_dtype():
-    from . import config
-    return config().act_dtype
+    return _cfg().act_dtype
+
+
+class _NoGradCtx:
+    """Stand-in for the autograd context when gradients are off: the forward of every Function below then runs as a plain
+    call (torch.autograd.Function.apply costs ~15 us per op on the host, 135 ops per arch0 forward)."""
+    needs_input_grad = (False,) * 32
+
+    def save_for_backward(self, *tensors):
+        pass
+
+
+def _apply(fn, *args):
+    if torch.is_grad_enabled():
+        return fn.apply(*args)
+    return fn.forward(_NoGradCtx(), *args)
+
+
+_config_obj = None
+
+
+def _cfg():
+    global _config_obj
+    if _config_obj is None:
+        from . import config
+        _config_obj = config()
+    return _config_obj
 
 
 def conv_out_hw(h, w, ks, stride, dil, pad):
@@ -31,8 +56,7 @@ def _grad_in(dy, like_dtype):
 
 
 def _dw_stats_on():
-    from . import config
-    return config().fuse_dw_stats
+    return _cfg().fuse_dw_stats
 
 
 def _bn_momentum(bn):
@@ -44,14 +68,12 @@ def _bn_momentum(bn):
 
 
 def _tiles_on():
-    from . import config
-    return config().use_tma_tiles
+    return _cfg().use_tma_tiles
 
 
 def _tc_ok(x, cin, cout, out_dtype):
     """Can this pointwise GEMM (K=cin -> N=cout) run on the tcgen05 kernel?  bf16 in/out, 8-aligned channels/pitches."""
-    from . import config
-    if not config().use_tcgen05 or x.dtype != torch.bfloat16 or out_dtype != torch.bfloat16:
+    if not _cfg().use_tcgen05 or x.dtype != torch.bfloat16 or out_dtype != torch.bfloat16:
         return False
     if x.data_ptr() % 16 or lib.desc(x).cstride % 8:
         return False
@@ -59,8 +81,7 @@ def _tc_ok(x, cin, cout, out_dtype):
 
 
 def _tc_wgrad_ok(x, dz, cout):
-    from . import config
-    if not config().use_tcgen05 or x.dtype != torch.bfloat16 or dz.dtype != torch.bfloat16:
+    if not _cfg().use_tcgen05 or x.dtype != torch.bfloat16 or dz.dtype != torch.bfloat16:
         return False
     if x.data_ptr() % 16 or dz.data_ptr() % 16 or lib.desc(x).cstride % 8 or lib.desc(dz).cstride % 8:
         return False
@@ -68,16 +89,14 @@ def _tc_wgrad_ok(x, dz, cout):
 
 
 def _stem_tc_ok(cout):
-    from . import config
     lb = lib.load()
-    return bool(config().use_tcgen05 and cout % 8 == 0 and lb.nasb_pw_tc_supported(32, int(cout))
+    return bool(_cfg().use_tcgen05 and cout % 8 == 0 and lb.nasb_pw_tc_supported(32, int(cout))
                 and lb.nasb_pw_tc_wgrad_supported(int(cout), 32))
 
 
 def _c3_ok(x, cin, cout, ks, stride, dil, pad):
     """3x3 implicit GEMM on the tensor cores: bf16 input with a 16-byte pixel pitch, stride 1, 'same' geometry."""
-    from . import config
-    if not config().use_tcgen05 or ks != 3 or stride != 1 or pad != dil or x.dtype != torch.bfloat16:
+    if not _cfg().use_tcgen05 or ks != 3 or stride != 1 or pad != dil or x.dtype != torch.bfloat16:
         return False
     if x.data_ptr() % 16 or lib.desc(x).cstride % 8:
         return False
@@ -114,7 +133,12 @@ def _pack_weight(weight, transpose):
         return wp
     cout, cin = weight.shape[0], weight.shape[1]
     r, k = (cin, cout) if transpose else (cout, cin)
-    wp = torch.empty(r * ((k + 7) // 8 * 8), dtype=torch.bfloat16, device=weight.device)
+    if not torch.is_grad_enabled():  # inference: one buffer per weight, rewritten (in stream order) by every call
+        wp = getattr(weight, "_nasb_wp", None)
+        if wp is None or wp.device != weight.device:
+            wp = weight._nasb_wp = torch.empty(r * ((k + 7) // 8 * 8), dtype=torch.bfloat16, device=weight.device)
+    else:
+        wp = torch.empty(r * ((k + 7) // 8 * 8), dtype=torch.bfloat16, device=weight.device)
     call("nasb_pack_weight_bf16", ptr(weight), cout, cin, 1 if transpose else 0, ptr(wp))
     return wp
 
@@ -194,7 +218,13 @@ class _ConvUnit(torch.autograd.Function):
         if bn is None:
             run_conv(y, None, bias, act, fused_res)
         elif not training:
-            ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
+            if torch.is_grad_enabled():
+                ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
+            else:  # inference: the folded constants live in one buffer per BN module, rewritten (in stream order) per call
+                ss = bn.__dict__.get("_nasb_ss")
+                if ss is None or ss.device != dev:
+                    ss = torch.empty((2, cout), dtype=torch.float32, device=dev)
+                    object.__setattr__(bn, "_nasb_ss", ss)
             call("nasb_bn_fold", ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps), cout,
                  ptr(ss[0]), ptr(ss[1]))
             run_conv(y, ss[0], ss[1], act, fused_res)
@@ -330,13 +360,43 @@ class _ConvUnit(torch.autograd.Function):
         return dx0, dx1, dweight, dgamma, dbeta, dbias, dres, None, None
 
 
+def _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, in_relu, out_dtype):
+    """Inference path of a conv unit: BN fold + operand pack + kernel choice behind ONE C-ABI call (csrc/unit.cu).  The
+    parameter block and the scratch buffer live on the weight tensor and are rebuilt when any address or setting changes."""
+    lib.require_cuda(x0)
+    n, _, h, w = x0.shape
+    cout = weight.shape[0]
+    if bn is not None and bn.running_mean is None:
+        raise RuntimeError("BatchNorm2d without running statistics is not supported")
+    settings = (ks, stride, dil, pad, act, dw, in_relu, id(bn))
+    st = weight.__dict__.get("_nasb_unit")
+    wp = weight.data_ptr()
+    if (st is None or st[2] != settings or st[0].weight != wp or st[0].bias != (bias.data_ptr() if bias is not None else None)
+            or (bn is not None and st[0].running_mean != bn.running_mean.data_ptr())):
+        u = lib.NasbConvUnit(wp, ptr(bn.weight) if bn is not None else None, ptr(bn.bias) if bn is not None else None,
+                             ptr(bn.running_mean) if bn is not None else None, ptr(bn.running_var) if bn is not None else None,
+                             ptr(bias), float(bn.eps) if bn is not None else 0.0, cout, ks, stride, dil, pad, int(bool(dw)),
+                             int(in_relu), act)
+        nbytes = int(lib.load().nasb_conv_unit_scratch(cout, int(x0.shape[1])))
+        st = (u, torch.empty(nbytes, dtype=torch.uint8, device=weight.device), settings, nbytes)
+        weight._nasb_unit = st
+    oh, ow = conv_out_hw(h, w, ks, stride, dil, pad)
+    y = lib.new_act(n, cout, oh, ow, out_dtype or x0.dtype, x0.device)
+    cfg = _cfg()
+    call("nasb_conv_unit_infer", ref(desc(x0)), C.byref(st[0]), ref(desc(res)) if res is not None else None, ref(desc(y)),
+         st[1].data_ptr(), st[3], (1 if cfg.use_tcgen05 else 0) | (2 if cfg.use_tma_tiles else 0))
+    return y
+
+
 def conv_unit(x0, weight, bn=None, *, ks, stride=1, dil=1, pad=0, act=ACT_NONE, x1=None, bias=None, res=None, dw=False,
               in_relu=0, image=False, out_dtype=None):
     """Fused conv unit.  ``bn`` is the nn.BatchNorm2d module holding gamma/beta/running stats (or None)."""
+    if x1 is None and not image and not torch.is_grad_enabled() and (bn is None or not bn.training):
+        return _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, in_relu, out_dtype)
     cfg = dict(ks=ks, stride=stride, dil=dil, pad=pad, act=act, dw=dw, in_relu=in_relu, image=image, out_dtype=out_dtype)
     gamma = bn.weight if bn is not None else None
     beta = bn.bias if bn is not None else None
-    return _ConvUnit.apply(x0, x1, weight, gamma, beta, bias, res, bn, cfg)
+    return _apply(_ConvUnit, x0, x1, weight, gamma, beta, bias, res, bn, cfg)
 
 
 class _BnAct(torch.autograd.Function):
@@ -384,7 +444,7 @@ class _BnAct(torch.autograd.Function):
 
 
 def bn_act(x, bn, act=ACT_RELU):
-    return _BnAct.apply(x, bn.weight, bn.bias, bn, act)
+    return _apply(_BnAct, x, bn.weight, bn.bias, bn, act)
 
 
 class _Pool(torch.autograd.Function):
@@ -412,7 +472,7 @@ class _Pool(torch.autograd.Function):
 
 
 def pool3x3(x, mode, stride):
-    return _Pool.apply(x, mode, stride)
+    return _apply(_Pool, x, mode, stride)
 
 
 class _ResizeAxpby(torch.autograd.Function):
@@ -460,12 +520,12 @@ def resize(x, size):
     size = (int(size[0]), int(size[1]))
     if tuple(x.shape[2:]) == size:
         return x
-    return _ResizeAxpby.apply(x, None, None, None, size)
+    return _apply(_ResizeAxpby, x, None, None, None, size)
 
 
 def resize_add(x, y, sa=None, sb=None):
     """sa*resize(x -> y's size) + sb*y."""
-    return _ResizeAxpby.apply(x, y, sa, sb, (y.shape[2], y.shape[3]))
+    return _apply(_ResizeAxpby, x, y, sa, sb, (y.shape[2], y.shape[3]))
 
 
 class _ConcatResize(torch.autograd.Function):
@@ -512,7 +572,7 @@ class _ConcatResize(torch.autograd.Function):
 
 
 def concat_resize(tensors, size, relu=False):
-    return _ConcatResize.apply((int(size[0]), int(size[1])), bool(relu), *tensors)
+    return _apply(_ConcatResize, (int(size[0]), int(size[1])), bool(relu), *tensors)
 
 
 class _ChannelTile(torch.autograd.Function):
@@ -536,7 +596,7 @@ class _ChannelTile(torch.autograd.Function):
 
 
 def channel_tile(x, reps, stride=1, scale=1.0):
-    return _ChannelTile.apply(x, reps, stride, scale)
+    return _apply(_ChannelTile, x, reps, stride, scale)
 
 
 class _SpatialMean(torch.autograd.Function):
@@ -581,11 +641,11 @@ class _SpatialBcast(torch.autograd.Function):
 
 
 def spatial_mean(x):
-    return _SpatialMean.apply(x)
+    return _apply(_SpatialMean, x)
 
 
 def spatial_bcast(v, h, w, dtype):
-    return _SpatialBcast.apply(v, h, w, dtype)
+    return _apply(_SpatialBcast, v, h, w, dtype)
 
 
 class _Cast(torch.autograd.Function):
@@ -613,7 +673,7 @@ def as_act(x, dtype=None):
     if x.dtype == dtype:
         return lib.to_nhwc(x)
     x = lib.to_nhwc(x, None if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
-    return _Cast.apply(x, dtype)
+    return _apply(_Cast, x, dtype)
 
 
 # ------------------------------------------------------------------------------------------------------- losses

@@ -1,5 +1,9 @@
 """The few host utilities the engine functions depend on (reference: src/helpers/utils.py)."""
 import copy
+import logging
+import os
+
+logger = logging.getLogger(__name__)
 
 
 class AverageMeter(object):
@@ -23,7 +27,11 @@ def try_except(func):
     def wrapper_func(*args, **kwargs):
         try:
             return func(*args, **kwargs)
-        except RuntimeError:
+        except RuntimeError as e:
+            if os.environ.get("NASB_RAISE"):  # debugging aid: see the failure instead of "reward 0"
+                raise
+            logger.warning(" %s failed and returns 0 (reference convention): %s", getattr(func, "__name__", "call"),
+                           str(e).splitlines()[0] if str(e) else type(e).__name__)
             return 0
 
     wrapper_func.__wrapped__ = func

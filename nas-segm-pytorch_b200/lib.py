@@ -20,6 +20,13 @@ class NasbTensor(C.Structure):
                 ("cstride", C.c_int32), ("dtype", C.c_int32)]
 
 
+class NasbConvUnit(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("bias", C.c_void_p), ("eps", C.c_float), ("c_out", C.c_int32), ("ks", C.c_int32),
+                ("stride", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32), ("dw", C.c_int32), ("in_relu", C.c_int32),
+                ("act", C.c_int32)]
+
+
 _TP = C.POINTER(NasbTensor)
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -82,16 +89,18 @@ _SIG = {
     "nasb_mt_optim_step": [_P, _I, _P, _I, _P, _I, _P, _F, _P],
     "nasb_pack_elems": [_I, _I, _I],
     "nasb_mt_pack_bf16": [_P, _I, _P],
+    "nasb_conv_unit_scratch": [_I, _I],
+    "nasb_conv_unit_infer": [_TP, _P, _TP, _TP, _P, _L, _I, _P],
     "nasb_version": [],
 }
 _RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L,
-        "nasb_pack_elems": _L}
+        "nasb_pack_elems": _L, "nasb_conv_unit_scratch": _L}
 EXPORTS = tuple(sorted(_SIG))
 
 _lib = None
 launches = 0  # kernels launched through the C ABI by this process (bench.py reports the delta over its timed region)
 # kernels (and async memsets) behind one call of each entry point; everything not listed launches exactly one
-_KERNELS_PER_CALL = {"nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
+_KERNELS_PER_CALL = {"nasb_conv_unit_infer": 3, "nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
                      "nasb_spatial_mean": 2, "nasb_spatial_sum": 2}
 _prof = None  # list of (key, bytes, ev0, ev1) while profiling
 
@@ -125,7 +134,7 @@ def require_cuda(t):
 def call(name, *args):
     """Invoke an entry point on torch's current stream; raise RuntimeError on failure."""
     global launches
-    fn = getattr(load(), name)
+    fn = getattr(_lib or load(), name)
     if _prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -134,7 +143,7 @@ def call(name, *args):
         key, nbytes = _describe(name, args)
         _prof.append((key, nbytes, ev0, ev1))
     else:
-        rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = fn(*args, torch.cuda.current_stream().cuda_stream)
     launches += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError("%s failed with code %d%s" % (name, rc, _explain(rc)))
@@ -154,7 +163,7 @@ def try_call(name, *args):
             key, nbytes = _describe(name, args)
             _prof.append((key, nbytes, ev0, ev1))
     else:
-        rc = fn(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = fn(*args, torch.cuda.current_stream().cuda_stream)
     if rc == 10001:
         return False
     if rc != 0:
@@ -173,7 +182,7 @@ def _describe(name, args):
             esz = 2 if t.dtype == BF16 else 4
             nbytes += t.n * t.h * t.w * t.c * esz
             shapes.append("%dx%dx%dx%d%s" % (t.n, t.h, t.w, t.c, "b" if t.dtype == BF16 else "f"))
-    ints = [str(a) for a in args if isinstance(a, int) and not isinstance(a, bool)][:4]
+    ints = [str(a) for a in args if isinstance(a, int) and not isinstance(a, bool) and -65536 < a < 65536][:4]  # not addresses
     return name + "[" + ",".join(shapes) + "|" + ",".join(ints) + "]", nbytes
 
 
@@ -210,7 +219,9 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 def new_act(n, c, h, w, dtype, device):
     """Allocate an activation: logical NCHW view over dense NHWC memory."""
-    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+    t = torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+    t._nasb_d = NasbTensor(t.data_ptr(), n, h, w, c, c, _DT[dtype])
+    return t
 
 
 def zeros_act(n, c, h, w, dtype, device):
@@ -248,7 +259,11 @@ def to_nhwc(t, dtype=None):
 
 
 def desc(t):
-    """NasbTensor for a logical-NCHW torch tensor with NHWC storage."""
+    """NasbTensor for a logical-NCHW torch tensor with NHWC storage (memoised on the tensor object: a tensor's geometry
+    and address never change, and an activation is described once as an output and again by each of its consumers)."""
+    d = getattr(t, "_nasb_d", None)
+    if d is not None:
+        return d
     n, c, h, w = t.shape
     sn, sc, sh, sw = t.stride()
     if w > 1:
@@ -260,6 +275,7 @@ def desc(t):
     else:
         cs = c
     d = NasbTensor(t.data_ptr(), n, h, w, c, cs, _DT[t.dtype])
+    t._nasb_d = d
     return d
 
 
@@ -275,7 +291,8 @@ def ref(d):
 
 
 def ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else None
+    """Device address for a void* argument (ctypes converts a plain int; None is NULL)."""
+    return t.data_ptr() if t is not None else None
 
 
 class _ZeroArena:

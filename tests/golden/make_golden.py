@@ -258,7 +258,9 @@ def gen_segmenter():
     seg = nn.Module()
     seg.module = net
     seg.forward = lambda x: net(x)
-    B, H, W, n_it = 2, 128, 128, 2
+    # batch 4 @192x192: the deepest BatchNorm sees 144 samples per channel.  At 2 x 128x128 (32 samples) the REFERENCE's own
+    # fourth logged loss moves by 0.06 under a 1e-6 relative perturbation of the weights; here it moves by 1e-3.
+    B, H, W, n_it = 4, 192, 192, 2
     loader = ListLoader()
     out = {}
     for i in range(n_it):

@@ -62,9 +62,11 @@ def test_fused_step_matches_torch(kind):
         assert abs(float(norms[0]) - float(na)) <= 1e-5 * float(na)
         if kind != "sgd_nomom":
             assert abs(float(norms[1]) - float(nb)) <= 1e-5 * float(nb)
-        for p, q in zip(pa + pb, qa + qb):
+        for j, (p, q) in enumerate(zip(pa + pb, qa + qb)):
             assert torch.allclose(p, q, rtol=2e-6, atol=2e-7), (it, p.shape, float((p - q).abs().max()))
-            if p.grad is not None:  # clip_grad_norm_ leaves the scaled gradient behind
+            # clip_grad_norm_ leaves the scaled gradient behind (torch's foreach SGD additionally overwrites .grad with
+            # grad + momentum*buf when nesterov is on -- a side effect of its implementation that is not reproduced)
+            if p.grad is not None and not (kind == "sgd_nomom" and j >= len(pa)):
                 assert torch.allclose(p.grad, q.grad, rtol=2e-6, atol=1e-7)
         for a, b in zip(avg_f, avg_t):
             assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
