@@ -153,6 +153,47 @@ int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz, int ks, in
                            float *dweight, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm backward folded into its neighbours (InvertedResidual, layer_factory.py:125-158: 1x1 expand ->
+ * BN -> ReLU6 -> depthwise 3x3 -> ...).  For a unit  z = conv(x); y = act(BN_train(z))  the gradient is
+ *     dz = s*g + A*z + B,   g = dy * act'(y),  per-channel s, A, B from the two reductions  S1 = sum g, S2 = sum g*z.
+ * (1) The kernel that PRODUCES dy -- the depthwise data gradient of the consumer -- gates its output with act'(y) and
+ *     accumulates S1, S2 in its epilogue (NasbGate): the reductions cost one extra read of z instead of a pass over dy and z.
+ * (2) For a pointwise (1x1) unit z = W x, both consumers of dz are linear in (g, z) and z is linear in x, so dz is never
+ *     formed:   dW = diag(s) (g^T x) + diag(A) W (x^T x) + B (sum x)^T        dx = g (diag(s) W) + x (W^T diag(A) W) + B^T W
+ *     nasb_pw_bn_bwd_prepare turns S1, S2 and the small matrices g^T x, x^T x, sum x (nasb_pw_tc_wgrad / nasb_channel_sum)
+ *     into dW, dgamma, dbeta and the two bf16 operands + bias row of the dx GEMMs (nasb_pw_tc_fwd on g, and on x with the
+ *     first result as residual).  BatchNorm's own backward pass over the large tensors disappears.
+ * -------------------------------------------------------------------------------------------------------*/
+typedef struct NasbGate {
+    const NasbTensor *z;         /* pre-BN output of the unit whose input gradient is being produced (geometry of dx) */
+    const float *scale, *shift;  /* that unit's folded BN constants: activation input = z*scale + shift */
+    int32_t act;                 /* its activation (NASB_ACT_*) */
+    int32_t reserved;
+    double *sums;                /* fp64 [2][C], ACCUMULATED: S1 = sum g, S2 = sum g*z over the stored (bf16) g */
+} NasbGate;
+/* dx = gate(dwconv^T(dz)) for stride 1 (tile kernel) and the stride-2 3x3 case; NASB_ERR_UNSUPPORTED otherwise. */
+int nasb_dwconv_dgrad_gated(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
+                            const NasbGate *gate, const NasbTensor *dx, void *stream);
+/* weight [c_out][c_in] fp32; scale/mean/rstd = the unit's BN constants (scale = gamma*rstd); sums = S1,S2; P pixels;
+ * gx = g^T x [c_out][c_in], xx = x^T x [c_in][c_in], sx = sum x [c_in] (fp32).
+ * Outputs: dweight += (see above), dgamma += rstd*(S2 - mean*S1), dbeta += S1 (either may be NULL);
+ * pack_g = bf16 [c_in][Kp(c_out)] operand of dx = g.(diag(s)W); pack_x = bf16 [c_in][Kp(c_in)] operand of x.(W^T diag(A) W);
+ * bias_row = fp32 [c_in] = B^T W.  W enters the z terms as the bf16 values the forward GEMM multiplied with. */
+/* dx = gate(dz . W) on the tensor cores (the pointwise data gradient of the consumer; wpack_t = the transposed operand). */
+int nasb_pw_tc_dgrad_gated(const NasbTensor *dz, const void *wpack_t, int N, const NasbGate *gate, const NasbTensor *dx,
+                           void *stream);
+/* dz pass only, from the reductions a NasbGate epilogue accumulated (any conv type; bf16).  dgamma / dbeta are accumulated.
+ * workspace >= nasb_bn_stats_workspace(C) bytes.  NASB_ERR_UNSUPPORTED for layouts outside the packed bf16 kernels. */
+int nasb_bn_bwd_from_sums(const NasbTensor *dy, const NasbTensor *z, int act, const float *scale, const float *shift,
+                          const float *save_mean, const float *save_rstd, const double *raw_sums, float *dgamma, float *dbeta,
+                          const NasbTensor *dz, void *workspace, void *stream);
+int nasb_pw_bn_bwd_prepare(const float *weight, int c_out, int c_in, const float *scale, const float *mean, const float *rstd,
+                           const double *sums, long long P, const float *gx, const float *xx, const float *sx,
+                           float *dweight, float *dgamma, float *dbeta, void *pack_g, void *pack_x, float *bias_row,
+                           void *scratch, void *stream);
+long long nasb_pw_bn_bwd_scratch(int c_out); /* bytes of `scratch` */
+
+/* ---------------------------------------------------------------------------------------------------------
  * BatchNorm2d pieces (eps 1e-5, momentum 0.1 in the reference; both are arguments here).
  * nasb_bn_fold      : running stats -> per-channel (scale, shift) for the fused eval-mode epilogues.
  * nasb_bn_stats     : training mode: batch mean / biased var of z over (n,h,w); updates running stats

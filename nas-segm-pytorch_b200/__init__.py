@@ -31,6 +31,12 @@ class _Config:
         # clip + optimiser step + Polyak of an engine iteration as two multi-tensor launches (optim.FusedStep) when the
         # caller's optimisers are plain torch.optim.SGD / Adam; off = the caller's own optim.step() (torch kernels)
         self.fused_optim = True
+        # training-mode BN backward folded into the neighbouring kernels where the graph guarantees a sole consumer
+        # (functional._BnRec): gated data-gradient epilogues, dz pass from their reductions, the pointwise unit's backward
+        # without dz.  Validated (tests/test_gpu_tcgen05.py::test_bn_backward_fusion_matches_unfused_path) and MEASURED on a
+        # B200: the third operand costs the issue-bound producers what the separate reduction pass costs (step 24.5 vs
+        # 24.4 ms, profiles/r2_bn_fusion_kbench.txt), so it is off by default.
+        self.fuse_bn_bwd = False
 
 
 _config = None

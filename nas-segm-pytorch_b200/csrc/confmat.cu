@@ -55,6 +55,56 @@ __global__ void __launch_bounds__(256) confmat_labels_kernel(const uint8_t *pred
     }
 }
 
+// fast_cm for C <= 32: one PRIVATE histogram per warp (8 x C*C counters, no contention between warps; the single per-CTA
+// histogram spent its time on shared-memory atomic conflicts: 23 % of the HBM roofline on 16 Mpx of uniform random labels),
+// two 16-byte vectors of each array in flight per thread, and consecutive equal (gt, pred) pairs -- the common case in real
+// label maps -- merged in registers into one atomic.
+constexpr int CM_WARP_MAXC = 32;
+
+__global__ void __launch_bounds__(256) confmat_labels_warp_kernel(const uint8_t *pred, const uint8_t *gt, long long nvec, int C,
+                                                                  long long *cm) {
+    extern __shared__ int hist[];  // [8 warps][C*C]
+    const int CC = C * C;
+    for (int i = threadIdx.x; i < 8 * CC; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    int *mine = hist + (threadIdx.x >> 5) * CC;
+    const uint4 *pv = reinterpret_cast<const uint4 *>(pred), *gv = reinterpret_cast<const uint4 *>(gt);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int run_bin = -1, run_len = 0;
+    auto count = [&](unsigned g, unsigned p) {
+        const int bin = (g < (unsigned)C && p < (unsigned)C) ? (int)(g * C + p) : -1;
+        if (bin == run_bin) {
+            ++run_len;
+        } else {
+            if (run_bin >= 0) atomicAdd(&mine[run_bin], run_len);
+            run_bin = bin;
+            run_len = 1;
+        }
+    };
+    auto vec = [&](const uint4 &a, const uint4 &b) {
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) count((bw[w] >> (8 * k)) & 0xff, (aw[w] >> (8 * k)) & 0xff);
+    };
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nvec; i += 2 * stride) {
+        const uint4 a0 = __ldg(pv + i), b0 = __ldg(gv + i), a1 = __ldg(pv + i + stride), b1 = __ldg(gv + i + stride);
+        vec(a0, b0);
+        vec(a1, b1);
+    }
+    if (i < nvec) vec(__ldg(pv + i), __ldg(gv + i));
+    if (run_bin >= 0) atomicAdd(&mine[run_bin], run_len);
+    __syncthreads();
+    for (int b = threadIdx.x; b < CC; b += blockDim.x) {
+        int v = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += hist[w * CC + b];
+        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(&cm[b]), (unsigned long long)v);
+    }
+}
+
 // one thread = one full-resolution pixel
 template <typename T>
 __global__ void __launch_bounds__(256) confmat_logits_kernel(const T *x, int cs, int N, int h, int w, int C, const uint8_t *gt,
@@ -134,6 +184,17 @@ extern "C" int nasb_confmat_labels(const uint8_t *pred, const uint8_t *gt, long 
                                    void *stream) {
     if (!cm || n_classes <= 0 || n_classes > 256 || n < 0 || (n > 0 && (!pred || !gt))) return NASB_ERR_BAD_ARG;
     if (n == 0) return 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(gt)) & 15) == 0;
+    if (aligned && n_classes <= CM_WARP_MAXC && n >= 16) {  // 16-byte body on per-warp histograms, scalar tail below
+        const long long nvec = n / 16;
+        long long blocks = (nvec + 511) / 512, cap = (long long)NASB_SM_COUNT * 8;  // two vectors per thread and step
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        confmat_labels_warp_kernel<<<(int)blocks, 256, (size_t)8 * n_classes * n_classes * sizeof(int), ST>>>(pred, gt, nvec, n_classes, cm);
+        NASB_CHECK_LAUNCH();
+        pred += nvec * 16, gt += nvec * 16, n -= nvec * 16;
+        if (n == 0) return 0;
+    }
     long long vecs = (n + 15) / 16;
     long long blocks = (vecs + 255) / 256;
     long long cap = (long long)NASB_SM_COUNT * 8;

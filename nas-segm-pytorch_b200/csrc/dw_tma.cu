@@ -58,6 +58,13 @@ struct DwT {
     bf16 *out;
     int out_cs;
     double *stats;                // optional [2][C]: sum / sum of squares of the stored output (training-mode BN fused)
+    // STATS == 2 (data gradient feeding a conv -> BN(train) -> act unit, whose pre-BN output is gz): the stored value is
+    // g = dx gated by lo < gz*g_scale + g_shift < hi (the activation's derivative mask) and stats receives
+    // [sum g, sum g*gz] -- the two reductions of that unit's BatchNorm backward, which then needs no pass of its own.
+    const bf16 *gz;
+    int gz_cs;
+    const float *g_scale, *g_shift;
+    float g_lo, g_hi;
 };
 
 constexpr int DW_P = 4;  // output pixels per strip (a vertical strip: 4 consecutive rows of one column)
@@ -87,7 +94,7 @@ __device__ __forceinline__ void ldw8(uint32_t a, float2 (&w)[4]) {
 // and converted once and feeds all the taps / output rows it belongs to out of registers; the weights of the current
 // kernel column sit in registers.  S == 0 is the general (dilated) path: one load per tap.
 // All arithmetic is packed fp32 (fma.rn.f32x2), accumulation in fp32.
-template <int K, int S, bool STATS>
+template <int K, int S, int STATS>
 __global__ void __launch_bounds__(256, 2) dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const DwT p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
@@ -199,6 +206,13 @@ __global__ void __launch_bounds__(256, 2) dw_tile_kernel(const __grid_constant__
                 }
             }
             bf16 *op = p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.out_cs + c0;
+            uint4 zr[DW_P];
+            if constexpr (STATS == 2) {  // all gate operands of the strip in flight before the first one is needed
+                const bf16 *zp = p.gz + (((size_t)n * p.OH + oy) * p.OW + ox) * p.gz_cs + c0;
+#pragma unroll
+                for (int q = 0; q < DW_P; ++q)
+                    zr[q] = oy + q < p.OH ? __ldg(reinterpret_cast<const uint4 *>(zp + (size_t)q * p.OW * p.gz_cs)) : make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
             for (int q = 0; q < DW_P; ++q) {
                 if (oy + q >= p.OH) break;
@@ -209,6 +223,18 @@ __global__ void __launch_bounds__(256, 2) dw_tile_kernel(const __grid_constant__
                         const float2 sh = p.shift ? *reinterpret_cast<const float2 *>(p.shift + c0 + 2 * j) : make_float2(0.f, 0.f);
                         const float2 e = ffma2(acc[q][j], sc, sh);
                         acc[q][j] = make_float2(apply_act(e.x, p.act), apply_act(e.y, p.act));
+                    }
+                }
+                float2 zv[4];
+                if constexpr (STATS == 2) {
+                    cvt8(zr[q], zv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 gs = *reinterpret_cast<const float2 *>(p.g_scale + c0 + 2 * j);
+                        const float2 gb = *reinterpret_cast<const float2 *>(p.g_shift + c0 + 2 * j);
+                        const float2 pre = ffma2(zv[j], gs, gb);
+                        if (!(pre.x > p.g_lo && pre.x < p.g_hi)) acc[q][j].x = 0.f;
+                        if (!(pre.y > p.g_lo && pre.y < p.g_hi)) acc[q][j].y = 0.f;
                     }
                 }
                 uint4 o;
@@ -224,7 +250,8 @@ __global__ void __launch_bounds__(256, 2) dw_tile_kernel(const __grid_constant__
                     for (int j = 0; j < 4; ++j) {
                         st1[j].x += r[j].x;
                         st1[j].y += r[j].y;
-                        st2[j] = ffma2(r[j], r[j], st2[j]);
+                        if constexpr (STATS == 2) st2[j] = ffma2(r[j], zv[j], st2[j]);
+                        else st2[j] = ffma2(r[j], r[j], st2[j]);
                     }
                 }
             }
@@ -459,9 +486,16 @@ struct DwQ {
     const float *w;
     bf16 *dx;
     int dx_cs;
+    // GATE: see DwT (gated data gradient + the producing unit's BatchNorm-backward reductions)
+    const bf16 *gz;
+    int gz_cs;
+    const float *g_scale, *g_shift;
+    float g_lo, g_hi;
+    double *stats;
 };
 constexpr int DQ_QS = 4;  // quads per strip
 
+template <bool GATE>
 __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_constant__ CUtensorMap map_dz, const DwQ p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
@@ -469,10 +503,16 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_cons
     const size_t tile_stride = (tile_bytes + 127) & ~(size_t)127;
     bf16 *tiles[2] = {reinterpret_cast<bf16 *>(base), reinterpret_cast<bf16 *>(base + tile_stride)};
     float *wsm = reinterpret_cast<float *>(base + 2 * tile_stride);  // [9][CC]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + 9 * p.CC);
+    float *ssm = wsm + 9 * p.CC;                                      // [2][CC] (GATE)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ssm + 2 * p.CC);
     const int tid = threadIdx.x;
     const int chunk = blockIdx.y, c_base = chunk * p.CC;
     const int tiles_img = p.tiles_x * p.tiles_y, total = tiles_img * p.N;
+    if (GATE)
+        for (int i = tid; i < 2 * p.CC; i += blockDim.x) ssm[i] = 0.f;
+    float2 st1[4], st2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st1[j] = st2[j] = make_float2(0.f, 0.f);
     auto origin = [&](int t, int &n, int &iy0, int &ix0) {
         n = t / tiles_img;
         const int r = t - n * tiles_img, ty = r / p.tiles_x;
@@ -504,6 +544,7 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_cons
     const uint32_t wcv = dsmem_u32(wsm) + cv * 32;
     const uint32_t tile_a[2] = {dsmem_u32(tiles[0]) + cv * 16, dsmem_u32(tiles[1]) + cv * 16};
     const size_t orow = (size_t)p.IW * p.dx_cs;
+    const size_t zrow = (size_t)p.IW * p.gz_cs;
 
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
@@ -523,10 +564,21 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_cons
             cvt8(lds16(zp), z0[0]);
             cvt8(lds16(zp + pxb), z0[1]);
             bf16 *op = p.dx + (((size_t)n * p.IH + iyb) * p.IW + ix) * p.dx_cs + c0;
-#pragma unroll
+            const bf16 *gp = GATE ? p.gz + (((size_t)n * p.IH + iyb) * p.IW + ix) * p.gz_cs + c0 : nullptr;
+            constexpr int UNR = GATE ? 2 : DQ_QS;  // the gated epilogue needs some of the registers four unrolled quads would take
+#pragma unroll UNR
             for (int q = 0; q < DQ_QS; ++q) {
                 const int iy = iyb + 2 * q;
                 if (iy >= p.IH) break;
+                uint4 zq[4];
+                if (GATE) {  // the quad's gate operands: in flight while the taps are accumulated
+                    const bf16 *g0 = gp + (size_t)(2 * q) * zrow;
+                    const bool y1ok = iy + 1 < p.IH;
+                    zq[0] = __ldg(reinterpret_cast<const uint4 *>(g0));
+                    zq[1] = x1ok ? __ldg(reinterpret_cast<const uint4 *>(g0 + p.gz_cs)) : make_uint4(0, 0, 0, 0);
+                    zq[2] = y1ok ? __ldg(reinterpret_cast<const uint4 *>(g0 + zrow)) : make_uint4(0, 0, 0, 0);
+                    zq[3] = (y1ok && x1ok) ? __ldg(reinterpret_cast<const uint4 *>(g0 + zrow + p.gz_cs)) : make_uint4(0, 0, 0, 0);
+                }
                 cvt8(lds16(zp + (uint32_t)(q + 1) * rowb), z1[0]);
                 cvt8(lds16(zp + (uint32_t)(q + 1) * rowb + pxb), z1[1]);
                 float2 w[4], o00[4], o01[4], o10[4], o11[4];
@@ -558,16 +610,38 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_cons
                 ldw8(wcv + 8 * tapb, w);  // w22
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o11[j] = ffma2(z0[0][j], w[j], o11[j]);
-                auto st = [&](bf16 *dst, const float2 (&o)[4]) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y),
-                                                                 pack_bf16x2(o[2].x, o[2].y), pack_bf16x2(o[3].x, o[3].y));
+                auto st = [&](bf16 *dst, float2 (&o)[4], const uint4 &zraw) {
+                    float2 zv[4];
+                    if (GATE) {
+                        cvt8(zraw, zv);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {  // per-channel constants from L1 (registers are the scarce resource here)
+                            const float2 pre = ffma2(zv[j], *reinterpret_cast<const float2 *>(p.g_scale + c0 + 2 * j),
+                                                     *reinterpret_cast<const float2 *>(p.g_shift + c0 + 2 * j));
+                            if (!(pre.x > p.g_lo && pre.x < p.g_hi)) o[j].x = 0.f;
+                            if (!(pre.y > p.g_lo && pre.y < p.g_hi)) o[j].y = 0.f;
+                        }
+                    }
+                    const uint4 ov = make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y),
+                                                pack_bf16x2(o[2].x, o[2].y), pack_bf16x2(o[3].x, o[3].y));
+                    *reinterpret_cast<uint4 *>(dst) = ov;
+                    if (GATE) {  // reductions over the values as stored (bf16-rounded)
+                        float2 r[4];
+                        cvt8(ov, r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            st1[j].x += r[j].x;
+                            st1[j].y += r[j].y;
+                            st2[j] = ffma2(r[j], zv[j], st2[j]);
+                        }
+                    }
                 };
                 bf16 *r0 = op + (size_t)(2 * q) * orow;
-                st(r0, o00);
-                if (x1ok) st(r0 + p.dx_cs, o01);
+                st(r0, o00, zq[0]);
+                if (x1ok) st(r0 + p.dx_cs, o01, zq[1]);
                 if (iy + 1 < p.IH) {
-                    st(r0 + orow, o10);
-                    if (x1ok) st(r0 + orow + p.dx_cs, o11);
+                    st(r0 + orow, o10, zq[2]);
+                    if (x1ok) st(r0 + orow + p.dx_cs, o11, zq[3]);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -577,6 +651,20 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_cons
             }
         }
         __syncthreads();
+    }
+    if (GATE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&ssm[cv * 8 + 2 * j], st1[j].x);
+            atomicAdd(&ssm[cv * 8 + 2 * j + 1], st1[j].y);
+            atomicAdd(&ssm[p.CC + cv * 8 + 2 * j], st2[j].x);
+            atomicAdd(&ssm[p.CC + cv * 8 + 2 * j + 1], st2[j].y);
+        }
+        __syncthreads();
+        for (int i = tid; i < p.CC; i += blockDim.x) {
+            atomicAdd(&p.stats[c_base + i], (double)ssm[i]);
+            atomicAdd(&p.stats[p.C + c_base + i], (double)ssm[p.CC + i]);
+        }
     }
 }
 
@@ -644,10 +732,19 @@ using namespace nasb;
 
 // Forward (mode 0) or stride-1 data gradient (mode 1: x = dz, out = dx, flipped kernel).  Returns NASB_ERR_UNSUPPORTED for
 // configurations the tile path does not cover (the caller then uses the gather kernels of dwconv.cu).
-extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
-                                const float *out_scale, const float *out_shift, int act, const NasbTensor *out, double *stats,
-                                void *stream) {
+static int dw_dgrad_strided(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad, const NasbTensor *dx,
+                            const NasbGate *gate, void *stream);
+
+static int dw_tile_launch(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
+                          const float *out_scale, const float *out_shift, int act, const NasbTensor *out, double *stats,
+                          const NasbGate *gate, void *stream) {
     if (!x || !out || !weight) return NASB_ERR_BAD_ARG;
+    if (gate) {
+        if (mode != 1 || !gate->z || !gate->sums || !gate->scale || !gate->shift || stats) return NASB_ERR_BAD_ARG;
+        if (gate->z->dtype != NASB_BF16 || gate->z->c != out->c || npix(*gate->z) != npix(*out) || gate->z->h != out->h ||
+            !vec_ok(*gate->z, 8))
+            return NASB_ERR_UNSUPPORTED;
+    }
     if (x->dtype != NASB_BF16 || out->dtype != NASB_BF16 || x->c != out->c || x->n != out->n) return NASB_ERR_UNSUPPORTED;
     if ((ks != 3 && ks != 5) || !vec_ok(*x, 8) || !vec_ok(*out, 8)) return NASB_ERR_UNSUPPORTED;
     if (mode == 1 && stride != 1) return NASB_ERR_UNSUPPORTED;
@@ -687,6 +784,15 @@ extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks
     p.out = (bf16 *)out->ptr;
     p.out_cs = out->cstride;
     p.stats = stats;
+    if (gate) {
+        p.stats = gate->sums;
+        p.gz = (const bf16 *)gate->z->ptr;
+        p.gz_cs = gate->z->cstride;
+        p.g_scale = gate->scale;
+        p.g_shift = gate->shift;
+        p.g_lo = gate->act == NASB_ACT_NONE ? -INFINITY : 0.f;
+        p.g_hi = gate->act == NASB_ACT_RELU6 ? 6.f : INFINITY;
+    }
     CUtensorMap mx;
     if (!make_map4(&mx, x, pl.CC, pl.ITW, pl.ITH)) return NASB_ERR_UNSUPPORTED;
     const size_t tile_b = ((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127;
@@ -696,13 +802,16 @@ extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks
     while (L * CVn > 256 || L > nstrips) L >>= 1;
     const int threads = L * CVn;
     typedef void (*Kern)(const CUtensorMap, const DwT);
-    static const Kern kerns[2][3][2] = {
-        {{dw_tile_kernel<3, 0, false>, dw_tile_kernel<3, 0, true>}, {dw_tile_kernel<3, 1, false>, dw_tile_kernel<3, 1, true>},
-         {dw_tile_kernel<3, 2, false>, dw_tile_kernel<3, 2, true>}},
-        {{dw_tile_kernel<5, 0, false>, dw_tile_kernel<5, 0, true>}, {dw_tile_kernel<5, 1, false>, dw_tile_kernel<5, 1, true>},
-         {dw_tile_kernel<5, 2, false>, dw_tile_kernel<5, 2, true>}}};
-    static bool cfg[2][3][2] = {};
-    const int ki = ks == 3 ? 0 : 1, si = (dil == 1 && stride <= 2) ? stride : 0, ti = stats ? 1 : 0;
+    // [k][s][stats]: stats 2 = gated data gradient (stride 1 only, so the s = 2 slots repeat the general kernel)
+    static const Kern kerns[2][3][3] = {
+        {{dw_tile_kernel<3, 0, 0>, dw_tile_kernel<3, 0, 1>, dw_tile_kernel<3, 0, 2>},
+         {dw_tile_kernel<3, 1, 0>, dw_tile_kernel<3, 1, 1>, dw_tile_kernel<3, 1, 2>},
+         {dw_tile_kernel<3, 2, 0>, dw_tile_kernel<3, 2, 1>, dw_tile_kernel<3, 0, 2>}},
+        {{dw_tile_kernel<5, 0, 0>, dw_tile_kernel<5, 0, 1>, dw_tile_kernel<5, 0, 2>},
+         {dw_tile_kernel<5, 1, 0>, dw_tile_kernel<5, 1, 1>, dw_tile_kernel<5, 1, 2>},
+         {dw_tile_kernel<5, 2, 0>, dw_tile_kernel<5, 2, 1>, dw_tile_kernel<5, 0, 2>}}};
+    static bool cfg[2][3][3] = {};
+    const int ki = ks == 3 ? 0 : 1, si = (dil == 1 && stride <= 2) ? stride : 0, ti = gate ? 2 : (stats ? 1 : 0);
     Kern kern = kerns[ki][si][ti];
     if (!cfg[ki][si][ti]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
@@ -784,10 +893,36 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     return 0;
 }
 
+extern "C" int nasb_dwconv_tile(const NasbTensor *x, const float *weight, int ks, int stride, int dil, int pad, int mode,
+                                const float *out_scale, const float *out_shift, int act, const NasbTensor *out, double *stats,
+                                void *stream) {
+    return dw_tile_launch(x, weight, ks, stride, dil, pad, mode, out_scale, out_shift, act, out, stats, nullptr, stream);
+}
+
+// Stride-1 data gradient whose epilogue gates dx with the activation mask of the unit that produced the conv input and
+// accumulates that unit's two BatchNorm-backward reductions (see DwT / NasbGate).
+extern "C" int nasb_dwconv_dgrad_gated(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
+                                       const NasbGate *gate, const NasbTensor *dx, void *stream) {
+    if (!gate) return NASB_ERR_BAD_ARG;
+    if (stride == 1) return dw_tile_launch(dz, weight, ks, 1, dil, pad, 1, nullptr, nullptr, NASB_ACT_NONE, dx, nullptr, gate, stream);
+    return dw_dgrad_strided(dz, weight, ks, stride, dil, pad, dx, gate, stream);
+}
+
 // Strided (stride >= 2) data gradient on tiles; stride-1 goes through nasb_dwconv_tile(mode 1).
 extern "C" int nasb_dwconv_dgrad_strided_tile(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad,
                                               const NasbTensor *dx, void *stream) {
+    return dw_dgrad_strided(dz, weight, ks, stride, dil, pad, dx, nullptr, stream);
+}
+
+static int dw_dgrad_strided(const NasbTensor *dz, const float *weight, int ks, int stride, int dil, int pad, const NasbTensor *dx,
+                            const NasbGate *gate, void *stream) {
     if (!dz || !dx || !weight) return NASB_ERR_BAD_ARG;
+    if (gate) {
+        if (!gate->z || !gate->sums || !gate->scale || !gate->shift) return NASB_ERR_BAD_ARG;
+        if (gate->z->dtype != NASB_BF16 || gate->z->c != dx->c || npix(*gate->z) != npix(*dx) || gate->z->h != dx->h ||
+            !vec_ok(*gate->z, 8))
+            return NASB_ERR_UNSUPPORTED;
+    }
     if (dz->dtype != NASB_BF16 || dx->dtype != NASB_BF16 || dz->c != dx->c || dz->n != dx->n) return NASB_ERR_UNSUPPORTED;
     if ((ks != 3 && ks != 5) || stride < 2 || !vec_ok(*dz, 8) || !vec_ok(*dx, 8) || dx->n > 65535) return NASB_ERR_UNSUPPORTED;
     int cc = pick_cc(dx->c);
@@ -815,28 +950,40 @@ extern "C" int nasb_dwconv_dgrad_strided_tile(const NasbTensor *dz, const float 
         CUtensorMap mq;
         if (!make_map4(&mq, dz, cc, q.ZTW, q.ZTH)) return NASB_ERR_UNSUPPORTED;
         const size_t tile_b = ((size_t)q.ZTH * q.ZTW * cc * 2 + 127) & ~(size_t)127;
-        const size_t smem = 2 * tile_b + (size_t)9 * cc * 4 + 16 + 256;
+        const size_t smem = 2 * tile_b + (size_t)9 * cc * 4 + (size_t)2 * cc * 4 + 16 + 256;
         const int CVn = cc / 8, nstrips = (q.TH / (2 * DQ_QS)) * (q.TW / 2);
         int L = 64;
         while (L * CVn > 256 || L > nstrips) L >>= 1;
         const int threads = L * CVn;
-        static bool cfgq = false;
-        if (!cfgq) {
-            if (cudaFuncSetAttribute(dw_dgrad_s2k3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        if (gate) {
+            q.gz = (const bf16 *)gate->z->ptr;
+            q.gz_cs = gate->z->cstride;
+            q.g_scale = gate->scale;
+            q.g_shift = gate->shift;
+            q.g_lo = gate->act == NASB_ACT_NONE ? -INFINITY : 0.f;
+            q.g_hi = gate->act == NASB_ACT_RELU6 ? 6.f : INFINITY;
+            q.stats = gate->sums;
+        }
+        typedef void (*KernQ)(const CUtensorMap, const DwQ);
+        KernQ kq = gate ? (KernQ)dw_dgrad_s2k3_kernel<true> : (KernQ)dw_dgrad_s2k3_kernel<false>;
+        static bool cfgq[2] = {false, false};
+        if (!cfgq[gate ? 1 : 0]) {
+            if (cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
                 return NASB_ERR_UNSUPPORTED;
-            cfgq = true;
+            cfgq[gate ? 1 : 0] = true;
         }
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dw_dgrad_s2k3_kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kq, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         if (per_sm > 6) per_sm = 6;
         long long total = (long long)q.tiles_x * q.tiles_y * dx->n;
         long long gx = (long long)NASB_SM_COUNT * per_sm / q.nchunks;
         if (gx < 1) gx = 1;
         if (gx > total) gx = total;
-        dw_dgrad_s2k3_kernel<<<dim3((unsigned)gx, q.nchunks), threads, smem, (cudaStream_t)stream>>>(mq, q);
+        kq<<<dim3((unsigned)gx, q.nchunks), threads, smem, (cudaStream_t)stream>>>(mq, q);
         NASB_CHECK_LAUNCH();
         return 0;
     }
+    if (gate) return NASB_ERR_UNSUPPORTED;  // the general strided kernel has no gated epilogue
     const int TH = 16, TW = 32;
     DwG p{};
     // dz rows touched by TH dx rows: ((TH-1) + (ks-1)*dil) / stride + 2

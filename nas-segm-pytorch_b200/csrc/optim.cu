@@ -323,3 +323,96 @@ extern "C" int nasb_mt_pack_bf16(const NasbPackJob *jobs, int n, void *stream) {
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ pointwise unit: BN backward without dz
+// See include/nasb200.h (NasbGate / nasb_pw_bn_bwd_prepare).  All matrices here are tiny (c_out <= 1024, c_in <= 64):
+// block b handles output channel rows; the c_in x c_in matrix M = W^T diag(A) W is reduced over c_out by block 0's threads.
+namespace nasb {
+
+struct PwBnP {
+    const float *w;
+    int co, ci;
+    const float *scale, *mean, *rstd;
+    const double *sums;
+    double invP;
+    const float *gx, *xx, *sx;
+    float *dw, *dgamma, *dbeta;
+    bf16 *pack_g, *pack_x;
+    float *bias_row;
+    float *coef;  // scratch [3][co]: s, A, B
+};
+
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// per output channel: the constants of dz = s*g + A*z + B, and the BatchNorm parameter gradients
+__global__ void __launch_bounds__(256) pw_bn_coef_kernel(const PwBnP p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.co) return;
+    const double S1 = p.sums[c], S2 = p.sums[p.co + c];
+    const double mu = (double)p.mean[c], rs = (double)p.rstd[c];
+    const double s2c = rs * (S2 - mu * S1);  // sum g*xhat
+    const float k1 = (float)(S1 * p.invP), k2 = (float)(s2c * p.invP);
+    const float s = p.scale[c];
+    p.coef[c] = s;
+    p.coef[p.co + c] = -s * k2 * (float)rs;
+    p.coef[2 * p.co + c] = s * (k2 * (float)rs * (float)mu - k1);
+    if (p.dgamma) p.dgamma[c] += (float)s2c;
+    if (p.dbeta) p.dbeta[c] += (float)S1;
+}
+
+// blockIdx.y == 0: rows -- dW[c][i] += s gx + A (W_b xx)[c][i] + B sx[i]; pack_g[i][c] = bf16(s W[c][i])
+// blockIdx.y == 1: M[o][i] = sum_c W_b[c][i] A[c] W_b[c][o] -> pack_x[o][Kp(ci)]; bias_row[o] = sum_c B[c] W_b[c][o]
+__global__ void __launch_bounds__(256) pw_bn_mats_kernel(const PwBnP p) {
+    const int Kp = (p.co + 7) / 8 * 8, Kpi = (p.ci + 7) / 8 * 8;
+    const float *cs = p.coef, *cA = p.coef + p.co, *cB = p.coef + 2 * p.co;
+    if (blockIdx.y == 0) {
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.co * p.ci; idx += gridDim.x * blockDim.x) {
+            const int c = idx / p.ci, i = idx - c * p.ci;
+            float wg = 0.f;  // (W_b . xx)[c][i]
+            for (int k = 0; k < p.ci; ++k) wg = fmaf(bf16r(p.w[(size_t)c * p.ci + k]), p.xx[(size_t)k * p.ci + i], wg);
+            p.dw[idx] += cs[c] * p.gx[idx] + cA[c] * wg + cB[c] * p.sx[i];
+            p.pack_g[(size_t)i * Kp + c] = __float2bfloat16_rn(cs[c] * p.w[idx]);
+        }
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.ci * (Kp - p.co); idx += gridDim.x * blockDim.x) {
+            const int i = idx / (Kp - p.co), k = p.co + idx % (Kp - p.co);  // zero the K padding of pack_g
+            p.pack_g[(size_t)i * Kp + k] = __float2bfloat16_rn(0.f);
+        }
+    } else {
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.ci * Kpi; idx += gridDim.x * blockDim.x) {
+            const int o = idx / Kpi, i = idx - o * Kpi;
+            float m = 0.f, br = 0.f;
+            if (i < p.ci) {
+                for (int c = 0; c < p.co; ++c) {
+                    const float wo = bf16r(p.w[(size_t)c * p.ci + o]);
+                    m = fmaf(bf16r(p.w[(size_t)c * p.ci + i]) * cA[c], wo, m);
+                    if (i == 0) br = fmaf(cB[c], wo, br);
+                }
+            }
+            p.pack_x[idx] = __float2bfloat16_rn(m);
+            if (i == 0) p.bias_row[o] = br;
+        }
+    }
+}
+
+}  // namespace nasb
+
+extern "C" long long nasb_pw_bn_bwd_scratch(int c_out) { return c_out > 0 ? 3LL * c_out * (long long)sizeof(float) : -1; }
+
+extern "C" int nasb_pw_bn_bwd_prepare(const float *weight, int c_out, int c_in, const float *scale, const float *mean,
+                                      const float *rstd, const double *sums, long long P, const float *gx, const float *xx,
+                                      const float *sx, float *dweight, float *dgamma, float *dbeta, void *pack_g, void *pack_x,
+                                      float *bias_row, void *scratch, void *stream) {
+    if (!weight || !scale || !mean || !rstd || !sums || !gx || !xx || !sx || !dweight || !pack_g || !pack_x || !bias_row ||
+        !scratch || c_out <= 0 || c_in <= 0 || P <= 0)
+        return NASB_ERR_BAD_ARG;
+    if (c_in > 256 || c_out > 4096) return NASB_ERR_UNSUPPORTED;
+    PwBnP p{weight, c_out, c_in, scale, mean, rstd, sums, 1.0 / (double)P, gx, xx, sx, dweight, dgamma, dbeta,
+            (bf16 *)pack_g, (bf16 *)pack_x, bias_row, (float *)scratch};
+    pw_bn_coef_kernel<<<cdiv(c_out, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    NASB_CHECK_LAUNCH();
+    const int Kpi = (c_in + 7) / 8 * 8;
+    long long work = (long long)c_out * c_in > (long long)c_in * Kpi ? (long long)c_out * c_in : (long long)c_in * Kpi;
+    pw_bn_mats_kernel<<<dim3(cdiv(work, 256), 2), 256, 0, (cudaStream_t)stream>>>(p);
+    NASB_CHECK_LAUNCH();
+    return 0;
+}

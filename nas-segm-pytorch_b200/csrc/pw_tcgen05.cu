@@ -29,6 +29,11 @@ struct PwParams {
     const bf16 *res;
     int res_cs;
     double *stats;  // [2][N] (sum, sumsq) or null
+    // gate != 0 (data gradient feeding a conv -> BN(train) -> act unit whose pre-BN output is read through map_z): the
+    // stored value is g = out gated by g_lo < z*g_scale + g_shift < g_hi and stats receives [sum g, sum g*z] (NasbGate)
+    int gate;
+    const float *g_scale, *g_shift;
+    float g_lo, g_hi;
 };
 
 constexpr int TC_THREADS = 128;
@@ -41,20 +46,23 @@ constexpr int TILE_N = 64;
 // overlap; the A tile of a pixel block is re-read by the nnb CTAs that share it out of L2.
 __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                            const __grid_constant__ CUtensorMap map_b,
-                                                           const __grid_constant__ CUtensorMap map_o, const PwParams p) {
+                                                           const __grid_constant__ CUtensorMap map_o,
+                                                           const __grid_constant__ CUtensorMap map_z, const PwParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                    // nkb x [64 x 128 B]
     uint8_t *sA = sB + (size_t)p.nkb * TILE_N * 128;       // nkb x [128 x 128 B]
     uint8_t *sO = sA + (size_t)p.nkb * TILE_M * 128;       // [128 x 128 B]
-    float *s_scale = (float *)(sO + (size_t)TILE_M * 128);
+    uint8_t *sZ = sO + (size_t)TILE_M * 128;               // [128 x 128 B] gate operand (only when p.gate)
+    float *s_scale = (float *)(sZ + (p.gate ? (size_t)TILE_M * 128 : 0));
     float *s_shift = s_scale + TILE_N;
     float *s_sum = s_shift + TILE_N;
     float *s_sq = s_sum + TILE_N;
     uint64_t *bar_b = (uint64_t *)(s_sq + TILE_N);
     uint64_t *bar_a = bar_b + 1;
     uint64_t *bar_mma = bar_a + 1;
-    uint32_t *s_tmem = (uint32_t *)(bar_mma + 1);
+    uint64_t *bar_z = bar_mma + 1;
+    uint32_t *s_tmem = (uint32_t *)(bar_z + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.M + TILE_M - 1) / TILE_M;
@@ -68,11 +76,13 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         mbar_init(bar_b, 1);
         mbar_init(bar_a, 1);
         mbar_init(bar_mma, 1);
+        mbar_init(bar_z, 1);
         fence_barrier_init();
     }
     for (int i = tid; i < TILE_N; i += TC_THREADS) {
-        s_scale[i] = (p.scale && i < nblk) ? p.scale[n0 + i] : 1.f;
-        s_shift[i] = (p.shift && i < nblk) ? p.shift[n0 + i] : 0.f;
+        // gated data gradient: the epilogue constants are the GATE's (the accumulator itself goes out unscaled)
+        s_scale[i] = p.gate ? (i < nblk ? p.g_scale[n0 + i] : 0.f) : ((p.scale && i < nblk) ? p.scale[n0 + i] : 1.f);
+        s_shift[i] = p.gate ? (i < nblk ? p.g_shift[n0 + i] : 0.f) : ((p.shift && i < nblk) ? p.shift[n0 + i] : 0.f);
         s_sum[i] = 0.f;
         s_sq[i] = 0.f;
     }
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
     }
     const uint32_t idesc = make_idesc_bf16(npb);
     const int row = warp * 32 + lane;  // TMEM lane == row of the tile owned by this thread
-    const bool affine = p.scale || p.shift || p.act != NASB_ACT_NONE;
+    const bool affine = !p.gate && (p.scale || p.shift || p.act != NASB_ACT_NONE);
     const int st_ch = tid & 7, st_rg = tid >> 3;  // statistics: this thread's 8-channel chunk and first row
     const bool st_on = st_ch * 8 < nblk;
     float2 st1[4], st2[4];
@@ -105,6 +115,10 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         const uint32_t parity = it & 1;
         const int m0 = tile * TILE_M;
         if (tid == 0) {
+            if (p.gate) {  // sZ was released by the __syncthreads that ended the previous tile
+                mbar_expect_tx(bar_z, (uint32_t)(TILE_M * 128));
+                tma_load_2d(sZ, &map_z, bar_z, n0, m0);
+            }
             if (it == 0) mbar_wait(bar_b, 0);
             mbar_wait(bar_a, parity);
             tc_fence_after();
@@ -126,6 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         const long long m = (long long)m0 + row;
         const bool row_ok = m < p.M;
         uint8_t *orow = sO + (size_t)row * 128;
+        if (p.gate) mbar_wait(bar_z, parity);
 #pragma unroll 1
         for (int c0 = 0; c0 < npb; c0 += 16) {
             float v[16];
@@ -133,6 +148,19 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
             if (affine) {  // uniform: raw accumulator goes out untouched for training-mode z and for data gradients
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+            }
+            if (p.gate) {  // activation mask of the unit that produced this GEMM's "input": pre-activation = z*gs + gb
+                const uint8_t *zrow = sZ + (size_t)row * 128;
+                float2 zv[8];
+                cvt8(*reinterpret_cast<const uint4 *>(zrow + ((((c0 >> 3)) ^ (row & 7)) << 4)), *reinterpret_cast<float2(*)[4]>(&zv[0]));
+                cvt8(*reinterpret_cast<const uint4 *>(zrow + ((((c0 >> 3) + 1) ^ (row & 7)) << 4)), *reinterpret_cast<float2(*)[4]>(&zv[4]));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float pa = zv[j].x * s_scale[c0 + 2 * j] + s_shift[c0 + 2 * j];
+                    const float pb = zv[j].y * s_scale[c0 + 2 * j + 1] + s_shift[c0 + 2 * j + 1];
+                    if (!(pa > p.g_lo && pa < p.g_hi)) v[2 * j] = 0.f;
+                    if (!(pb > p.g_lo && pb < p.g_hi)) v[2 * j + 1] = 0.f;
+                }
             }
             if (p.res && row_ok) {
                 const bf16 *rp = p.res + m * p.res_cs + n0 + c0;
@@ -179,13 +207,14 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 #pragma unroll
             for (int k = 0; k < TILE_M / 16; ++k) {
                 const int r = st_rg + 16 * k;
-                float2 q[4];
+                float2 q[4], zq[4];
                 cvt8(*reinterpret_cast<const uint4 *>(sO + (size_t)r * 128 + ((st_ch ^ (r & 7)) << 4)), q);
+                if (p.gate) cvt8(*reinterpret_cast<const uint4 *>(sZ + (size_t)r * 128 + ((st_ch ^ (r & 7)) << 4)), zq);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     st1[j].x += q[j].x;
                     st1[j].y += q[j].y;
-                    st2[j] = ffma2(q[j], q[j], st2[j]);
+                    st2[j] = ffma2(q[j], p.gate ? zq[j] : q[j], st2[j]);
                 }
             }
         }
@@ -572,7 +601,7 @@ extern "C" int nasb_pack_weight_bf16(const float *w, int rows, int cols, int tra
 // Shapes the tensor-core path accepts: bf16 in/out, 8-aligned channels and pitches, C_in / C_out small enough for the
 // whole weight matrix plus one A tile and one output tile to fit in shared memory.
 static size_t pw_smem_bytes(int nkb) {
-    return (size_t)nkb * TILE_N * 128 + (size_t)nkb * TILE_M * 128 + (size_t)TILE_M * 128 + 4 * TILE_N * 4 + 64 + 1024;
+    return (size_t)nkb * TILE_N * 128 + (size_t)nkb * TILE_M * 128 + (size_t)TILE_M * 128 + 4 * TILE_N * 4 + 64 + 1024 + 64;
 }
 
 extern "C" int nasb_pw_tc_supported(int K, int N) {
@@ -581,9 +610,15 @@ extern "C" int nasb_pw_tc_supported(int K, int N) {
     return pw_smem_bytes(nkb) <= 200 * 1024 ? 1 : 0;
 }
 
-extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
-                              const NasbTensor *res, const NasbTensor *out, double *stats, void *stream) {
+static int pw_tc_launch(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
+                        const NasbTensor *res, const NasbTensor *out, double *stats, const NasbGate *gate, void *stream) {
     if (!x || !out || !wpack) return NASB_ERR_BAD_ARG;
+    if (gate) {
+        if (!gate->z || !gate->sums || !gate->scale || !gate->shift || stats || res || scale || shift || act != NASB_ACT_NONE)
+            return NASB_ERR_BAD_ARG;
+        if (gate->z->dtype != NASB_BF16 || gate->z->c != N || npix(*gate->z) != npix(*out) || !vec_ok(*gate->z, 8))
+            return NASB_ERR_UNSUPPORTED;
+    }
     if (x->dtype != NASB_BF16 || out->dtype != NASB_BF16 || out->c != N || npix(*x) != npix(*out)) return NASB_ERR_BAD_ARG;
     if (!vec_ok(*x, 8) || !vec_ok(*out, 8) || !nasb_pw_tc_supported(x->c, N)) return NASB_ERR_UNSUPPORTED;
     if (res && (res->dtype != NASB_BF16 || res->c != N || npix(*res) != npix(*out) || !vec_ok(*res, 8))) return NASB_ERR_BAD_ARG;
@@ -602,18 +637,29 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     p.res = res ? (const bf16 *)res->ptr : nullptr;
     p.res_cs = res ? res->cstride : 0;
     p.stats = stats;
+    if (gate) {
+        p.gate = 1;
+        p.stats = gate->sums;
+        p.g_scale = gate->scale;
+        p.g_shift = gate->shift;
+        p.g_lo = gate->act == NASB_ACT_NONE ? -INFINITY : 0.f;
+        p.g_hi = gate->act == NASB_ACT_RELU6 ? 6.f : INFINITY;
+    }
     int Kp = (p.K + 7) / 8 * 8;
-    CUtensorMap ma, mb, mo;
+    CUtensorMap ma, mb, mo, mz;
     if (!tc_make_map2(&ma, x->ptr, (uint64_t)p.K, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)N, (uint64_t)Kp, TILE_N)) return NASB_ERR_UNSUPPORTED;
     if (!tc_make_map2(&mo, out->ptr, (uint64_t)N, (uint64_t)M, (uint64_t)out->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    mz = mo;
+    if (gate && !tc_make_map2(&mz, gate->z->ptr, (uint64_t)N, (uint64_t)M, (uint64_t)gate->z->cstride, TILE_M))
+        return NASB_ERR_UNSUPPORTED;
     // Schedule choice (measured on a B200, profiles/r2_switches_kbench.txt): the warp-specialised kernel wins 5-30 % up to
     // 2^20 pixels (8 x 256 x 512) and loses 5-20 % on the 512 x 1024 maps, where its second output tile costs occupancy.
     // NASB_PW_WS=0 / 1 forces one schedule (kernel comparisons in tools/kbench.py).
     static int ws_mode = -1;
     if (ws_mode < 0) ws_mode = getenv("NASB_PW_WS") ? atoi(getenv("NASB_PW_WS")) : 2;
     int ntiles = (int)((M + TILE_M - 1) / TILE_M);
-    if (ws_mode == 1 || (ws_mode == 2 && M <= (1LL << 20))) {  // warp-specialised schedule (see pw_tc_ws_kernel)
+    if (!gate && (ws_mode == 1 || (ws_mode == 2 && M <= (1LL << 20)))) {  // warp-specialised schedule (see pw_tc_ws_kernel)
         const size_t smem_ws = (size_t)p.nkb * TILE_N * 128 + (size_t)WS_SA * p.nkb * TILE_M * 128 + (size_t)2 * TILE_M * 128 +
                                4 * TILE_N * 4 + 128 + 1024;
         if (smem_ws <= 200 * 1024) {
@@ -634,7 +680,8 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
             return 0;
         }
     }
-    size_t smem = pw_smem_bytes(p.nkb);
+    size_t smem = pw_smem_bytes(p.nkb) + (gate ? (size_t)TILE_M * 128 : 0);
+    if (smem > 200 * 1024) return NASB_ERR_UNSUPPORTED;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
@@ -647,9 +694,22 @@ extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, con
     long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;  // a multiple of the N blocks
     if (grid < p.nnb) grid = p.nnb;
     if (grid > (long long)ntiles * p.nnb) grid = (long long)ntiles * p.nnb;
-    pw_tc_kernel<<<(int)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, p);
+    pw_tc_kernel<<<(int)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, mz, p);
     NASB_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int nasb_pw_tc_fwd(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
+                              const NasbTensor *res, const NasbTensor *out, double *stats, void *stream) {
+    return pw_tc_launch(x, wpack, N, scale, shift, act, res, out, stats, nullptr, stream);
+}
+
+// Data gradient dx = dz . W (transposed pack) whose epilogue gates dx with the activation mask of the unit that produced the
+// convolution's input and accumulates that unit's BatchNorm-backward reductions (NasbGate).
+extern "C" int nasb_pw_tc_dgrad_gated(const NasbTensor *dz, const void *wpack_t, int N, const NasbGate *gate, const NasbTensor *dx,
+                                      void *stream) {
+    if (!gate) return NASB_ERR_BAD_ARG;
+    return pw_tc_launch(dz, wpack_t, N, nullptr, nullptr, NASB_ACT_NONE, nullptr, dx, nullptr, gate, stream);
 }
 
 extern "C" int nasb_pw_tc_wgrad_supported(int Co, int Ci) {

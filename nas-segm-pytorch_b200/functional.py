@@ -143,6 +143,47 @@ def _pack_weight(weight, transpose):
     return wp
 
 
+class _BnRec:
+    """Link between a conv -> BN(train) -> act unit and the SOLE consumer of its output (set by InvertedResidual / SepConv,
+    where the graph guarantees it): the consumer's data-gradient kernel gates its result with this unit's activation mask
+    and accumulates this unit's two BatchNorm-backward reductions in its epilogue (NasbGate), so that the unit's own backward
+    needs no pass over (dy, z) for them -- and, for a pointwise unit, no dz at all (include/nasb200.h)."""
+    __slots__ = ("z", "ss", "act", "g", "sums")
+
+    def __init__(self, z, ss, act):
+        self.z, self.ss, self.act, self.g, self.sums = z, ss, act, None, None
+
+
+def _pw_unit_bwd_nodz(g, x0, weight, has_g, has_b, ss, sv, sums, need_dx):
+    """Backward of a pointwise conv -> BN(train) -> act unit from the gated gradient g and the reductions S1, S2 its consumer
+    left behind: dW, dgamma, dbeta and dx without forming dz (nasb_pw_bn_bwd_prepare)."""
+    dev = g.device
+    cout, cin = weight.shape[0], weight.shape[1]
+    n, _, h, w = g.shape
+    gx = lib.zeros((cout, cin), torch.float32, dev)
+    call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(desc(g)), ptr(gx))
+    xx = lib.zeros((cin, cin), torch.float32, dev)
+    call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(desc(x0)), ptr(xx))
+    sx = lib.zeros(cin, torch.float32, dev)
+    call("nasb_channel_sum", ref(desc(x0)), ptr(sx), None)
+    dweight = lib.zeros(tuple(weight.shape), torch.float32, dev)
+    dgamma = lib.zeros(cout, torch.float32, dev) if has_g else None
+    dbeta = lib.zeros(cout, torch.float32, dev) if has_b else None
+    pack_g = torch.empty(cin * ((cout + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+    pack_x = torch.empty(cin * ((cin + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+    bias_row = torch.empty(cin + 3 * cout, dtype=torch.float32, device=dev)  # + the kernel's [3][cout] coefficient scratch
+    call("nasb_pw_bn_bwd_prepare", ptr(weight), cout, cin, ptr(ss[0]), ptr(sv[0]), ptr(sv[1]), ptr(sums), C.c_longlong(n * h * w),
+         ptr(gx), ptr(xx), ptr(sx), ptr(dweight), ptr(dgamma), ptr(dbeta), ptr(pack_g), ptr(pack_x), ptr(bias_row),
+         bias_row.data_ptr() + 4 * cin)
+    dx = None
+    if need_dx:
+        tmp = lib.new_act(*x0.shape, x0.dtype, dev)   # x.(W^T diag(A) W) + B^T W : the z terms of dz, through x
+        call("nasb_pw_tc_fwd", ref(desc(x0)), ptr(pack_x), cin, None, ptr(bias_row), ACT_NONE, None, ref(desc(tmp)), None)
+        dx = lib.new_act(*x0.shape, x0.dtype, dev)
+        call("nasb_pw_tc_fwd", ref(desc(g)), ptr(pack_g), cin, None, None, ACT_NONE, ref(desc(tmp)), ref(desc(dx)), None)
+    return dx, dweight, dgamma, dbeta
+
+
 class _ConvUnit(torch.autograd.Function):
     """conv (dense 1x1/3x3 or depthwise kxk) [+ BatchNorm2d train/eval] [+ bias] [+ ReLU/ReLU6] [+ residual].
 
@@ -263,10 +304,16 @@ class _ConvUnit(torch.autograd.Function):
         ctx.cfg, ctx.bn_mode = cfg, (0 if bn is None else (2 if training else 1))
         ctx.has = (x1 is not None, gamma is not None, beta is not None, bias is not None, res is not None)
         ctx.save_for_backward(x0, x1, weight, gamma, beta, y, z, ss, sv)
+        # BN-backward fusion links (see _BnRec): what this unit's input producer left on x0, what this unit leaves on y
+        fuse = _cfg().fuse_bn_bwd and out_dtype == torch.bfloat16
+        ctx.prod = getattr(x0, "_nasb_rec", None) if (fuse and cfg.get("sole") and any(ctx.needs_input_grad)) else None
+        ctx.rec = None
         if late_res and not res_done:
             out = lib.new_act(n, cout, oh, ow, out_dtype, dev)
             call("nasb_resize_axpby", ref(desc(y)), None, ref(desc(res)), None, 0, ref(desc(out)))
             return out
+        if fuse and training and res is None and any(ctx.needs_input_grad):
+            ctx.rec = y._nasb_rec = _BnRec(z, ss, act)
         return y
 
     @staticmethod
@@ -280,17 +327,34 @@ class _ConvUnit(torch.autograd.Function):
         cout = weight.shape[0]
         dy = _grad_in(dy, y.dtype)
         need = ctx.needs_input_grad
+        rec, gsums = ctx.rec, None
+        if rec is not None and rec.g is not None:
+            g, sums = rec.g, rec.sums
+            rec.g = rec.sums = rec.z = None  # one-shot; drop the references
+            # the consumer's gated gradient IS the incoming gradient (nothing else was accumulated into it)
+            if g.data_ptr() == dy.data_ptr() and tuple(g.shape) == tuple(dy.shape) and ctx.bn_mode == 2:
+                cin = x0.shape[1]
+                if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not in_relu and not image and not has_bias
+                        and not has_res and not ctx.stem_tc and 2 * cin <= cout and cin <= 64 and _tc_wgrad_ok(x0, dy, cout)
+                        and lib.load().nasb_pw_tc_wgrad_supported(int(cin), int(cin))
+                        and _tc_ok(dy, cout, cin, x0.dtype) and _tc_ok(x0, cin, cin, x0.dtype)):
+                    # pointwise unit with a narrow input (MobileNet-v2 expansion): no dz at all
+                    dx0, dweight, dgamma, dbeta = _pw_unit_bwd_nodz(dy, x0, weight, has_g, has_b, ss, sv, sums, need[0])
+                    return dx0, None, dweight if need[2] else None, dgamma, dbeta, None, None, None, None
+                gsums = sums  # any other unit: the reductions exist, only the dz pass remains
         dgamma = lib.zeros(cout, torch.float32, dev) if has_g else None
         dbeta = lib.zeros(cout, torch.float32, dev) if has_b else None
         if ctx.bn_mode or act != ACT_NONE:
             dz = lib.new_act(*y.shape, y.dtype, dev)
-            # training: the mask is recomputed from z, y is neither read nor passed
-            call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)) if z is None else None, ref(desc(z)) if z is not None else None,
-                 act, ptr(gamma),
-                 ptr(beta), ptr(ss[0]) if ss is not None else None, ptr(ss[1]) if ss is not None else None,
-                 ptr(sv[0]) if sv is not None else None,
-                 ptr(sv[1]) if sv is not None else None, 1 if ctx.bn_mode == 2 else 0, ptr(dgamma), ptr(dbeta),
-                 ref(desc(dz)), ptr(_ws(dev, cout)))
+            if not (gsums is not None and try_call(
+                    "nasb_bn_bwd_from_sums", ref(desc(dy)), ref(desc(z)), act, ptr(ss[0]), ptr(ss[1]), ptr(sv[0]), ptr(sv[1]),
+                    ptr(gsums), ptr(dgamma), ptr(dbeta), ref(desc(dz)), ptr(_ws(dev, cout)))):
+                # training: the mask is recomputed from z, y is neither read nor passed
+                call("nasb_bn_act_bwd", ref(desc(dy)), ref(desc(y)) if z is None else None,
+                     ref(desc(z)) if z is not None else None, act, ptr(gamma), ptr(beta),
+                     ptr(ss[0]) if ss is not None else None, ptr(ss[1]) if ss is not None else None,
+                     ptr(sv[0]) if sv is not None else None, ptr(sv[1]) if sv is not None else None,
+                     1 if ctx.bn_mode == 2 else 0, ptr(dgamma), ptr(dbeta), ref(desc(dz)), ptr(_ws(dev, cout)))
         else:
             dz = dy
         dbias = None
@@ -336,11 +400,29 @@ class _ConvUnit(torch.autograd.Function):
                      ACT_NONE, ref(desc(dx0)), None)
             elif (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image
                     and _tc_ok(dz, cout, x0.shape[1], x0.dtype)):
-                call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
-                     ref(desc(dx0)), None)
+                prod, gated = ctx.prod, False
+                if prod is not None and prod.z is not None:  # sole consumer of a BN(train) unit: see the depthwise branch
+                    sums = lib.zeros(2 * x0.shape[1], torch.float64, dev)
+                    gate = lib.NasbGate(C.pointer(desc(prod.z)), ptr(prod.ss[0]), ptr(prod.ss[1]), prod.act, 0, ptr(sums))
+                    gated = try_call("nasb_pw_tc_dgrad_gated", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1],
+                                     C.byref(gate), ref(desc(dx0)))
+                    if gated:
+                        prod.g, prod.sums = dx0, sums
+                if not gated:
+                    call("nasb_pw_tc_fwd", ref(ddz), ptr(_pack_weight(weight, True)), x0.shape[1], None, None, ACT_NONE, None,
+                         ref(desc(dx0)), None)
             elif dw:
                 tiled = False
-                if dz.dtype == torch.bfloat16 and _tiles_on():
+                prod = ctx.prod
+                if prod is not None and prod.z is not None and dz.dtype == torch.bfloat16 and _tiles_on():
+                    # sole consumer of a conv -> BN(train) -> act unit: gate dx with its mask and leave its reductions behind
+                    sums = lib.zeros(2 * x0.shape[1], torch.float64, dev)
+                    gate = lib.NasbGate(C.pointer(desc(prod.z)), ptr(prod.ss[0]), ptr(prod.ss[1]), prod.act, 0, ptr(sums))
+                    tiled = try_call("nasb_dwconv_dgrad_gated", ref(ddz), ptr(weight), ks, stride, dil, pad, C.byref(gate),
+                                     ref(desc(dx0)))
+                    if tiled:
+                        prod.g, prod.sums = dx0, sums
+                if not tiled and dz.dtype == torch.bfloat16 and _tiles_on():
                     if stride == 1:
                         tiled = try_call("nasb_dwconv_tile", ref(ddz), ptr(weight), ks, stride, dil, pad, 1, None, None, ACT_NONE,
                                          ref(desc(dx0)), None)
@@ -389,11 +471,13 @@ def _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, i
 
 
 def conv_unit(x0, weight, bn=None, *, ks, stride=1, dil=1, pad=0, act=ACT_NONE, x1=None, bias=None, res=None, dw=False,
-              in_relu=0, image=False, out_dtype=None):
-    """Fused conv unit.  ``bn`` is the nn.BatchNorm2d module holding gamma/beta/running stats (or None)."""
+              in_relu=0, image=False, out_dtype=None, sole=False):
+    """Fused conv unit.  ``bn`` is the nn.BatchNorm2d module holding gamma/beta/running stats (or None).  ``sole``: the
+    caller guarantees that this unit is the ONLY consumer of x0 (enables the BN-backward fusion link, see _BnRec)."""
     if x1 is None and not image and not torch.is_grad_enabled() and (bn is None or not bn.training):
         return _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, in_relu, out_dtype)
-    cfg = dict(ks=ks, stride=stride, dil=dil, pad=pad, act=act, dw=dw, in_relu=in_relu, image=image, out_dtype=out_dtype)
+    cfg = dict(ks=ks, stride=stride, dil=dil, pad=pad, act=act, dw=dw, in_relu=in_relu, image=image, out_dtype=out_dtype,
+               sole=sole)
     gamma = bn.weight if bn is not None else None
     beta = bn.bias if bn is not None else None
     return _apply(_ConvUnit, x0, x1, weight, gamma, beta, bias, res, bn, cfg)
@@ -426,6 +510,9 @@ class _BnAct(torch.autograd.Function):
         ctx.act, ctx.training = act, training
         ctx.has = (gamma is not None, beta is not None)
         ctx.save_for_backward(x, gamma, beta, y, ss, sv)
+        ctx.rec = None
+        if training and _cfg().fuse_bn_bwd and x.dtype == torch.bfloat16 and ctx.needs_input_grad[0]:
+            ctx.rec = y._nasb_rec = _BnRec(x, ss, act)  # the BN input plays the part of z (see _BnRec)
         return y
 
     @staticmethod
@@ -436,6 +523,14 @@ class _BnAct(torch.autograd.Function):
         dgamma = lib.zeros(c, torch.float32, dev) if ctx.has[0] else None
         dbeta = lib.zeros(c, torch.float32, dev) if ctx.has[1] else None
         dx = lib.new_act(*y.shape, y.dtype, dev)
+        rec = ctx.rec
+        if rec is not None and rec.g is not None:
+            g, sums = rec.g, rec.sums
+            rec.g = rec.sums = rec.z = None
+            if g.data_ptr() == dy.data_ptr() and tuple(g.shape) == tuple(dy.shape) and try_call(
+                    "nasb_bn_bwd_from_sums", ref(desc(dy)), ref(desc(x)), ctx.act, ptr(ss[0]), ptr(ss[1]), ptr(sv[0]), ptr(sv[1]),
+                    ptr(sums), ptr(dgamma), ptr(dbeta), ref(desc(dx)), ptr(_ws(dev, c))):
+                return dx, dgamma, dbeta, None, None
         call("nasb_bn_act_bwd", ref(desc(dy)), None if ctx.training else ref(desc(y)), ref(desc(x)) if ctx.training else None,
              ctx.act, ptr(gamma),
              ptr(beta), ptr(ss[0]), ptr(ss[1]), ptr(sv[0]) if sv is not None else None, ptr(sv[1]) if sv is not None else None,

@@ -20,6 +20,11 @@ class NasbTensor(C.Structure):
                 ("cstride", C.c_int32), ("dtype", C.c_int32)]
 
 
+class NasbGate(C.Structure):
+    _fields_ = [("z", C.POINTER(NasbTensor)), ("scale", C.c_void_p), ("shift", C.c_void_p), ("act", C.c_int32),
+                ("reserved", C.c_int32), ("sums", C.c_void_p)]
+
+
 class NasbConvUnit(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("bias", C.c_void_p), ("eps", C.c_float), ("c_out", C.c_int32), ("ks", C.c_int32),
@@ -55,6 +60,11 @@ _SIG = {
     "nasb_dwconv_tile": [_TP, _P, _I, _I, _I, _I, _I, _P, _P, _I, _TP, _P, _P],
     "nasb_dwconv_dgrad_strided_tile": [_TP, _P, _I, _I, _I, _I, _TP, _P],
     "nasb_dwconv_wgrad_tile": [_TP, _TP, _I, _I, _I, _I, _P, _P],
+    "nasb_dwconv_dgrad_gated": [_TP, _P, _I, _I, _I, _I, _P, _TP, _P],
+    "nasb_pw_tc_dgrad_gated": [_TP, _P, _I, _P, _TP, _P],
+    "nasb_bn_bwd_from_sums": [_TP, _TP, _I, _P, _P, _P, _P, _P, _P, _P, _TP, _P, _P],
+    "nasb_pw_bn_bwd_prepare": [_P, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "nasb_pw_bn_bwd_scratch": [_I],
     "nasb_bn_fold": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "nasb_bn_stats_workspace": [_I],
     "nasb_bn_stats": [_TP, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -94,13 +104,13 @@ _SIG = {
     "nasb_version": [],
 }
 _RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L,
-        "nasb_pack_elems": _L, "nasb_conv_unit_scratch": _L}
+        "nasb_pack_elems": _L, "nasb_conv_unit_scratch": _L, "nasb_pw_bn_bwd_scratch": _L}
 EXPORTS = tuple(sorted(_SIG))
 
 _lib = None
 launches = 0  # kernels launched through the C ABI by this process (bench.py reports the delta over its timed region)
 # kernels (and async memsets) behind one call of each entry point; everything not listed launches exactly one
-_KERNELS_PER_CALL = {"nasb_conv_unit_infer": 3, "nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
+_KERNELS_PER_CALL = {"nasb_bn_bwd_from_sums": 2, "nasb_pw_bn_bwd_prepare": 2, "nasb_conv_unit_infer": 3, "nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
                      "nasb_spatial_mean": 2, "nasb_spatial_sum": 2}
 _prof = None  # list of (key, bytes, ev0, ev1) while profiling
 

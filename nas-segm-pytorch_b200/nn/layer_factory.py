@@ -101,8 +101,9 @@ class InvertedResidual(nn.Module):
         x = _entry(x)
         c = self.conv
         y = Fn.conv_unit(x, c[0].weight, c[1], ks=1, act=ACT_RELU6)
-        y = Fn.conv_unit(y, c[3].weight, c[4], ks=3, stride=self.stride, pad=1, act=ACT_RELU6, dw=True)
-        return Fn.conv_unit(y, c[6].weight, c[7], ks=1, act=ACT_NONE, res=x if self.use_res_connect else None)
+        # `sole`: the expansion feeds the depthwise convolution only, which feeds the projection only
+        y = Fn.conv_unit(y, c[3].weight, c[4], ks=3, stride=self.stride, pad=1, act=ACT_RELU6, dw=True, sole=True)
+        return Fn.conv_unit(y, c[6].weight, c[7], ks=1, act=ACT_NONE, res=x if self.use_res_connect else None, sole=True)
 
 
 class Pool(nn.Module):
@@ -172,10 +173,11 @@ class SepConv(nn.Module):
 
     def forward(self, x):
         x = _entry(x)
-        for blk in self.op:
+        for idx, blk in enumerate(self.op):
             dwc = blk[0]
+            # from the second repeat on, the depthwise conv is the only consumer of the previous repeat's output (`sole`)
             x = Fn.conv_unit(x, dwc.weight, None, ks=dwc.kernel_size[0], stride=dwc.stride[0], dil=dwc.dilation[0],
-                             pad=dwc.padding[0], dw=True)
+                             pad=dwc.padding[0], dw=True, sole=idx > 0)
             x = Fn.conv_unit(x, blk[1].weight, blk[2], ks=1, act=ACT_RELU)
         return x
 
@@ -324,7 +326,7 @@ class ConcatReduce(nn.Module):
         x, y, size = self.adapt.channels(x, y)
         z = Fn.concat_resize([x, y], size)
         z = Fn.bn_act(z, self.conv1x1[0], ACT_RELU)
-        return Fn.conv_unit(z, self.conv1x1[2].weight, None, ks=1)
+        return Fn.conv_unit(z, self.conv1x1[2].weight, None, ks=1, sole=True)  # the only consumer of the BN + ReLU output
 
 
 AGG_OPS = {

@@ -219,3 +219,59 @@ def test_inverted_residual_block_bf16_training_vs_torch():
         for a, b in ((m.conv[1].running_var, ref[1].running_var), (m.conv[7].running_mean, ref[7].running_mean)):
             assert float((a - b).abs().max() / b.abs().max()) < 2e-2, tag
         assert int(m.conv[4].num_batches_tracked) == 1
+
+
+def test_bn_backward_fusion_matches_unfused_path():
+    """InvertedResidual in speed mode with the BN-backward fusion links on (gated depthwise data gradient + the expansion
+    unit's backward without dz: functional._BnRec, include/nasb200.h NasbGate / nasb_pw_bn_bwd_prepare) against the same
+    block with them off (separate sums + dz passes): every gradient agrees to bf16 rounding, and the fused entry points
+    really ran."""
+    import copy
+    from nas_segm_b200.nn.layer_factory import InvertedResidual
+    cfg = nas_segm_b200.config()
+    torch.manual_seed(5)
+    seen = []
+    orig = lib.call
+
+    def spy(name, *a):
+        seen.append(name)
+        return orig(name, *a)
+    for (inp, oup, stride, t, n, h, w) in [(16, 24, 2, 6, 2, 64, 96), (24, 24, 1, 6, 3, 33, 47), (32, 16, 1, 1, 2, 40, 56),
+                                           (32, 64, 2, 6, 2, 37, 53)]:
+        m = InvertedResidual(inp, oup, stride, t).cuda().train()
+        m2 = copy.deepcopy(m)
+        x = torch.randn(n, inp, h, w, device="cuda").to(torch.bfloat16)
+        nas_segm_b200.set_act_dtype(torch.bfloat16)
+        try:
+            res = []
+            for mod, fuse in ((m, True), (m2, False)):
+                cfg.fuse_bn_bwd = fuse
+                xi = lib.to_nhwc(x.clone()).requires_grad_(True)
+                del seen[:]
+                lib.call = Fn.call = spy
+                try:
+                    y = mod(xi)
+                    gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).to(torch.bfloat16)
+                    (y.float() * gy.float()).sum().backward()
+                finally:
+                    lib.call = Fn.call = orig
+                res.append((y.detach().float(), xi.grad.float(), {k: p.grad.clone() for k, p in mod.conv.named_parameters()}, list(seen)))
+        finally:
+            cfg.fuse_bn_bwd = False
+            nas_segm_b200.set_act_dtype(torch.float32)
+        (y1, gx1, g1, calls1), (y2, gx2, g2, calls2) = res
+        tag = (inp, oup, stride, t)
+        # expansion: no BN pass at all (dz never formed); depthwise: the dz pass only, from the projection's gated epilogue
+        assert "nasb_pw_bn_bwd_prepare" in calls1 and "nasb_pw_bn_bwd_prepare" not in calls2, tag
+        assert "nasb_dwconv_dgrad_gated" in calls1 and "nasb_pw_tc_dgrad_gated" in calls1 and "nasb_bn_bwd_from_sums" in calls1, tag
+        assert not any(c in calls2 for c in ("nasb_dwconv_dgrad_gated", "nasb_pw_tc_dgrad_gated", "nasb_bn_bwd_from_sums")), tag
+        assert calls1.count("nasb_bn_act_bwd") == calls2.count("nasb_bn_act_bwd") - 2, tag
+        assert torch.equal(y1, y2), tag
+        assert float((gx1 - gx2).norm() / gx2.norm()) < 2e-2, (tag, float((gx1 - gx2).norm() / gx2.norm()))
+        for k in g1:
+            scale = g2[k].norm()
+            if g1[k].dim() == 1:  # BN vectors: judged on the scale of the (gamma, beta) pair (see the test above)
+                idx = k.split(".")[0]
+                scale = torch.maximum(g2[idx + ".weight"].norm(), g2[idx + ".bias"].norm())
+            e = float((g1[k] - g2[k]).norm() / scale.clamp_min(1e-6))
+            assert e < 3e-2, (tag, k, e)

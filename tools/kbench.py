@@ -205,6 +205,50 @@ def _():
         report("dwconv_dgrad_strided_tile[%dx%dx%dx%d k%d]" % (n, h, w, c, ks), timeit(sets), nb)
 
 
+@case("dgrad_gated")
+def _():
+    """Data gradients with the NasbGate epilogue (gate + the producer's BN-backward reductions) next to the plain ones."""
+    import ctypes as C
+    # depthwise 3x3: (n, c, h, w of dx, stride)
+    for n, c, h, w, s in [(8, 96, 512, 1024, 2), (8, 144, 256, 512, 2), (8, 144, 256, 512, 1), (8, 32, 512, 1024, 1), (8, 192, 128, 256, 1)]:
+        oh, ow = _ohw(h, w, 3, s, 1, 1)
+        nb = n * c * (h * w + oh * ow) * 2
+        for gated in (0, 1):
+            sets = []
+            for _ in range(nsets(nb + gated * n * c * h * w * 2)):
+                dz, dx, z = act(n, c, oh, ow), act(n, c, h, w, fill=None), act(n, c, h, w)
+                wt = torch.randn(c, 1, 3, 3, device=DEV)
+                gs, gb, sums = fvec(c), fvec(c, -0.5, 0.5), torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+                gate = lib.NasbGate(C.pointer(desc(z)), ptr(gs), ptr(gb), 2, 0, ptr(sums))
+                if gated:
+                    sets.append(lambda dz=dz, dx=dx, wt=wt, gate=gate, keep=(z, gs, gb, sums): call(
+                        "nasb_dwconv_dgrad_gated", ref(desc(dz)), ptr(wt), 3, s, 1, 1, C.byref(gate), ref(desc(dx))))
+                elif s == 1:
+                    sets.append(lambda dz=dz, dx=dx, wt=wt: call("nasb_dwconv_tile", ref(desc(dz)), ptr(wt), 3, 1, 1, 1, 1, None, None,
+                                                                 0, ref(desc(dx)), None))
+                else:
+                    sets.append(lambda dz=dz, dx=dx, wt=wt: call("nasb_dwconv_dgrad_strided_tile", ref(desc(dz)), ptr(wt), 3, s, 1, 1,
+                                                                 ref(desc(dx))))
+            report("dw3x3_dgrad[%dx%dx%dx%d s%d %s]" % (n, h, w, c, s, "gated" if gated else "plain"), timeit(sets), nb)
+    # pointwise: dz [P, cdz] -> dx [P, cdx]
+    for n, h, w, cdz, cdx in [(8, 256, 512, 24, 144), (8, 512, 1024, 16, 32), (8, 256, 512, 64, 128), (8, 128, 256, 32, 192)]:
+        nb = n * h * w * (cdz + cdx) * 2
+        for gated in (0, 1):
+            sets = []
+            for _ in range(nsets(nb + gated * n * h * w * cdx * 2)):
+                dz, dx, z = act(n, cdz, h, w), act(n, cdx, h, w, fill=None), act(n, cdx, h, w)
+                wp = torch.randn(cdx * ((cdz + 7) // 8 * 8), device=DEV).to(torch.bfloat16)
+                gs, gb, sums = fvec(cdx), fvec(cdx, -0.5, 0.5), torch.zeros(2 * cdx, dtype=torch.float64, device=DEV)
+                gate = lib.NasbGate(C.pointer(desc(z)), ptr(gs), ptr(gb), 2, 0, ptr(sums))
+                if gated:
+                    sets.append(lambda dz=dz, dx=dx, wp=wp, gate=gate, keep=(z, gs, gb, sums): call(
+                        "nasb_pw_tc_dgrad_gated", ref(desc(dz)), ptr(wp), cdx, C.byref(gate), ref(desc(dx))))
+                else:
+                    sets.append(lambda dz=dz, dx=dx, wp=wp: call("nasb_pw_tc_fwd", ref(desc(dz)), ptr(wp), cdx, None, None, 0, None,
+                                                                 ref(desc(dx)), None))
+            report("pw_dgrad[%dx%dx%d %d->%d %s]" % (n, h, w, cdz, cdx, "gated" if gated else "plain"), timeit(sets), nb)
+
+
 # (n, h, w, cin, cout, stats)
 PW_SHAPES = [(8, 512, 1024, 16, 96, 1), (8, 256, 512, 24, 144, 1), (8, 256, 512, 144, 24, 1), (8, 512, 1024, 32, 32, 1),
              (8, 512, 1024, 96, 16, 0), (8, 256, 512, 224, 64, 1), (8, 128, 256, 32, 192, 1), (8, 128, 256, 192, 32, 1),
