@@ -667,7 +667,7 @@ def fwd_latency(dev, genotype, h, w, dtype, iters=20, graph=False):
         torch.cuda.synchronize()
         e0.record()
         for _ in range(iters):
-            run(x)
+            run(x)  # eager: plain module call, BN fold + operand pack per unit and call (weights may change between calls)
         e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters

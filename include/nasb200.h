@@ -384,6 +384,7 @@ int nasb_mt_pack_bf16(const NasbPackJob *jobs, int n, void *stream);
  * -------------------------------------------------------------------------------------------------------*/
 #define NASB_UNIT_TENSOR_CORES 1
 #define NASB_UNIT_TMA_TILES 2
+#define NASB_UNIT_PREPARED 4 /* scratch already holds the folded constants and the packed operand (nasb_conv_units_prepare) */
 typedef struct NasbConvUnit {
     const float *weight;                                      /* [c_out][c_in / groups][ks][ks] */
     const float *gamma, *beta, *running_mean, *running_var;   /* BatchNorm2d (eval) or NULL */
@@ -394,6 +395,11 @@ typedef struct NasbConvUnit {
 long long nasb_conv_unit_scratch(int c_out, int c_in);
 int nasb_conv_unit_infer(const NasbTensor *x, const NasbConvUnit *u, const NasbTensor *res, const NasbTensor *out,
                          void *scratch, long long scratch_bytes, int flags, void *stream);
+/* BN fold + operand pack of n units in ONE launch (units / c_in / scratch are HOST arrays; scratch[i] as above).  For regions
+ * in which the weights do not change -- a validate() loop, a captured inference graph -- this replaces two small launches per
+ * unit and call (200 of the ~360 launches of an arch0 forward); nasb_conv_unit_infer is then called with NASB_UNIT_PREPARED. */
+int nasb_conv_units_prepare(const NasbConvUnit *const *units, const int *c_in, void *const *scratch, int n, int flags,
+                            void *stream);
 
 #ifdef __cplusplus
 }

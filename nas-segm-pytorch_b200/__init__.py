@@ -9,6 +9,7 @@ Sub-packages mirror the reference's ``src/`` layout: ``nn`` (op/cell registry, d
 (name tables), ``engine`` (populate_task0 / train_task0 / train_segmenter / validate), ``helpers.miou_utils``
 (fast_cm / compute_iu / compute_ius_accs).  ``dropin()`` registers them under the reference's top-level module names.
 """
+import os as _os
 import sys as _sys
 
 __version__ = "0.1.0"
@@ -37,6 +38,10 @@ class _Config:
         # B200: the third operand costs the issue-bound producers what the separate reduction pass costs (step 24.5 vs
         # 24.4 ms, profiles/r2_bn_fusion_kbench.txt), so it is off by default.
         self.fuse_bn_bwd = False
+        # weight-gradient kernels of an engine iteration on a second stream, joined before the optimiser step (lib._WgradStream)
+        self.async_wgrad = _os.environ.get("NASB_ASYNC_WGRAD", "1") != "0"
+        # independent decoder branches (the two inputs of every aggregation) on concurrent streams (lib._BranchStreams)
+        self.branch_streams = _os.environ.get("NASB_BRANCH_STREAMS", "1") != "0"
 
 
 _config = None

@@ -49,6 +49,7 @@ def _finish_step(owner, entries, polyak_params, avg_param, polyak_decay):
     (trainer.py:163-169,258-272).  Plain SGD / Adam run as two multi-tensor launches (optim.FusedStep, cached on `owner`
     with strong references to everything its key names); anything else keeps the caller's own torch calls."""
     do_polyak = avg_param is not None and polyak_params is not None
+    lib.wgrad_stream.join()  # the weight gradients of this iteration were computed on the side stream
     if _config().fused_optim and FusedStep.supported(entries):
         key = tuple(id(o) for o, _, _ in entries) + tuple(float(mn) for _, _, mn in entries) + (id(avg_param) if do_polyak else 0,)
         cached = getattr(owner, "_nasb_fused_step", None)
@@ -155,9 +156,11 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
     def iteration(idx):
         lib.zero_arena.begin(dev)
         packs.begin(decoder)
+        lib.wgrad_stream.begin(dev)
         try:
             return _iteration(idx)
         finally:
+            lib.wgrad_stream.end()
             packs.end()
             lib.zero_arena.end()
 
@@ -216,10 +219,12 @@ def segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, en
     target, CE (+ aux), backward, the two grad-norm clips, the two optimiser steps, Polyak.  Returns the loss tensor."""
     lib.zero_arena.begin(image.device)
     packs.begin(segmenter)
+    lib.wgrad_stream.begin(image.device)
     try:
         return _segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
                                do_polyak, aux_weight, avg_param, polyak_decay)
     finally:
+        lib.wgrad_stream.end()
         packs.end()
         lib.zero_arena.end()
 
@@ -303,7 +308,8 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
         else:
             loss = segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, enc_grad_clip, dec_grad_clip,
                                   do_polyak, aux_weight, avg_param, polyak_decay)
-        loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
+        # (clone: a replayed graph returns the SAME static loss tensor every iteration -- an alias would be overwritten)
+        loss_sum = loss.detach().clone() if loss_sum is None else loss_sum + loss.detach()
         n_it += 1
         if i % print_every == 0:
             logger.info(" Train epoch: {} [{}/{}]\tAvg. Loss: {:.3f}\tAvg. Time: {:.3f}".format(

@@ -4,6 +4,7 @@ Every function here is a thin ``torch.autograd.Function``: ``forward`` / ``backw
 the library; there is no torch arithmetic on activations.  Tensors are logical NCHW views over dense NHWC storage
 (``lib.new_act``); parameters stay fp32 in the reference's layouts.
 """
+import contextlib
 import ctypes as C
 
 import torch
@@ -369,27 +370,33 @@ class _ConvUnit(torch.autograd.Function):
         ddz = desc(dz)
         if need[2] and ctx.stem_tc:  # x0 is the saved bf16 patch matrix; columns 27..31 of the product are zero padding
             dw32 = lib.zeros((cout, 32), torch.float32, dev)
-            call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dw32))
-            dweight = dw32[:, :27].reshape(weight.shape)
+            dweight = torch.empty(tuple(weight.shape), dtype=torch.float32, device=dev)
+            with (lib.wgrad_stream.fork((x0, dz)) or contextlib.nullcontext()):
+                call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dw32))
+                dweight.view(cout, 27).copy_(dw32[:, :27])  # on the stream that produced dw32
         elif need[2] and c3:
             dweight = lib.zeros(tuple(weight.shape), torch.float32, dev)
-            call("nasb_conv3_tc_wgrad", ref(desc(x0)), ref(ddz), dil, pad, ptr(dweight))
+            with (lib.wgrad_stream.fork((x0, dz)) or contextlib.nullcontext()):
+                call("nasb_conv3_tc_wgrad", ref(desc(x0)), ref(ddz), dil, pad, ptr(dweight))
         elif need[2]:
             dweight = lib.zeros(tuple(weight.shape), torch.float32, dev)
-            if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image and not in_relu
-                    and _tc_wgrad_ok(x0, dz, cout)):
-                call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dweight))
-            elif dw:
-                if not (not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and try_call(
-                        "nasb_dwconv_wgrad_tile", ref(desc(x0)), ref(ddz), ks, stride, dil, pad, ptr(dweight))):
-                    call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
-            elif image and try_call("nasb_stem_wgrad", ref(lib.desc_nchw_f32(x0)), ref(ddz), ks, stride, dil, pad,
-                                    ptr(dweight)):
-                pass
-            else:
-                dsrc0 = lib.desc_nchw_f32(x0) if image else desc(x0)
-                call("nasb_conv_wgrad", ref(dsrc0), ref(desc(x1)) if has_x1 else None, None, None, in_relu, ref(ddz), ks,
-                     stride, dil, pad, ptr(dweight))
+            # the weight gradient is not needed before the optimiser step: inside an engine iteration it runs on the side
+            # stream (lib._WgradStream) while this stream goes on with the data gradient
+            with (lib.wgrad_stream.fork((x0, x1, dz)) or contextlib.nullcontext()):
+                if (not dw and ks == 1 and stride == 1 and pad == 0 and not has_x1 and not image and not in_relu
+                        and _tc_wgrad_ok(x0, dz, cout)):
+                    call("nasb_pw_tc_wgrad", ref(desc(x0)), ref(ddz), ptr(dweight))
+                elif dw:
+                    if not (not in_relu and x0.dtype == torch.bfloat16 and _tiles_on() and try_call(
+                            "nasb_dwconv_wgrad_tile", ref(desc(x0)), ref(ddz), ks, stride, dil, pad, ptr(dweight))):
+                        call("nasb_dwconv_wgrad", ref(desc(x0)), in_relu, ref(ddz), ks, stride, dil, pad, ptr(dweight))
+                elif image and try_call("nasb_stem_wgrad", ref(lib.desc_nchw_f32(x0)), ref(ddz), ks, stride, dil, pad,
+                                        ptr(dweight)):
+                    pass
+                else:
+                    dsrc0 = lib.desc_nchw_f32(x0) if image else desc(x0)
+                    call("nasb_conv_wgrad", ref(dsrc0), ref(desc(x1)) if has_x1 else None, None, None, in_relu, ref(ddz), ks,
+                         stride, dil, pad, ptr(dweight))
         dx0 = dx1 = None
         if (need[0] or (has_x1 and need[1])) and not ctx.stem_tc:
             dx0 = lib.new_act(*x0.shape, x0.dtype, dev)
@@ -460,13 +467,16 @@ def _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, i
                              ptr(bias), float(bn.eps) if bn is not None else 0.0, cout, ks, stride, dil, pad, int(bool(dw)),
                              int(in_relu), act)
         nbytes = int(lib.load().nasb_conv_unit_scratch(cout, int(x0.shape[1])))
-        st = (u, torch.empty(nbytes, dtype=torch.uint8, device=weight.device), settings, nbytes)
+        st = (u, torch.empty(nbytes, dtype=torch.uint8, device=weight.device), settings, nbytes, weight)
         weight._nasb_unit = st
     oh, ow = conv_out_hw(h, w, ks, stride, dil, pad)
     y = lib.new_act(n, cout, oh, ow, out_dtype or x0.dtype, x0.device)
     cfg = _cfg()
+    flags = (1 if cfg.use_tcgen05 else 0) | (2 if cfg.use_tma_tiles else 0)
+    if packs.infer_prepared(st, int(x0.shape[1])):  # a scope (validate(), GraphedForward) folded / packed every unit at once
+        flags |= 4
     call("nasb_conv_unit_infer", ref(desc(x0)), C.byref(st[0]), ref(desc(res)) if res is not None else None, ref(desc(y)),
-         st[1].data_ptr(), st[3], (1 if cfg.use_tcgen05 else 0) | (2 if cfg.use_tma_tiles else 0))
+         st[1].data_ptr(), st[3], flags)
     return y
 
 

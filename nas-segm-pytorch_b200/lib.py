@@ -101,6 +101,7 @@ _SIG = {
     "nasb_mt_pack_bf16": [_P, _I, _P],
     "nasb_conv_unit_scratch": [_I, _I],
     "nasb_conv_unit_infer": [_TP, _P, _TP, _TP, _P, _L, _I, _P],
+    "nasb_conv_units_prepare": [_P, _P, _P, _I, _I, _P],
     "nasb_version": [],
 }
 _RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L,
@@ -368,11 +369,115 @@ def zeros(shape, dtype, device):
     return zero_arena.take(shape, dtype, device)
 
 
+class _WgradStream:
+    """Weight-gradient kernels of an engine iteration on a second stream.
+
+    Nothing in the backward pass depends on a weight gradient until the optimiser step, and the ~100 weight-gradient kernels
+    of the small decoder layers are latency-bound (0.2-1 TB/s): inside an engine iteration (begin() ... end()) each unit forks
+    them onto one side stream right after its dz exists and the main stream carries on with the data gradient; join() -- called
+    before the optimiser step and by end() -- makes the main stream wait.  Works the same under CUDA-graph capture (the fork
+    and join become graph edges).  Tensors the side stream reads are recorded on it, so the allocator cannot hand their
+    memory to a later main-stream allocation while the side kernel is still pending.  Outside an engine iteration the weight
+    gradients stay on the caller's stream (a user reading .grad right after backward() must not need to know about this)."""
+
+    def __init__(self):
+        self.streams, self.active, self.forked = {}, False, None
+
+    def begin(self, device):
+        from . import config
+        device = torch.device(device)
+        self.active = bool(config().async_wgrad) and device.type == "cuda"
+        self.forked = None
+
+    def fork(self, tensors):
+        """Context manager that routes launches to the side stream, or None when inactive."""
+        if not self.active:
+            return None
+        main = torch.cuda.current_stream()
+        side = self.streams.get(main.device)
+        if side is None:
+            side = self.streams[main.device] = torch.cuda.Stream(device=main.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(side)
+        self.forked = side
+        return torch.cuda.stream(side)
+
+    def join(self):
+        if self.forked is not None:
+            torch.cuda.current_stream().wait_stream(self.forked)
+            self.forked = None
+
+    def end(self):
+        self.join()
+        self.active = False
+
+
+wgrad_stream = _WgradStream()
+
+
+class _BranchStreams:
+    """Independent branches of the decoder graph on concurrent streams.
+
+    Both inputs of every aggregation (TemplateDecoder: op1(feat1) / op2(feat2); MergeCell: two contextual cells; a cell
+    layer's two ops; Adapt's two 1x1 convolutions) are independent sub-graphs of small, latency-bound kernels.  run2(fa, fb)
+    executes fb on a side stream (one per nesting depth) between a fork and a join of the current stream -- plain stream
+    semantics in eager mode, graph edges under CUDA-graph capture, and autograd replays the backward of each branch on the
+    stream its forward ran on.  Tensors that cross streams are recorded on the consuming stream."""
+
+    def __init__(self):
+        self.pool, self.depth, self.ws = {}, 0, {}
+
+    def side(self, device):
+        key = (device.index, self.depth)
+        s = self.pool.get(key)
+        if s is None:
+            s = self.pool[key] = torch.cuda.Stream(device=device)
+            # reduction scratch of its own: two branches may run BatchNorm reductions at the same time
+            self.ws[s.cuda_stream] = torch.empty(1 << 20, dtype=torch.uint8, device=device)
+        return s
+
+    def run2(self, fa, fb, b_inputs=()):
+        from . import config
+        if not config().branch_streams or not torch.cuda.is_available():
+            return fa(), fb()
+        main = torch.cuda.current_stream()
+        if torch.cuda.is_current_stream_capturing() and (main.device.index, self.depth) not in self.pool:
+            return fa(), fb()  # never create streams / scratch inside a capture (the eager warm-up creates them)
+        side = self.side(main.device)
+        self.depth += 1
+        try:
+            for t in b_inputs:
+                if t is not None and t.is_cuda:
+                    t.record_stream(side)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                b = fb()
+            a = fa()
+            main.wait_stream(side)
+        finally:
+            self.depth -= 1
+        for t in (b if isinstance(b, (tuple, list)) else (b,)):
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(main)
+        return a, b
+
+
+branch_streams = _BranchStreams()
+
 _ws = {}
 
 
 def workspace(device, nbytes=1 << 20):
-    """Per-device scratch for the reductions (BN statistics, loss sums); calls on one stream are serialised."""
+    """Per-device scratch for the reductions (BN statistics, loss sums); calls on one stream are serialised.  The side
+    streams of _BranchStreams have a scratch each."""
+    if branch_streams.ws:
+        own = branch_streams.ws.get(torch.cuda.current_stream().cuda_stream)
+        if own is not None and own.numel() >= nbytes:
+            return own
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:

@@ -286,9 +286,11 @@ class Adapt(nn.Module):
 
     def channels(self, x1, x2):
         x1, x2 = _entry(x1), _entry(x2)
-        if self.C_in0 != self.C_out:
+        if self.C_in0 != self.C_out and self.C_in1 != self.C_out:  # two independent 1x1 units: concurrent streams
+            x1, x2 = Fn.lib.branch_streams.run2(lambda: self.conv0(x1), lambda: self.conv1(x2), (x2,))
+        elif self.C_in0 != self.C_out:
             x1 = self.conv0(x1)
-        if self.C_in1 != self.C_out:
+        elif self.C_in1 != self.C_out:
             x2 = self.conv1(x2)
         return x1, x2, _pick_size(x1.shape[2:], x2.shape[2:], self.larger)
 

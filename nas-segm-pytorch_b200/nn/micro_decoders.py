@@ -58,7 +58,7 @@ class AggregateCell(nn.Module):
 
     def forward(self, x1, x2):
         if self.pre_transform:
-            x1, x2 = self.branch_1(x1), self.branch_2(x2)
+            x1, x2 = Fn.lib.branch_streams.run2(lambda: self.branch_1(x1), lambda: self.branch_2(x2), (x2,))
         s1, s2 = tuple(x1.shape[2:]), tuple(x2.shape[2:])
         if s1 < s2:  # tuple comparison, as torch.Size compares
             return Fn.resize_add(x1, x2)
@@ -97,11 +97,21 @@ class ContextualCell(nn.Module):
 
     def forward(self, x):
         feats = [x]
-        for pos, op in zip(self._pos, self._ops):
+        n, k = len(self._ops), 0
+        while k < n:
+            pos, op = self._pos[k], self._ops[k]
             if isinstance(pos, list):
                 feats.append(op(feats[pos[0]], feats[pos[1]]))
+                k += 1
+            elif k + 2 < n and not isinstance(self._pos[k + 1], list) and isinstance(self._pos[k + 2], list):
+                # the two ops of a cell layer are independent of each other (both read earlier features): concurrent streams
+                op2, f1, f2 = self._ops[k + 1], feats[pos], feats[self._pos[k + 1]]
+                a, b = Fn.lib.branch_streams.run2(lambda: op(f1), lambda: op2(f2), (f2,))
+                feats.extend((a, b))
+                k += 2
             else:
                 feats.append(op(feats[pos]))
+                k += 1
         out = feats[self._collect_inds[0]]
         for i in self._collect_inds[1:]:
             out = Fn.resize_add(feats[i], out)
@@ -122,7 +132,8 @@ class MergeCell(nn.Module):
         self.agg = AggregateCell(inps[0], inps[1], agg_size)
 
     def forward(self, x1, x2):
-        return self.agg(self.op_1(x1), self.op_2(x2))
+        a, b = Fn.lib.branch_streams.run2(lambda: self.op_1(x1), lambda: self.op_2(x2), (x2,))
+        return self.agg(a, b)
 
     def prettify(self):
         return self.op_1.prettify()
@@ -255,7 +266,9 @@ class TemplateDecoder(nn.Module):
             feat1, feat2 = feats[pos[0]], feats[pos[1]]
             out = None
             for i in range(repeat):
-                out = ops[i * 3 + 2](ops[i * 3](feat1), ops[i * 3 + 1](feat2))
+                # the two operand branches of an aggregation are independent: concurrent streams (lib._BranchStreams)
+                a, b = Fn.lib.branch_streams.run2(lambda: ops[i * 3](feat1), lambda: ops[i * 3 + 1](feat2), (feat2,))
+                out = ops[i * 3 + 2](a, b)
                 feat1, feat2 = feat2, out
             feats.append(out)
         return _head(self.pre_clf, self.conv_clf, collect_all(feats, self._collect_inds, relu=True))

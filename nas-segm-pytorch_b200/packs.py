@@ -25,6 +25,11 @@ _JOB = np.dtype([("src", np.uint64), ("dst", np.uint64), ("c_out", np.int32), ("
 
 _active = None  # {(weight.data_ptr(), kind): packed tensor} of the open scope
 
+# ---- inference units (functional._conv_unit_infer): BN fold + operand pack of EVERY unit of the model in one launch
+_scope_model = None   # the model of the open scope
+_prepared = None      # {scratch address} of the units the open scope has prepared (None: no scope)
+_pending = None       # units met inside the scope that were not in the model's plan yet: [(unit_state, c_in)]
+
 
 class _ModelPacks:
     def __init__(self, model):
@@ -63,10 +68,44 @@ class _ModelPacks:
                 lib.call("nasb_mt_pack_bf16", C.c_void_p(self.jobs.ctypes.data), len(self.jobs))
 
 
+def _prepare_infer(model):
+    """One launch that folds BatchNorm and packs the operand of every inference unit the model has run before."""
+    global _scope_model, _prepared, _pending
+    from . import config
+    _scope_model, _prepared, _pending = model, set(), []
+    plan = model.__dict__.get("_nasb_infer_plan")
+    if not plan or torch.is_grad_enabled():
+        return
+    units = [(st, cin) for st, cin in plan if st[0].weight == st[4].data_ptr() and st[1].is_cuda]
+    if len(units) != len(plan):  # parameters moved (model.to(...)): the stale states are rebuilt at their next call
+        object.__setattr__(model, "_nasb_infer_plan", units)
+    if not units:
+        return
+    n = len(units)
+    arr_u = (C.c_void_p * n)(*[C.addressof(st[0]) for st, _ in units])
+    arr_c = (C.c_int * n)(*[cin for _, cin in units])
+    arr_s = (C.c_void_p * n)(*[st[1].data_ptr() for st, _ in units])
+    cfg = config()
+    with torch.cuda.device(units[0][0][1].device):
+        lib.call("nasb_conv_units_prepare", arr_u, arr_c, arr_s, n, (1 if cfg.use_tcgen05 else 0) | (2 if cfg.use_tma_tiles else 0))
+    _prepared = {st[1].data_ptr() for st, _ in units}
+
+
+def infer_prepared(state, c_in):
+    """Is this inference unit's scratch already filled by the open scope?  Unknown units are noted for the next scope."""
+    if _prepared is None:
+        return False
+    if state[1].data_ptr() in _prepared:
+        return True
+    _pending.append((state, c_in))
+    return False
+
+
 def begin(model):
     """Open a scope: re-pack every tensor-core operand of `model` (one launch) and serve them to the conv units."""
     global _active
     from . import config
+    _prepare_infer(model)
     if config().act_dtype != torch.bfloat16 or not config().use_tcgen05:
         _active = None
         return
@@ -82,8 +121,14 @@ def begin(model):
 
 
 def end():
-    global _active
+    global _active, _scope_model, _prepared, _pending
     _active = None
+    if _scope_model is not None and _pending:
+        plan = _scope_model.__dict__.get("_nasb_infer_plan") or []
+        known = {st[1].data_ptr() for st, _ in plan}
+        plan = plan + [(st, cin) for st, cin in _pending if st[1].data_ptr() not in known and not known.add(st[1].data_ptr())]
+        object.__setattr__(_scope_model, "_nasb_infer_plan", plan)
+    _scope_model = _prepared = _pending = None
 
 
 @contextlib.contextmanager

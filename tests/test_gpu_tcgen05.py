@@ -231,11 +231,17 @@ def test_bn_backward_fusion_matches_unfused_path():
     cfg = nas_segm_b200.config()
     torch.manual_seed(5)
     seen = []
-    orig = lib.call
+    orig, orig_try = lib.call, lib.try_call
 
     def spy(name, *a):
         seen.append(name)
         return orig(name, *a)
+
+    def spy_try(name, *a):
+        ok = orig_try(name, *a)
+        if ok:
+            seen.append(name)
+        return ok
     for (inp, oup, stride, t, n, h, w) in [(16, 24, 2, 6, 2, 64, 96), (24, 24, 1, 6, 3, 33, 47), (32, 16, 1, 1, 2, 40, 56),
                                            (32, 64, 2, 6, 2, 37, 53)]:
         m = InvertedResidual(inp, oup, stride, t).cuda().train()
@@ -249,12 +255,14 @@ def test_bn_backward_fusion_matches_unfused_path():
                 xi = lib.to_nhwc(x.clone()).requires_grad_(True)
                 del seen[:]
                 lib.call = Fn.call = spy
+                lib.try_call = Fn.try_call = spy_try
                 try:
                     y = mod(xi)
                     gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).to(torch.bfloat16)
                     (y.float() * gy.float()).sum().backward()
                 finally:
                     lib.call = Fn.call = orig
+                    lib.try_call = Fn.try_call = orig_try
                 res.append((y.detach().float(), xi.grad.float(), {k: p.grad.clone() for k, p in mod.conv.named_parameters()}, list(seen)))
         finally:
             cfg.fuse_bn_bwd = False
