@@ -281,6 +281,7 @@ def torch_b200_numbers(dev, a, budget_s=150.0):
     from oracle import nas_oracle as O
     t_start = time.time()
     res = {}
+    torch.backends.cudnn.benchmark = True  # let cuDNN pick its fastest algorithm per shape (the warm-up absorbs the search)
 
     def params(seed_e=1, seed_d=2):
         Pe, Pd = O.Params(seed=seed_e), O.Params(seed=seed_d)
@@ -395,7 +396,7 @@ def torch_b200_numbers(dev, a, budget_s=150.0):
         except Exception as e:  # noqa: BLE001
             res["train_%s_error" % dn] = repr(e)[:300]
         torch.cuda.empty_cache()
-    res["what"] = ("stock PyTorch %s (cuDNN/ATen; channels_last; bf16 = torch.autocast) running the reference's module graph "
+    res["what"] = ("stock PyTorch %s (cuDNN/ATen, cudnn.benchmark on; channels_last; bf16 = torch.autocast) running the reference's module graph "
                    "(oracle/nas_oracle.py restatement) on this GPU" % torch.__version__)
     return res
 
@@ -454,6 +455,22 @@ def metric_numbers(dev):
     res["confmat_labels_gbs"] = 2.0 * n / (ms * 1e-3) / 1e9
     res["confmat_labels_frac_of_hbm_peak"] = res["confmat_labels_gbs"] / peak
     res["confmat_labels_gpx_per_s"] = n / (ms * 1e-3) / 1e9
+    # the same on label maps with spatial structure (64x64-pixel regions of one class, 5 % ignore pixels): uniform random
+    # labels are the worst case of any histogram -- every pixel is a different (gt, pred) pair -- real maps are not
+    bsets = []
+    for _ in range(6):
+        small = torch.randint(0, C, (B, H // 64, W // 64), generator=g)
+        gtb = small.repeat_interleave(64, 1).repeat_interleave(64, 2).to(torch.uint8)
+        prb = gtb.clone()
+        flip = torch.rand(B, H, W, generator=g)
+        prb[flip < 0.1] = torch.randint(0, C, (int((flip < 0.1).sum()),), generator=g).to(torch.uint8)  # 10 % errors
+        gtb[flip > 0.95] = 255
+        bsets.append((prb.view(-1).to(dev), gtb.view(-1).to(dev)))
+    ms = timed([lambda p=p, q=q: Fn.confmat_labels(p, q, C, cm) for p, q in bsets])
+    res["confmat_labels_structured_ms"] = ms
+    res["confmat_labels_structured_gbs"] = 2.0 * n / (ms * 1e-3) / 1e9
+    res["confmat_labels_structured_frac_of_hbm_peak"] = res["confmat_labels_structured_gbs"] / peak
+    del bsets
     for dt, dn in ((torch.float32, "f32"),):
         lsets = []
         for i in range(4):
@@ -837,10 +854,19 @@ def main():
     roof, top_list = None, []
     if rank == 0:
         n_prof = min(a.steps, 3)
-        lib.profile_begin()
-        for _ in range(n_prof):
+        # per-kernel durations need the kernels one after another: the side-stream weight gradients and the concurrent
+        # decoder branches of the timed runs above would overlap (and stretch) the launches being measured
+        cfg_ = nas_segm_b200.config()
+        saved = (cfg_.async_wgrad, cfg_.branch_streams)
+        cfg_.async_wgrad = cfg_.branch_streams = False
+        try:
             trainer.segmenter_step(seg, img_d, lab_d, optim_enc, optim_dec, crit, 3.0, 3.0, False)
-        prof = lib.profile_end()
+            lib.profile_begin()
+            for _ in range(n_prof):
+                trainer.segmenter_step(seg, img_d, lab_d, optim_enc, optim_dec, crit, 3.0, 3.0, False)
+            prof = lib.profile_end()
+        finally:
+            cfg_.async_wgrad, cfg_.branch_streams = saved
         tot = sum(v[1] for v in prof.values())
         if a.profile_out:
             with open(a.profile_out, "w") as f:

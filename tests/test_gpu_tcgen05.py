@@ -270,8 +270,10 @@ def test_bn_backward_fusion_matches_unfused_path():
         (y1, gx1, g1, calls1), (y2, gx2, g2, calls2) = res
         tag = (inp, oup, stride, t)
         # expansion: no BN pass at all (dz never formed); depthwise: the dz pass only, from the projection's gated epilogue
-        assert "nasb_pw_bn_bwd_prepare" in calls1 and "nasb_pw_bn_bwd_prepare" not in calls2, tag
+        nodz = t >= 2  # the algebraic path needs a narrow input (2 * C_in <= C_out); t = 1 keeps the dz pass, from the sums
+        assert ("nasb_pw_bn_bwd_prepare" in calls1) == nodz and "nasb_pw_bn_bwd_prepare" not in calls2, tag
         assert "nasb_dwconv_dgrad_gated" in calls1 and "nasb_pw_tc_dgrad_gated" in calls1 and "nasb_bn_bwd_from_sums" in calls1, tag
+        assert calls1.count("nasb_bn_bwd_from_sums") == (1 if nodz else 2), tag
         assert not any(c in calls2 for c in ("nasb_dwconv_dgrad_gated", "nasb_pw_tc_dgrad_gated", "nasb_bn_bwd_from_sums")), tag
         assert calls1.count("nasb_bn_act_bwd") == calls2.count("nasb_bn_act_bwd") - 2, tag
         assert torch.equal(y1, y2), tag
