@@ -178,7 +178,7 @@ def train_task0(Xy_train, segmenter, optim_dec, epoch, segm_crit, kd_crit, batch
         if aux_weight > 0:
             for aux_out in aux_outs:
                 loss = loss + _segm_loss(segm_crit, aux_out, y, out_size) * aux_weight
-        optim_dec.zero_grad()
+        optim_dec.zero_grad(set_to_none=True)
         loss.backward()
         if dec_grad_clip > 0:
             _finish_step(decoder, [(optim_dec, dec_params, dec_grad_clip)], dec_params if do_polyak else None,
@@ -240,8 +240,8 @@ def _segmenter_step(segmenter, image, target, optim_enc, optim_dec, segm_crit, e
     if aux_weight > 0:
         for aux_out in aux_outs:
             loss = loss + _segm_loss(segm_crit, aux_out, target_var, tuple(target_var.size()[1:])) * aux_weight
-    optim_enc.zero_grad()
-    optim_dec.zero_grad()
+    optim_enc.zero_grad(set_to_none=True)
+    optim_dec.zero_grad(set_to_none=True)
     loss.backward()
     _finish_step(segmenter, [(optim_enc, segmenter.module.encoder.parameters(), enc_grad_clip),
                              (optim_dec, segmenter.module.decoder.parameters(), dec_grad_clip)],

@@ -310,8 +310,10 @@ class _ZeroArena:
     """Zero-initialised scratch for one training iteration (gradient accumulators of the atomically-reduced kernels,
     fp64 statistics cells): one memset per iteration instead of ~300 two-microsecond fill kernels.  The engine's step
     functions bracket an iteration with begin()/end(); outside of that take() is plain torch.zeros.  A tensor taken in
-    iteration i is zeroed again by begin() of iteration i+1, so only the engine loops (which drop gradients with
-    zero_grad() every iteration) switch it on.
+    iteration i is zeroed again by begin() of iteration i+1, so only the engine loops switch it on: they drop every
+    gradient with zero_grad(set_to_none=True) before the next backward pass, which is what makes handing arena views to
+    autograd as parameter gradients safe.  Code that keeps .grad tensors alive across iterations (gradient accumulation,
+    set_to_none=False) must not run inside begin() / end() -- outside of it take() is plain torch.zeros.
 
     The buffer of a device is allocated ONCE (CAPACITY bytes) and never replaced: a captured CUDA graph bakes in its
     address (the memset and every view), and a graph of an earlier model may still be replayed after a larger model has
@@ -429,7 +431,7 @@ class _BranchStreams:
     stream its forward ran on.  Tensors that cross streams are recorded on the consuming stream."""
 
     def __init__(self):
-        self.pool, self.depth, self.ws = {}, 0, {}
+        self.pool, self.depth, self.ws, self.quiet = {}, 0, {}, False
 
     def side(self, device):
         key = (device.index, self.depth)
@@ -449,6 +451,13 @@ class _BranchStreams:
         if capturing and (main.device.index, self.depth) not in self.pool:
             return fa(), fb()  # never create streams / scratch inside a capture (the eager warm-up creates them)
         side = self.side(main.device)
+        if torch.is_grad_enabled() and not self.quiet:
+            # parameters live on the stream they were created on, their gradients now arrive from the branch streams: autograd's
+            # "AccumulateGrad stream mismatch" note is about a synchronisation this design accepts
+            fn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if fn is not None:
+                fn(False)
+            self.quiet = True
         if not capturing and not torch.is_grad_enabled():
             # eager inference is bound by host dispatch, not by the GPU: a fork / join (two event round trips) costs more than
             # the overlap returns (arch0 480x360: 4.1 -> 4.9 ms).  The streams exist now, so a later capture can use them.

@@ -276,7 +276,9 @@ def test_bn_backward_fusion_matches_unfused_path():
         assert calls1.count("nasb_bn_bwd_from_sums") == (1 if nodz else 2), tag
         assert not any(c in calls2 for c in ("nasb_dwconv_dgrad_gated", "nasb_pw_tc_dgrad_gated", "nasb_bn_bwd_from_sums")), tag
         assert calls1.count("nasb_bn_act_bwd") == calls2.count("nasb_bn_act_bwd") - 2, tag
-        assert torch.equal(y1, y2), tag
+        # same forward kernels; the fp64 statistics are reduced with atomics, so a rare last-bit difference of a batch mean can
+        # flip single bf16 roundings of y
+        assert float((y1 - y2).abs().max()) <= 2.0 ** -7 * float(y2.abs().max()), tag
         assert float((gx1 - gx2).norm() / gx2.norm()) < 2e-2, (tag, float((gx1 - gx2).norm() / gx2.norm()))
         for k in g1:
             scale = g2[k].norm()

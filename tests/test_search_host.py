@@ -127,7 +127,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, logpath):
+def _worker(rank, world, port, q, logpath, sync_every=1, rounds=2):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     from nas_segm_b200 import parallel
     from nas_segm_b200.engine.search import GenotypeLog, search_rounds
@@ -146,7 +146,7 @@ def _worker(rank, world, port, q, logpath):
         return (0.1 * (cfg[0][0] + 1) + 0.01 * cfg[0][1], 3) if cfg[0][1] == 0 else 0   # slot 1 "fails" -> reward 0
 
     log = GenotypeLog(logpath) if rank == 0 else None
-    hist = search_rounds(2, sample, build, evaluate, update_fn=updates.append, log=log, first_epoch=10)
+    hist = search_rounds(rounds, sample, build, evaluate, update_fn=updates.append, log=log, first_epoch=10, sync_every=sync_every)
     if log is not None:
         log.close()
     q.put((rank, [h[:, 0].tolist() for h in hist], built, updates))
@@ -176,3 +176,44 @@ def test_two_rank_search_rounds_gloo(tmp_path):
     assert len(lines) == 4
     assert [int(re.search(r"epoch: (\d+)", ln).group(1)) for ln in lines] == [10, 11, 12, 13]
     assert all("params: 20," in ln for ln in lines) and lines[0].startswith("reward: 0.1000,") and lines[1].startswith("reward: 0.0000,")
+
+
+def test_two_rank_blocked_exchange_gloo(tmp_path):
+    """sync_every = k: k rounds per all-gather (a rank whose candidate stopped early moves on instead of waiting); history,
+    controller updates and log lines are the same as with one exchange per round, in (round, slot) order."""
+    ctx = mp.get_context("spawn")
+    out = {}
+    for sync_every in (1, 3):
+        world, port = 2, _free_port()
+        logpath = str(tmp_path / ("genotypes_%d.out" % sync_every))
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, q, logpath, sync_every, 3)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=120) for _ in range(world))
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert res[0][1] == res[1][1] and res[0][3] == res[1][3]
+        lines = [re.sub(r"epoch_time: [0-9.]+", "epoch_time: T", ln) for ln in open(logpath).read().splitlines()]
+        out[sync_every] = (res[0][1], res[0][3], lines)
+    assert out[1][0] == out[3][0] and out[1][1] == out[3][1] and out[1][2] == out[3][2] and len(out[3][2]) == 6
+
+
+def test_uniform_sampler_covers_the_reference_search_space():
+    """engine.search.uniform_sampler: ranges of src/rl/micro_controllers.py:94-120,180-262; deterministic in (seed, round, slot)."""
+    from nas_segm_b200.engine.search import uniform_sampler
+    s = uniform_sampler(seed=3)
+    seen_ops, seen_pos = set(), set()
+    for rnd in range(40):
+        for slot in range(4):
+            (ctx, conns), ent, logp = s(rnd, slot)
+            assert s(rnd, slot)[0] == [ctx, conns] and abs(ent + logp) < 1e-12
+            assert len(conns) == 3 and all(len(c) == 2 and 0 <= c[0] < 4 + i and 0 <= c[1] < 4 + i for i, c in enumerate(conns))
+            assert 0 <= ctx[0] < 11 and len(ctx) == 4
+            for layer, cfg in enumerate(ctx[1:], start=1):
+                assert len(cfg) == 4 and all(0 <= p < 1 + 3 * (layer - 1) for p in cfg[:2]) and all(0 <= o < 11 for o in cfg[2:])
+                seen_ops.update(cfg[2:])
+                seen_pos.add((layer, cfg[0]))
+    assert seen_ops == set(range(11)) and (3, 6) in seen_pos
+    assert s(0, 0)[0] != s(0, 1)[0] or s(0, 0)[0] != s(1, 0)[0]
