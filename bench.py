@@ -585,12 +585,30 @@ def search_numbers(a, dev, rank, world, rounds, warm_rounds, n_task0, task1_iter
         dec = MicroDecoder(list(enc.out_sizes), 21, cfg, agg_size=48, aux_cell=True, repeats=1)
         return Wrapper(Seg(enc, dec).to(dev))
 
+    from nas_segm_b200.engine import inference as _inference
+    phases = {"train_task0": 0.0, "train_segmenter": 0.0, "validate": 0.0}
+
+    def _timed(name, fn):  # per-phase host time (each engine call ends with a device sync of its own: the logged loss / the reward)
+        def wrapped(*a, **k):
+            t = time.time()
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.synchronize()
+                phases[name] += time.time() - t
+        return wrapped
+
+    class engine_ns:  # noqa: N801
+        train_task0 = staticmethod(_timed("train_task0", trainer.train_task0))
+        train_segmenter = staticmethod(_timed("train_segmenter", trainer.train_segmenter))
+        validate = staticmethod(_timed("validate", _inference.validate))
+
     def evaluate(seg, cfg):
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record()
         try:
-            out = search.evaluate_candidate(seg, Xy, train1, val, args, task_ps)
+            out = search.evaluate_candidate(seg, Xy, train1, val, args, task_ps, engine=engine_ns)
         except Exception as e:  # noqa: BLE001 -- keep the ranks' collectives matched whatever one candidate does
             errors.append(repr(e)[:200])
             out = (0.0, 1)
@@ -607,6 +625,8 @@ def search_numbers(a, dev, rank, world, rounds, warm_rounds, n_task0, task1_iter
     if warm_rounds:
         search.search_rounds(warm_rounds, lambda r, s: sampler(10000 + r, s), build, evaluate, sync_every=warm_rounds)
     n_warm = len(per_candidate)
+    for k in phases:
+        phases[k] = 0.0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.time()
@@ -636,6 +656,7 @@ def search_numbers(a, dev, rank, world, rounds, warm_rounds, n_task0, task1_iter
             "per_candidate_s": [[round(float(v), 3) for v in allt[r, :, 0]] for r in range(world)],
             "epochs_run": [[int(v) for v in allt[r, :, 1]] for r in range(world)],
             "rewards": [[round(float(t[s, 0]), 5) for s in range(world)] for t in hist],
+            "phase_seconds_per_candidate_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},
             "populate_task0_s_per_image": t_populate_per_image, "n_task0": n_task0, "task1_iterations": task1_iters,
             "val_images": len(val) * 64, "errors": errors[:3],
             "recipe": "task0: 5 epochs x %d it (batch 64, 64x64 feats, KD+aux, Adam, clip, Polyak) + validate; TaskPerformer; "

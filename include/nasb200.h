@@ -401,6 +401,21 @@ int nasb_conv_unit_infer(const NasbTensor *x, const NasbConvUnit *u, const NasbT
 int nasb_conv_units_prepare(const NasbConvUnit *const *units, const int *c_in, void *const *scratch, int n, int flags,
                             void *stream);
 
+/* The fused separable primitive (inference): depthwise k x k (k in {3,5}, stride 1, dilation 1, "same" padding) -> folded BN
+ * / activation -> pointwise 1x1 (C_out <= 64) on the tensor cores -> folded BN / activation (+ residual) in ONE kernel:
+ * TMA halo tile -> depthwise in registers -> bf16 A operand written into SWIZZLE_128B shared memory -> tcgen05.mma (TMEM
+ * accumulator) -> epilogue -> TMA store.  The depthwise tensor is never written to HBM.
+ * SepConv's dw -> 1x1 -> BN -> ReLU (layer_factory.py:241-256), InvertedResidual's dw -> BN -> ReLU6 -> 1x1 -> BN (+x) (:141-158).
+ * nasb_sepconv_tc_fwd : the kernel (mid_* = folded constants between the convolutions, wpack = nasb_pack_weight_bf16 of the
+ *                       pointwise weight); nasb_sep_unit_infer: the same behind two NasbConvUnit blocks (fold + pack inside). */
+int nasb_sepconv_tc_supported(int C, int N, int ks, int stride, int dil, int pad);
+int nasb_sepconv_tc_fwd(const NasbTensor *x, const float *dw_weight, int ks, int stride, int dil, int pad, const float *mid_scale,
+                        const float *mid_shift, int mid_act, const void *wpack, int N, const float *out_scale,
+                        const float *out_shift, int out_act, const NasbTensor *res, const NasbTensor *out, void *stream);
+int nasb_sep_unit_infer(const NasbTensor *x, const NasbConvUnit *udw, void *scratch_dw, long long scratch_dw_bytes,
+                        const NasbConvUnit *upw, void *scratch_pw, long long scratch_pw_bytes, const NasbTensor *res,
+                        const NasbTensor *out, int flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

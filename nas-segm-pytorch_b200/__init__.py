@@ -38,6 +38,8 @@ class _Config:
         # B200: the third operand costs the issue-bound producers what the separate reduction pass costs (step 24.5 vs
         # 24.4 ms, profiles/r2_bn_fusion_kbench.txt), so it is off by default.
         self.fuse_bn_bwd = False
+        # inference: depthwise -> pointwise pairs as one kernel (csrc/sep_tcgen05.cu) when the shapes allow
+        self.fused_sep = _os.environ.get("NASB_FUSED_SEP", "1") != "0"
         # weight-gradient kernels of an engine iteration on a second stream, joined before the optimiser step (lib._WgradStream)
         self.async_wgrad = _os.environ.get("NASB_ASYNC_WGRAD", "1") != "0"
         # independent decoder branches (the two inputs of every aggregation) on concurrent streams (lib._BranchStreams)

@@ -165,3 +165,46 @@ extern "C" int nasb_conv_unit_infer(const NasbTensor *x, const NasbConvUnit *u, 
     return nasb_conv_fwd(x, nullptr, u->weight, u->ks, u->stride, u->dil, u->pad, nullptr, nullptr, u->in_relu, scale, shift,
                          u->act, res, out, stream);
 }
+
+// Depthwise unit followed by a pointwise unit (SepConv repeat, InvertedResidual's depthwise + projection) as ONE kernel
+// (csrc/sep_tcgen05.cu) when the shapes allow; NASB_ERR_UNSUPPORTED otherwise (the caller then runs the two units one after
+// the other).  scratch_* as for nasb_conv_unit_infer; with NASB_UNIT_PREPARED both must have been prepared.
+extern "C" int nasb_sep_unit_infer(const NasbTensor *x, const NasbConvUnit *udw, void *scratch_dw, long long scratch_dw_bytes,
+                                   const NasbConvUnit *upw, void *scratch_pw, long long scratch_pw_bytes, const NasbTensor *res,
+                                   const NasbTensor *out, int flags, void *stream) {
+    if (!x || !udw || !upw || !out || !udw->weight || !upw->weight) return NASB_ERR_BAD_ARG;
+    if (!(flags & NASB_UNIT_TENSOR_CORES) || !udw->dw || upw->dw || udw->in_relu || upw->in_relu || udw->bias || upw->bias ||
+        upw->ks != 1 || upw->stride != 1 || upw->pad != 0 || udw->c_out != x->c || x->dtype != NASB_BF16 || out->dtype != NASB_BF16)
+        return NASB_ERR_UNSUPPORTED;
+    const int C = x->c, N = upw->c_out;
+    if (!nasb_sepconv_tc_supported(C, N, udw->ks, udw->stride, udw->dil, udw->pad)) return NASB_ERR_UNSUPPORTED;
+    const bool prepared = (flags & NASB_UNIT_PREPARED) != 0;
+    const float *ms = nullptr, *mb = nullptr, *os = nullptr, *ob = nullptr;
+    if (udw->running_mean) {
+        if (!udw->running_var || !scratch_dw || scratch_dw_bytes < 2LL * C * (long long)sizeof(float)) return NASB_ERR_BAD_ARG;
+        float *ss = (float *)scratch_dw;
+        if (!prepared) {
+            int rc = nasb_bn_fold(udw->gamma, udw->beta, udw->running_mean, udw->running_var, udw->eps, C, ss, ss + C, stream);
+            if (rc) return rc;
+        }
+        ms = ss, mb = ss + C;
+    }
+    const long long ss_bytes = (2LL * N * (long long)sizeof(float) + 255) / 256 * 256;
+    if (!scratch_pw || scratch_pw_bytes < ss_bytes + 2LL * N * ((C + 7) / 8 * 8)) return NASB_ERR_BAD_ARG;
+    if (upw->running_mean) {
+        if (!upw->running_var) return NASB_ERR_BAD_ARG;
+        float *ss = (float *)scratch_pw;
+        if (!prepared) {
+            int rc = nasb_bn_fold(upw->gamma, upw->beta, upw->running_mean, upw->running_var, upw->eps, N, ss, ss + N, stream);
+            if (rc) return rc;
+        }
+        os = ss, ob = ss + N;
+    }
+    void *pack = (char *)scratch_pw + ss_bytes;
+    if (!prepared) {
+        int rc = nasb_pack_weight_bf16(upw->weight, N, C, 0, pack, stream);
+        if (rc) return rc;
+    }
+    return nasb_sepconv_tc_fwd(x, udw->weight, udw->ks, udw->stride, udw->dil, udw->pad, ms, mb, udw->act, pack, N, os, ob, upw->act,
+                               res, out, stream);
+}

@@ -449,11 +449,9 @@ class _ConvUnit(torch.autograd.Function):
         return dx0, dx1, dweight, dgamma, dbeta, dbias, dres, None, None
 
 
-def _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, in_relu, out_dtype):
-    """Inference path of a conv unit: BN fold + operand pack + kernel choice behind ONE C-ABI call (csrc/unit.cu).  The
-    parameter block and the scratch buffer live on the weight tensor and are rebuilt when any address or setting changes."""
-    lib.require_cuda(x0)
-    n, _, h, w = x0.shape
+def _unit_state(cin, weight, bn, ks, stride, dil, pad, act, dw, in_relu, bias):
+    """The NasbConvUnit parameter block + scratch buffer of an inference unit; they live on the weight tensor and are rebuilt
+    when any address or setting changes.  -> (struct, scratch, settings, scratch bytes, weight)"""
     cout = weight.shape[0]
     if bn is not None and bn.running_mean is None:
         raise RuntimeError("BatchNorm2d without running statistics is not supported")
@@ -466,18 +464,51 @@ def _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, i
                              ptr(bn.running_mean) if bn is not None else None, ptr(bn.running_var) if bn is not None else None,
                              ptr(bias), float(bn.eps) if bn is not None else 0.0, cout, ks, stride, dil, pad, int(bool(dw)),
                              int(in_relu), act)
-        nbytes = int(lib.load().nasb_conv_unit_scratch(cout, int(x0.shape[1])))
+        nbytes = int(lib.load().nasb_conv_unit_scratch(cout, int(cin)))
         st = (u, torch.empty(nbytes, dtype=torch.uint8, device=weight.device), settings, nbytes, weight)
         weight._nasb_unit = st
+    return st
+
+
+def _conv_unit_infer(x0, weight, bn, ks, stride, dil, pad, act, bias, res, dw, in_relu, out_dtype):
+    """Inference path of a conv unit: BN fold + operand pack + kernel choice behind ONE C-ABI call (csrc/unit.cu)."""
+    lib.require_cuda(x0)
+    n, cin, h, w = x0.shape
+    cout = weight.shape[0]
+    st = _unit_state(cin, weight, bn, ks, stride, dil, pad, act, dw, in_relu, bias)
     oh, ow = conv_out_hw(h, w, ks, stride, dil, pad)
     y = lib.new_act(n, cout, oh, ow, out_dtype or x0.dtype, x0.device)
     cfg = _cfg()
     flags = (1 if cfg.use_tcgen05 else 0) | (2 if cfg.use_tma_tiles else 0)
-    if packs.infer_prepared(st, int(x0.shape[1])):  # a scope (validate(), GraphedForward) folded / packed every unit at once
+    if packs.infer_prepared(st, int(cin)):  # a scope (validate(), GraphedForward) folded / packed every unit at once
         flags |= 4
     call("nasb_conv_unit_infer", ref(desc(x0)), C.byref(st[0]), ref(desc(res)) if res is not None else None, ref(desc(y)),
          st[1].data_ptr(), st[3], flags)
     return y
+
+
+def sep_unit(x, dw_weight, dw_bn, dw_act, pw_weight, pw_bn, pw_act, *, ks, stride, dil, pad, res=None, sole=(False, False)):
+    """Depthwise conv unit followed by a pointwise conv unit (a SepConv repeat, layer_factory.py:241-256; the depthwise +
+    projection half of InvertedResidual, :141-158).  At inference, when the shapes allow, ONE kernel (csrc/sep_tcgen05.cu):
+    the depthwise output goes from registers into the tensor core's shared-memory operand and never touches HBM.  Otherwise
+    (training, or shapes outside the fused kernel) the two units run one after the other.  `sole`: see conv_unit."""
+    cfg = _cfg()
+    if (cfg.fused_sep and cfg.use_tcgen05 and not torch.is_grad_enabled() and x.dtype == torch.bfloat16
+            and (dw_bn is None or not dw_bn.training) and (pw_bn is None or not pw_bn.training)
+            and lib.load().nasb_sepconv_tc_supported(int(x.shape[1]), int(pw_weight.shape[0]), ks, stride, dil, pad)):
+        lib.require_cuda(x)
+        n, c, h, w = x.shape
+        st_dw = _unit_state(c, dw_weight, dw_bn, ks, stride, dil, pad, dw_act, True, 0, None)
+        st_pw = _unit_state(c, pw_weight, pw_bn, 1, 1, 1, 0, pw_act, False, 0, None)
+        y = lib.new_act(n, pw_weight.shape[0], h, w, x.dtype, x.device)
+        flags = 1 | (2 if cfg.use_tma_tiles else 0)
+        if packs.infer_prepared(st_dw, int(c)) & packs.infer_prepared(st_pw, int(c)):
+            flags |= 4
+        if try_call("nasb_sep_unit_infer", ref(desc(x)), C.byref(st_dw[0]), st_dw[1].data_ptr(), st_dw[3], C.byref(st_pw[0]),
+                    st_pw[1].data_ptr(), st_pw[3], ref(desc(res)) if res is not None else None, ref(desc(y)), flags):
+            return y
+    t = conv_unit(x, dw_weight, dw_bn, ks=ks, stride=stride, dil=dil, pad=pad, act=dw_act, dw=True, sole=sole[0])
+    return conv_unit(t, pw_weight, pw_bn, ks=1, act=pw_act, res=res, sole=sole[1])
 
 
 def conv_unit(x0, weight, bn=None, *, ks, stride=1, dil=1, pad=0, act=ACT_NONE, x1=None, bias=None, res=None, dw=False,

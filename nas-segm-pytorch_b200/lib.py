@@ -102,6 +102,9 @@ _SIG = {
     "nasb_conv_unit_scratch": [_I, _I],
     "nasb_conv_unit_infer": [_TP, _P, _TP, _TP, _P, _L, _I, _P],
     "nasb_conv_units_prepare": [_P, _P, _P, _I, _I, _P],
+    "nasb_sepconv_tc_supported": [_I, _I, _I, _I, _I, _I],
+    "nasb_sepconv_tc_fwd": [_TP, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _TP, _TP, _P],
+    "nasb_sep_unit_infer": [_TP, _P, _P, _L, _P, _P, _L, _TP, _TP, _I, _P],
     "nasb_version": [],
 }
 _RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L,
@@ -111,7 +114,7 @@ EXPORTS = tuple(sorted(_SIG))
 _lib = None
 launches = 0  # kernels launched through the C ABI by this process (bench.py reports the delta over its timed region)
 # kernels (and async memsets) behind one call of each entry point; everything not listed launches exactly one
-_KERNELS_PER_CALL = {"nasb_bn_bwd_from_sums": 2, "nasb_pw_bn_bwd_prepare": 2, "nasb_conv_unit_infer": 3, "nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
+_KERNELS_PER_CALL = {"nasb_sep_unit_infer": 4, "nasb_bn_bwd_from_sums": 2, "nasb_pw_bn_bwd_prepare": 2, "nasb_conv_unit_infer": 3, "nasb_mt_grad_sumsq": 3, "nasb_mt_optim_step": 2, "nasb_bn_stats": 3, "nasb_bn_act_bwd": 3, "nasb_ce_fwd": 3, "nasb_mse_fwd": 3, "nasb_berhu_fwd": 4,
                      "nasb_spatial_mean": 2, "nasb_spatial_sum": 2}
 _prof = None  # list of (key, bytes, ev0, ev1) while profiling
 

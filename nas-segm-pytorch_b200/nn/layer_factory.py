@@ -101,9 +101,10 @@ class InvertedResidual(nn.Module):
         x = _entry(x)
         c = self.conv
         y = Fn.conv_unit(x, c[0].weight, c[1], ks=1, act=ACT_RELU6)
+        # depthwise + projection: one fused kernel at inference (Fn.sep_unit), two units in training.
         # `sole`: the expansion feeds the depthwise convolution only, which feeds the projection only
-        y = Fn.conv_unit(y, c[3].weight, c[4], ks=3, stride=self.stride, pad=1, act=ACT_RELU6, dw=True, sole=True)
-        return Fn.conv_unit(y, c[6].weight, c[7], ks=1, act=ACT_NONE, res=x if self.use_res_connect else None, sole=True)
+        return Fn.sep_unit(y, c[3].weight, c[4], ACT_RELU6, c[6].weight, c[7], ACT_NONE, ks=3, stride=self.stride, dil=1, pad=1,
+                           res=x if self.use_res_connect else None, sole=(True, True))
 
 
 class Pool(nn.Module):
@@ -176,9 +177,8 @@ class SepConv(nn.Module):
         for idx, blk in enumerate(self.op):
             dwc = blk[0]
             # from the second repeat on, the depthwise conv is the only consumer of the previous repeat's output (`sole`)
-            x = Fn.conv_unit(x, dwc.weight, None, ks=dwc.kernel_size[0], stride=dwc.stride[0], dil=dwc.dilation[0],
-                             pad=dwc.padding[0], dw=True, sole=idx > 0)
-            x = Fn.conv_unit(x, blk[1].weight, blk[2], ks=1, act=ACT_RELU)
+            x = Fn.sep_unit(x, dwc.weight, None, ACT_NONE, blk[1].weight, blk[2], ACT_RELU, ks=dwc.kernel_size[0],
+                            stride=dwc.stride[0], dil=dwc.dilation[0], pad=dwc.padding[0], sole=(idx > 0, False))
         return x
 
 

@@ -287,3 +287,63 @@ def test_bn_backward_fusion_matches_unfused_path():
                 scale = torch.maximum(g2[idx + ".weight"].norm(), g2[idx + ".bias"].norm())
             e = float((g1[k] - g2[k]).norm() / scale.clamp_min(1e-6))
             assert e < 3e-2, (tag, k, e)
+
+
+def test_fused_separable_kernel_matches_two_unit_path():
+    """csrc/sep_tcgen05.cu (depthwise -> folded BN / activation -> tcgen05 pointwise -> epilogue in ONE kernel, inference)
+    against the same modules evaluated as two units (TMA depthwise tile kernel + tcgen05 pointwise kernel) and against torch
+    fp32: InvertedResidual blocks with and without residual, SepConv 3x3 / 5x5 with two repeats, ragged sizes, a channel
+    count that is not a multiple of 64 (144) and more than one 64-channel block (192)."""
+    import copy
+    from nas_segm_b200.nn.layer_factory import OPS, InvertedResidual
+    cfg = nas_segm_b200.config()
+    torch.manual_seed(9)
+    seen = []
+    orig_try = lib.try_call
+
+    def spy_try(name, *a):
+        ok = orig_try(name, *a)
+        if ok:
+            seen.append(name)
+        return ok
+    cases = [("ir", dict(inp=24, oup=24, stride=1, expand_ratio=6), (2, 24, 33, 47)),
+             ("ir", dict(inp=32, oup=32, stride=1, expand_ratio=6), (1, 32, 40, 64)),
+             ("ir", dict(inp=32, oup=16, stride=1, expand_ratio=1), (2, 32, 21, 50)),
+             ("sep_conv_3x3", 48, (2, 48, 37, 29)), ("sep_conv_5x5", 64, (1, 64, 40, 72)), ("sep_conv_5x5", 32, (3, 32, 9, 17))]
+    for kind, arg, shape in cases:
+        m = (InvertedResidual(**arg) if kind == "ir" else OPS[kind](arg, arg, 1, True, repeats=2)).cuda().eval()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.data.uniform_(0.5, 1.5)
+                mod.bias.data.normal_(0, 0.2)
+        x = torch.randn(*shape, device="cuda").to(torch.bfloat16)
+        nas_segm_b200.set_act_dtype(torch.bfloat16)
+        try:
+            outs = []
+            for fused in (True, False):
+                cfg.fused_sep = fused
+                del seen[:]
+                lib.try_call = Fn.try_call = spy_try
+                try:
+                    with torch.no_grad():
+                        outs.append((m(lib.to_nhwc(x.clone())).float(), list(seen)))
+                finally:
+                    lib.try_call = Fn.try_call = orig_try
+        finally:
+            cfg.fused_sep = True
+            nas_segm_b200.set_act_dtype(torch.float32)
+        (yf, calls_f), (yu, calls_u) = outs
+        assert "nasb_sep_unit_infer" in calls_f and "nasb_sep_unit_infer" not in calls_u, (kind, arg)
+        assert calls_f.count("nasb_sep_unit_infer") == (1 if kind == "ir" else 2), (kind, arg)
+        scale = float(yu.abs().max())
+        assert float((yf - yu).abs().max()) <= 2.0 ** -6 * scale, (kind, arg, float((yf - yu).abs().max()) / scale)
+        ref = copy.deepcopy(m)
+        # torch fp32 of the same modules (their nn.Conv2d / BatchNorm2d children are real parameter holders)
+        with torch.no_grad():
+            if kind == "ir":
+                yr = ref.conv(x.float()) + (x.float() if ref.use_res_connect else 0)
+            else:
+                yr = ref.op(x.float())
+        assert float((yf - yr).abs().max()) <= 3e-2 * float(yr.abs().max()), (kind, arg)

@@ -1,0 +1,5 @@
+#!/bin/bash
+O=gpurun_out/c11; mkdir -p $O
+timeout -k 10 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo "bench n2 rc=$?" >> $O/rc.txt
+timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 > $O/ref_n2.json 2> $O/ref_n2.err; echo "ref n2 rc=$?" >> $O/rc.txt
+cat $O/rc.txt
