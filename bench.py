@@ -439,16 +439,25 @@ def metric_numbers(dev):
     cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
 
     def timed(fns, iters=30):
+        """Average device time per call: the calls are captured into ONE CUDA graph (one pass over the rotating buffer sets)
+        and the graph is replayed -- eagerly a 25 us kernel would be timed at the ~20 us the host needs to issue it."""
         for f in fns:
             f()
         torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for f in fns:
+                f()
+        reps = max(iters // len(fns), 2)
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            fns[i % len(fns)]()
+        for _ in range(reps):
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
+        return e0.elapsed_time(e1) / (reps * len(fns))
 
     ms = timed([lambda p=p, q=q: Fn.confmat_labels(p, q, C, cm) for p, q in sets])
     res["confmat_labels_ms_%dMpx_C%d" % (n >> 20, C)] = ms
@@ -963,7 +972,7 @@ def main():
             # confusion-matrix kernels vs HBM roofline, Cython fast_cm beside them
             extras["metric"] = child(["--metric-only"], 180)
             # BASELINE config 4 through engine.search (task0 + task1, TaskPerformer, per-candidate rebuild + capture)
-            sb = child(["--workload", "search", "--steps", "2", "--warmup", "1"], 420)
+            sb = child(["--workload", "search", "--steps", "3", "--warmup", "1"], 480)
             sb.pop("config", None)
             extras["search_loop"] = sb
         finally:
@@ -976,7 +985,7 @@ def main():
         seg = optim_enc = optim_dec = graphed = None
         torch.cuda.empty_cache()
         try:
-            sb = search_numbers(a, dev, rank, world, rounds=2, warm_rounds=1, n_task0=a.n_task0, task1_iters=a.task1_iters,
+            sb = search_numbers(a, dev, rank, world, rounds=3, warm_rounds=1, n_task0=a.n_task0, task1_iters=a.task1_iters,
                                 val_images=a.val_images)
             sb.pop("recipe", None)
             extras["search_loop"] = sb

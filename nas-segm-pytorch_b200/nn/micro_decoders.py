@@ -184,14 +184,22 @@ class MicroDecoder(nn.Module):
     def forward(self, x):
         x = [getattr(self, "adapt{}".format(i + 1))(Fn.as_act(f)) for i, f in enumerate(x)]
         aux_outs = []
+        run2 = Fn.lib.branch_streams.run2
+        pending, prev = None, None  # the auxiliary head of cell k runs next to cell k+1 (the last one next to the main head)
         for cell, head, conn in zip(self.cells, self.aux_clfs, self.conns):
-            cell_out = cell(x[conn[0]], x[conn[1]])
+            if pending is None:
+                cell_out = cell(x[conn[0]], x[conn[1]])
+            else:
+                cell_out, aux = run2(lambda: cell(x[conn[0]], x[conn[1]]), pending, (prev,))
+                aux_outs.append(aux)
             x.append(cell_out)
-            a = cell_out
-            if self.aux_cell:
-                a = head.aux_cell(a)
-            aux_outs.append(clf3x3(head.aux_clf, a))
-        out = _head(self.pre_clf, self.conv_clf, collect_all(x, self.collect_inds, relu=True))
+            pending = (lambda h=head, c=cell_out: clf3x3(h.aux_clf, h.aux_cell(c) if self.aux_cell else c))
+            prev = cell_out
+        main = (lambda: _head(self.pre_clf, self.conv_clf, collect_all(x, self.collect_inds, relu=True)))
+        if pending is None:
+            return main(), aux_outs
+        out, aux = run2(main, pending, (prev,))
+        aux_outs.append(aux)
         return out, aux_outs
 
 

@@ -205,6 +205,32 @@ def _():
         report("dwconv_dgrad_strided_tile[%dx%dx%dx%d k%d]" % (n, h, w, c, ks), timeit(sets), nb)
 
 
+@case("sepconv")
+def _():
+    """The fused separable inference kernel (csrc/sep_tcgen05.cu) next to the two kernels it replaces (TMA depthwise tile
+    kernel + tcgen05 pointwise kernel), eval-mode constants, batch 8 and batch 1."""
+    for n, h, w, c, cout, ks in [(8, 256, 512, 144, 24, 3), (8, 128, 256, 192, 32, 3), (8, 512, 1024, 32, 16, 3), (8, 128, 256, 64, 64, 5),
+                                 (8, 256, 512, 32, 32, 3), (1, 256, 512, 144, 24, 3), (1, 128, 256, 64, 64, 5)]:
+        pad = (ks - 1) // 2
+        nb = n * h * w * (c + cout) * 2
+        fused, two = [], []
+        for _ in range(nsets(nb + n * h * w * c * 4)):
+            x, t, y = act(n, c, h, w), act(n, c, h, w, fill=None), act(n, cout, h, w, fill=None)
+            dww = torch.randn(c, 1, ks, ks, device=DEV)
+            ms, mb, os_, ob = fvec(c), fvec(c, -0.5, 0.5), fvec(cout), fvec(cout, -0.5, 0.5)
+            wp = torch.randn(cout * ((c + 7) // 8 * 8), device=DEV).to(torch.bfloat16)
+            fused.append(lambda x=x, y=y, dww=dww, ms=ms, mb=mb, os_=os_, ob=ob, wp=wp: call(
+                "nasb_sepconv_tc_fwd", ref(desc(x)), ptr(dww), ks, 1, 1, pad, ptr(ms), ptr(mb), 2, ptr(wp), cout, ptr(os_), ptr(ob), 0,
+                None, ref(desc(y))))
+
+            def both(x=x, t=t, y=y, dww=dww, ms=ms, mb=mb, os_=os_, ob=ob, wp=wp):
+                call("nasb_dwconv_tile", ref(desc(x)), ptr(dww), ks, 1, 1, pad, 0, ptr(ms), ptr(mb), 2, ref(desc(t)), None)
+                call("nasb_pw_tc_fwd", ref(desc(t)), ptr(wp), cout, ptr(os_), ptr(ob), 0, None, ref(desc(y)), None)
+            two.append(both)
+        report("sepconv[%dx%dx%d %d->%d k%d fused]" % (n, h, w, c, cout, ks), timeit(fused), nb)
+        report("sepconv[%dx%dx%d %d->%d k%d dw+pw]" % (n, h, w, c, cout, ks), timeit(two), nb)
+
+
 @case("dgrad_gated")
 def _():
     """Data gradients with the NasbGate epilogue (gate + the producer's BN-backward reductions) next to the plain ones."""
