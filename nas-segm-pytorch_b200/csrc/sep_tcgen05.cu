@@ -281,7 +281,12 @@ using namespace nasb;
 extern "C" int nasb_sepconv_tc_supported(int C, int N, int ks, int stride, int dil, int pad) {
     if ((ks != 3 && ks != 5) || stride != 1 || dil != 1 || pad != (ks - 1) / 2) return 0;
     if (C < 8 || (C % 8) || N < 8 || (N % 8) || N > 64 || C > 1024) return 0;
-    return sep_smem((C + 63) / 64, ks) <= 200 * 1024 ? 1 : 0;
+    // The depthwise stage works on whole 64-channel blocks: a partly filled last block is computed in full.  Measured on a
+    // B200 (profiles/r2_sepconv_kbench.txt): -12 % vs the two kernels at C = 192 and C = 64, +16 % at C = 144 (33 % padding),
+    // +45...65 % at C = 32 (100 % padding) -- so the fused kernel takes the shapes with at most 15 % padding.
+    const int nkb = (C + 63) / 64;
+    if ((nkb * 64 - C) * 100 > 15 * C) return 0;
+    return sep_smem(nkb, ks) <= 200 * 1024 ? 1 : 0;
 }
 
 extern "C" int nasb_sepconv_tc_fwd(const NasbTensor *x, const float *dw_weight, int ks, int stride, int dil, int pad,

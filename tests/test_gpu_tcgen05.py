@@ -306,10 +306,11 @@ def test_fused_separable_kernel_matches_two_unit_path():
         if ok:
             seen.append(name)
         return ok
-    cases = [("ir", dict(inp=24, oup=24, stride=1, expand_ratio=6), (2, 24, 33, 47)),
-             ("ir", dict(inp=32, oup=32, stride=1, expand_ratio=6), (1, 32, 40, 64)),
-             ("ir", dict(inp=32, oup=16, stride=1, expand_ratio=1), (2, 32, 21, 50)),
-             ("sep_conv_3x3", 48, (2, 48, 37, 29)), ("sep_conv_5x5", 64, (1, 64, 40, 72)), ("sep_conv_5x5", 32, (3, 32, 9, 17))]
+    # (the kernel takes channel counts with <= 15 % padding to whole 64-channel blocks: 56, 64, 120, 128, 192, ...)
+    cases = [("ir", dict(inp=32, oup=32, stride=1, expand_ratio=6), (1, 32, 40, 64)),     # 192 channels, residual
+             ("ir", dict(inp=32, oup=16, stride=1, expand_ratio=2), (2, 32, 21, 50)),     # 64 channels, no residual
+             ("ir", dict(inp=40, oup=40, stride=1, expand_ratio=3), (2, 40, 33, 47)),     # 120 channels: partial last block
+             ("sep_conv_3x3", 56, (2, 56, 37, 29)), ("sep_conv_5x5", 64, (1, 64, 40, 72)), ("sep_conv_5x5", 64, (3, 64, 9, 17))]
     for kind, arg, shape in cases:
         m = (InvertedResidual(**arg) if kind == "ir" else OPS[kind](arg, arg, 1, True, repeats=2)).cuda().eval()
         for mod in m.modules():
