@@ -23,7 +23,7 @@ class _Config:
         import torch
         self.act_dtype = torch.float32
         self.use_tcgen05 = True  # bf16 pointwise convolutions on the tensor cores when shapes allow
-        self.graph_warmup = 3  # eager iterations before an engine loop captures its CUDA graph
+        self.graph_warmup = 1  # eager iterations before an engine loop captures its CUDA graph
         self.cuda_graphs = False  # engine loops replay one captured CUDA graph per iteration (graphs.StepGraph)
         # training-BN statistics inside the depthwise tile kernel (per-thread register partials over the persistent loop,
         # one shared-memory merge per CTA): +15-25 % on the kernel, cheaper than the separate pass that re-reads z

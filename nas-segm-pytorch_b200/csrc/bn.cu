@@ -10,6 +10,7 @@ namespace nasb {
 
 __global__ void bn_fold_kernel(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int C,
                                float *scale, float *shift) {
+    pdl_sync();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -62,6 +63,7 @@ __device__ __forceinline__ void colreduce2(long long r0, long long r1, int C, do
 template <typename T, int V>
 __global__ void __launch_bounds__(256) bn_sums_vec_kernel(const T *z, int cs, long long P, int C, double *ws,
                                                           long long rows_per_cta) {
+    pdl_sync();
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
     colreduce2<V>(r0, r1, C, ws, [&](long long m, int c0, float (&a)[V], float (&b)[V]) {
         float v[V];
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_sums_vec_kernel(const T *dy, in
                                                                  const float *rstd, const float *gamma, const float *beta,
                                                                  int act, long long P, int C, double *ws,
                                                                  long long rows_per_cta) {
+    pdl_sync();
     extern __shared__ float red_sm[];  // [2][PL][C]
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
     const int CV = C / V, PL = blockDim.x / CV;
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_sums_vec_kernel(const T *dy, in
 template <typename T>
 __global__ void __launch_bounds__(256) bn_sums_kernel(const T *z, int cs, long long P, int C, double *ws,
                                                       long long rows_per_cta) {
+    pdl_sync();
     __shared__ double r1[256], r2[256];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const long long r0 = (long long)blockIdx.y * rows_per_cta, rend = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
@@ -191,6 +195,7 @@ __global__ void bn_stats_finalize_kernel(const double *ws, long long P, int C, c
                                          float eps, float momentum, float *running_mean, float *running_var,
                                          float *save_mean, float *save_rstd, float *scale, float *shift,
                                          long long *num_batches_tracked) {
+    pdl_sync();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;  // nn.BatchNorm2d's step counter, no extra launch
@@ -214,6 +219,7 @@ __global__ void bn_stats_finalize_kernel(const double *ws, long long P, int C, c
 template <typename T, int V>
 __global__ void __launch_bounds__(256) affine_act_kernel(const T *z, int z_cs, const float *scale, const float *shift, int act,
                                                          T *y, int y_cs, long long P, int C) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = P * CV;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -238,6 +244,7 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs
                                                           const float *mean, const float *rstd, int act,
                                                           const float *gamma, const float *beta, long long P, int C,
                                                           double *ws, long long rows_per_cta) {
+    pdl_sync();
     __shared__ double r1[256], r2[256];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const long long r0 = (long long)blockIdx.y * rows_per_cta, rend = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const T *dy, int dy_cs
 
 // dgamma += sum g*xhat ; dbeta += sum g ; coef[0..C) = mean g ; coef[C..2C) = mean g*xhat  (fp32, aliased after ws)
 __global__ void bn_bwd_finalize_kernel(const double *ws, long long P, int C, float *dgamma, float *dbeta, float *coef) {
+    pdl_sync();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s1 = ws[c], s2 = ws[C + c];
@@ -286,6 +294,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, 
                                                         const float *scale, const float *shift,
                                                         const float *coef, int training, T *dz, int dz_cs, long long P,
                                                         int C) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = P * CV;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -323,6 +332,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dz_kernel(const T *dy, int dy_cs, 
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 4) affine_act_fixed_kernel(const T *z, int z_cs, const float *scale, const float *shift,
                                                                int act, T *y, int y_cs, long long P, int C) {
+    pdl_sync();
     const int CV = C / V, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * V;
     if (pl >= PL) return;
@@ -354,6 +364,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_dz_fixed_kernel(const T *dy, in
                                                                  const float *scale, const float *shift, const float *mean,
                                                                  const float *rstd, const float *coef, int act, T *dz, int dz_cs,
                                                                  long long P, int C) {
+    pdl_sync();
     const int CV = C / V, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * V;
     if (pl >= PL) return;
@@ -449,6 +460,7 @@ template <bool DESC, bool COOP>
 __global__ void __launch_bounds__(256, 4) affine_act_bf16_kernel(const bf16 *z, int z_cs, const float *scale, const float *shift,
                                                                  int act, bf16 *y, int y_cs, long long P, int C, const BnFin fin,
                                                                  const bf16 *res, int res_cs) {
+    pdl_sync();
     __shared__ float cst[COOP ? 2 : 1][COOP ? BN_MAXC : 1];
     const int CV = C / 8, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
@@ -565,6 +577,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_sums_bf16_kernel(const bf16 *dy
                                                                   const float *k_s, const float *k_b, const float *mu,
                                                                   const float *rs, float lo, float hi, long long P, int C,
                                                                   double *ws, long long rows_per_cta) {
+    pdl_sync();
     extern __shared__ float red_sm[];  // [2][PL][C]
     const long long e1 = P - (long long)blockIdx.x * rows_per_cta;  // this CTA's slab is [e0, e1), counted from the end
     const long long e0 = e1 - rows_per_cta > 0 ? e1 - rows_per_cta : 0;
@@ -631,6 +644,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_dz_bf16_kernel(const bf16 *dy, 
                                                                 const float *mean, const float *rstd, float *dgamma,
                                                                 float *dbeta, float lo, float hi, bf16 *dz, int dz_cs,
                                                                 long long P, int C) {
+    pdl_sync();
     __shared__ float cst[COOP ? 4 : 1][COOP ? BN_MAXC : 1];
     const int CV = C / 8, PL = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV, c0 = cv * 8;
@@ -784,7 +798,7 @@ using namespace nasb;
 extern "C" int nasb_bn_fold(const float *gamma, const float *beta, const float *mean, const float *var, float eps, int C,
                             float *scale, float *shift, void *stream) {
     if (!mean || !var || !scale || !shift || C <= 0) return NASB_ERR_BAD_ARG;
-    bn_fold_kernel<<<cdiv(C, 128), 128, 0, ST>>>(gamma, beta, mean, var, eps, C, scale, shift);
+    nasb::launch_pdl((bn_fold_kernel), dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)(ST), gamma, beta, mean, var, eps, C, scale, shift);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -807,18 +821,18 @@ extern "C" int nasb_bn_stats(const NasbTensor *z, const float *gamma, const floa
     int blocks;
     size_t smem;
     if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_reduce_cfg<8>(C, P, blocks, rows, smem)) {
-        bn_sums_vec_kernel<bf16, 8><<<blocks, 256, smem, ST>>>((const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
+        nasb::launch_pdl((bn_sums_vec_kernel<bf16, 8>), dim3(blocks), dim3(256), smem, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
     } else if (z->dtype == NASB_F32 && vec_ok(*z, 4) && vec_reduce_cfg<4>(C, P, blocks, rows, smem)) {
-        bn_sums_vec_kernel<float, 4><<<blocks, 256, smem, ST>>>((const float *)z->ptr, z->cstride, P, C, ws, rows);
+        nasb::launch_pdl((bn_sums_vec_kernel<float, 4>), dim3(blocks), dim3(256), smem, (cudaStream_t)(ST), (const float *)z->ptr, z->cstride, P, C, ws, rows);
     } else {
         slab_grid(P, C, grid, rows);
         if (z->dtype == NASB_BF16)
-            bn_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
+            nasb::launch_pdl((bn_sums_kernel<bf16>), dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, P, C, ws, rows);
         else
-            bn_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)z->ptr, z->cstride, P, C, ws, rows);
+            nasb::launch_pdl((bn_sums_kernel<float>), dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)(ST), (const float *)z->ptr, z->cstride, P, C, ws, rows);
     }
     NASB_CHECK_LAUNCH();
-    bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, gamma, beta, eps, momentum, running_mean, running_var,
+    nasb::launch_pdl((bn_stats_finalize_kernel), dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)(ST), ws, P, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                            save_mean, save_rstd, scale, shift, num_batches_tracked);
     NASB_CHECK_LAUNCH();
     return 0;
@@ -829,7 +843,7 @@ extern "C" int nasb_bn_finalize(const double *sums, long long P, int C, const fl
                                 float momentum, float *running_mean, float *running_var, float *save_mean, float *save_rstd,
                                 float *scale, float *shift, long long *num_batches_tracked, void *stream) {
     if (!sums || !scale || !shift || P <= 0 || C <= 0) return NASB_ERR_BAD_ARG;
-    bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(sums, P, C, gamma, beta, eps, momentum, running_mean, running_var,
+    nasb::launch_pdl((bn_stats_finalize_kernel), dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)(ST), sums, P, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                            save_mean, save_rstd, scale, shift, num_batches_tracked);
     NASB_CHECK_LAUNCH();
     return 0;
@@ -847,13 +861,13 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
         int blocks;
         if (z->dtype == NASB_BF16 && vec_ok(*z, 8) && vec_ok(*y, 8) && fixed_cfg(C, 8, P, blocks)) {
             // descending: z was just written front-to-back by the convolution, its tail is still in L2
-            affine_act_bf16_kernel<true, false><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+            nasb::launch_pdl((affine_act_bf16_kernel<true, false>), dim3(blocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, scale, shift, act,
                                                                  (bf16 *)y->ptr, y->cstride, P, C, BnFin{}, nullptr, 0);
             NASB_CHECK_LAUNCH();
             return 0;
         }
         if (z->dtype == NASB_F32 && vec_ok(*z, 4) && vec_ok(*y, 4) && fixed_cfg(C, 4, P, blocks)) {
-            affine_act_fixed_kernel<float, 4><<<blocks, 256, 0, ST>>>((const float *)z->ptr, z->cstride, scale, shift, act,
+            nasb::launch_pdl((affine_act_fixed_kernel<float, 4>), dim3(blocks), dim3(256), 0, (cudaStream_t)(ST), (const float *)z->ptr, z->cstride, scale, shift, act,
                                                                       (float *)y->ptr, y->cstride, P, C);
             NASB_CHECK_LAUNCH();
             return 0;
@@ -861,17 +875,17 @@ extern "C" int nasb_affine_act(const NasbTensor *z, const float *scale, const fl
     }
     if (z->dtype == NASB_BF16) {
         if (vec_ok(*z, 8) && vec_ok(*y, 8))
-            affine_act_kernel<bf16, 8><<<ew_grid(P * (C / 8)), 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+            nasb::launch_pdl((affine_act_kernel<bf16, 8>), dim3(ew_grid(P * (C / 8))), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, scale, shift, act,
                                                                              (bf16 *)y->ptr, y->cstride, P, C);
         else
-            affine_act_kernel<bf16, 1><<<ew_grid(P * C), 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, scale, shift, act,
+            nasb::launch_pdl((affine_act_kernel<bf16, 1>), dim3(ew_grid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, scale, shift, act,
                                                                        (bf16 *)y->ptr, y->cstride, P, C);
     } else {
         if (vec_ok(*z, 4) && vec_ok(*y, 4))
-            affine_act_kernel<float, 4><<<ew_grid(P * (C / 4)), 256, 0, ST>>>((const float *)z->ptr, z->cstride, scale, shift, act,
+            nasb::launch_pdl((affine_act_kernel<float, 4>), dim3(ew_grid(P * (C / 4))), dim3(256), 0, (cudaStream_t)(ST), (const float *)z->ptr, z->cstride, scale, shift, act,
                                                                               (float *)y->ptr, y->cstride, P, C);
         else
-            affine_act_kernel<float, 1><<<ew_grid(P * C), 256, 0, ST>>>((const float *)z->ptr, z->cstride, scale, shift, act,
+            nasb::launch_pdl((affine_act_kernel<float, 1>), dim3(ew_grid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)z->ptr, z->cstride, scale, shift, act,
                                                                         (float *)y->ptr, y->cstride, P, C);
     }
     NASB_CHECK_LAUNCH();
@@ -894,11 +908,11 @@ extern "C" int nasb_bn_finalize_affine_act(const double *sums, long long P, cons
         fixed_cfg(C, 8, P, blocks)) {
         BnFin f{sums, P, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift, num_batches_tracked};
         if (bn_coop(P, C))
-            affine_act_bf16_kernel<true, true><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act,
+            nasb::launch_pdl((affine_act_bf16_kernel<true, true>), dim3(blocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act,
                                                                        (bf16 *)y->ptr, y->cstride, P, C, f,
                                                                        res ? (const bf16 *)res->ptr : nullptr, res ? res->cstride : 0);
         else
-            affine_act_bf16_kernel<true, false><<<blocks, 256, 0, ST>>>((const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act,
+            nasb::launch_pdl((affine_act_bf16_kernel<true, false>), dim3(blocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)z->ptr, z->cstride, nullptr, nullptr, act,
                                                                         (bf16 *)y->ptr, y->cstride, P, C, f,
                                                                         res ? (const bf16 *)res->ptr : nullptr, res ? res->cstride : 0);
         NASB_CHECK_LAUNCH();
@@ -914,6 +928,7 @@ extern "C" int nasb_bn_finalize_affine_act(const double *sums, long long P, cons
 
 // raw reductions of a gated data-gradient epilogue (S1 = sum g, S2 = sum g*z) -> the centred form the dz pass consumes
 __global__ void bn_bwd_centre_kernel(const double *raw, const float *mu, const float *rs, int C, double *ws) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double s1 = raw[c], s2 = raw[C + c];
@@ -937,14 +952,14 @@ extern "C" int nasb_bn_bwd_from_sums(const NasbTensor *dy, const NasbTensor *z, 
     if (!vec_ok(*dy, 8) || !vec_ok(*z, 8) || !vec_ok(*dz, 8) || !fixed_cfg(C, 8, P, dzblocks)) return NASB_ERR_UNSUPPORTED;
     double *ws = (double *)workspace;
     const float lo = act == NASB_ACT_NONE ? -INFINITY : 0.f, hi = act == NASB_ACT_RELU6 ? 6.f : INFINITY;
-    bn_bwd_centre_kernel<<<cdiv(C, 128), 128, 0, ST>>>(raw_sums, save_mean, save_rstd, C, ws);
+    nasb::launch_pdl((bn_bwd_centre_kernel), dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)(ST), raw_sums, save_mean, save_rstd, C, ws);
     NASB_CHECK_LAUNCH();
     if (bn_coop(P, C))
-        bn_bwd_dz_bf16_kernel<true><<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride, ws,
+        nasb::launch_pdl((bn_bwd_dz_bf16_kernel<true>), dim3(dzblocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride, ws,
                                                               scale, shift, save_mean, save_rstd, dgamma, dbeta, lo, hi,
                                                               (bf16 *)dz->ptr, dz->cstride, P, C);
     else
-        bn_bwd_dz_bf16_kernel<false><<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride, ws,
+        nasb::launch_pdl((bn_bwd_dz_bf16_kernel<false>), dim3(dzblocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride, ws,
                                                                scale, shift, save_mean, save_rstd, dgamma, dbeta, lo, hi,
                                                                (bf16 *)dz->ptr, dz->cstride, P, C);
     NASB_CHECK_LAUNCH();
@@ -983,15 +998,15 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
             vec_reduce_cfg<8>(C, P, blocks, rows, smem) && fixed_cfg(C, 8, P, dzblocks)) {
             cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST);
             if (e != cudaSuccess) return (int)e;
-            bn_bwd_sums_bf16_kernel<<<blocks, 256, smem, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
+            nasb::launch_pdl((bn_bwd_sums_bf16_kernel), dim3(blocks), dim3(256), smem, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
                                                                scale, shift, save_mean, save_rstd, lo, hi, P, C, ws, rows);
             NASB_CHECK_LAUNCH();
             if (bn_coop(P, C))
-                bn_bwd_dz_bf16_kernel<true><<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
+                nasb::launch_pdl((bn_bwd_dz_bf16_kernel<true>), dim3(dzblocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
                                                                       ws, scale, shift, save_mean, save_rstd, dgamma, dbeta, lo, hi,
                                                                       (bf16 *)dz->ptr, dz->cstride, P, C);
             else
-                bn_bwd_dz_bf16_kernel<false><<<dzblocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
+                nasb::launch_pdl((bn_bwd_dz_bf16_kernel<false>), dim3(dzblocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)z->ptr, z->cstride,
                                                                        ws, scale, shift, save_mean, save_rstd, dgamma, dbeta, lo, hi,
                                                                        (bf16 *)dz->ptr, dz->cstride, P, C);
             NASB_CHECK_LAUNCH();
@@ -1007,41 +1022,41 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
         size_t smem;
         const NasbTensor *yz = training ? z : y;
         if (dy->dtype == NASB_BF16 && vec_ok(*dy, 8) && vec_ok(*yz, 8) && vec_reduce_cfg<8>(C, P, blocks, rows, smem)) {
-            bn_bwd_sums_vec_kernel<bf16, 8><<<blocks, 256, smem, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)yz->ptr,
+            nasb::launch_pdl((bn_bwd_sums_vec_kernel<bf16, 8>), dim3(blocks), dim3(256), smem, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)yz->ptr,
                                                                        yz->cstride, training, scale, shift, save_mean,
                                                                        save_rstd, gamma, beta, act, P, C, ws, rows);
         } else if (dy->dtype == NASB_F32 && vec_ok(*dy, 4) && vec_ok(*yz, 4) && vec_reduce_cfg<4>(C, P, blocks, rows, smem)) {
-            bn_bwd_sums_vec_kernel<float, 4><<<blocks, 256, smem, ST>>>((const float *)dy->ptr, dy->cstride,
+            nasb::launch_pdl((bn_bwd_sums_vec_kernel<float, 4>), dim3(blocks), dim3(256), smem, (cudaStream_t)(ST), (const float *)dy->ptr, dy->cstride,
                                                                         (const float *)yz->ptr, yz->cstride, training, scale,
                                                                         shift, save_mean, save_rstd, gamma, beta, act, P, C, ws,
                                                                         rows);
         } else {
         slab_grid(P, C, grid, rows);
         if (dy->dtype == NASB_BF16)
-            bn_bwd_sums_kernel<bf16><<<grid, dim3(32, 8), 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
+            nasb::launch_pdl((bn_bwd_sums_kernel<bf16>), dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
                                                                    y->cstride, (const bf16 *)zp, zcs, scale, shift, save_mean, save_rstd, act,
                                                                    gamma, beta, P, C, ws, rows);
         else
-            bn_bwd_sums_kernel<float><<<grid, dim3(32, 8), 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
+            nasb::launch_pdl((bn_bwd_sums_kernel<float>), dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)(ST), (const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
                                                                     y->cstride, (const float *)zp, zcs, scale, shift, save_mean, save_rstd, act,
                                                                     gamma, beta, P, C, ws, rows);
         }
         NASB_CHECK_LAUNCH();
-        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(ws, P, C, dgamma, dbeta, coef);
+        nasb::launch_pdl((bn_bwd_finalize_kernel), dim3(cdiv(C, 128)), dim3(128), 0, (cudaStream_t)(ST), ws, P, C, dgamma, dbeta, coef);
         NASB_CHECK_LAUNCH();
     }
     {
         int blocks;
         const NasbTensor *yz = training ? z : y;
         if (dy->dtype == NASB_BF16 && vec_ok(*dy, 8) && vec_ok(*yz, 8) && vec_ok(*dz, 8) && fixed_cfg(C, 8, P, blocks)) {
-            bn_bwd_dz_fixed_kernel<bf16, 8><<<blocks, 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)yz->ptr,
+            nasb::launch_pdl((bn_bwd_dz_fixed_kernel<bf16, 8>), dim3(blocks), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)yz->ptr,
                                                                     yz->cstride, training, scale, shift, save_mean, save_rstd,
                                                                     coef, act, (bf16 *)dz->ptr, dz->cstride, P, C);
             NASB_CHECK_LAUNCH();
             return 0;
         }
         if (dy->dtype == NASB_F32 && vec_ok(*dy, 4) && vec_ok(*yz, 4) && vec_ok(*dz, 4) && fixed_cfg(C, 4, P, blocks)) {
-            bn_bwd_dz_fixed_kernel<float, 4><<<blocks, 256, 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)yz->ptr,
+            nasb::launch_pdl((bn_bwd_dz_fixed_kernel<float, 4>), dim3(blocks), dim3(256), 0, (cudaStream_t)(ST), (const float *)dy->ptr, dy->cstride, (const float *)yz->ptr,
                                                                      yz->cstride, training, scale, shift, save_mean, save_rstd,
                                                                      coef, act, (float *)dz->ptr, dz->cstride, P, C);
             NASB_CHECK_LAUNCH();
@@ -1050,21 +1065,21 @@ extern "C" int nasb_bn_act_bwd(const NasbTensor *dy, const NasbTensor *y, const 
     }
     if (dy->dtype == NASB_BF16) {
         if (vec_ok(*dy, 8) && vec_ok(*y, 8) && vec_ok(*dz, 8) && (!z || vec_ok(*z, 8)))
-            bn_bwd_dz_kernel<bf16, 8><<<ew_grid(P * (C / 8)), 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
+            nasb::launch_pdl((bn_bwd_dz_kernel<bf16, 8>), dim3(ew_grid(P * (C / 8))), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
                                                                             y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, shift, coef,
                                                                             training, (bf16 *)dz->ptr, dz->cstride, P, C);
         else
-            bn_bwd_dz_kernel<bf16, 1><<<ew_grid(P * C), 256, 0, ST>>>((const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
+            nasb::launch_pdl((bn_bwd_dz_kernel<bf16, 1>), dim3(ew_grid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)dy->ptr, dy->cstride, (const bf16 *)y->ptr,
                                                                       y->cstride, (const bf16 *)zp, zcs, save_mean, save_rstd, act, scale, shift, coef,
                                                                       training, (bf16 *)dz->ptr, dz->cstride, P, C);
     } else {
         if (vec_ok(*dy, 4) && vec_ok(*y, 4) && vec_ok(*dz, 4) && (!z || vec_ok(*z, 4)))
-            bn_bwd_dz_kernel<float, 4><<<ew_grid(P * (C / 4)), 256, 0, ST>>>((const float *)dy->ptr, dy->cstride,
+            nasb::launch_pdl((bn_bwd_dz_kernel<float, 4>), dim3(ew_grid(P * (C / 4))), dim3(256), 0, (cudaStream_t)(ST), (const float *)dy->ptr, dy->cstride,
                                                                              (const float *)y->ptr, y->cstride, (const float *)zp, zcs, save_mean,
                                                                              save_rstd, act, scale, shift, coef, training, (float *)dz->ptr,
                                                                              dz->cstride, P, C);
         else
-            bn_bwd_dz_kernel<float, 1><<<ew_grid(P * C), 256, 0, ST>>>((const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
+            nasb::launch_pdl((bn_bwd_dz_kernel<float, 1>), dim3(ew_grid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)dy->ptr, dy->cstride, (const float *)y->ptr,
                                                                        y->cstride, (const float *)zp, zcs, save_mean, save_rstd, act, scale, shift, coef,
                                                                        training, (float *)dz->ptr, dz->cstride, P, C);
     }

@@ -14,7 +14,48 @@
 
 #define NASB_SM_COUNT 148
 
+#include <stdlib.h>
+#include <utility>
+
 namespace nasb {
+
+// ---- programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_sync(): it lets the NEXT kernel of
+// the stream be scheduled as soon as all CTAs of this one have started (its CTAs then sit in griddepcontrol.wait), and waits
+// itself until the previous kernel has completed and its writes are visible.  Nothing is read before that wait, so the
+// data dependency is unchanged; what disappears is the launch latency and ramp-up between the ~700 (training iteration) /
+// ~1300 (NAS task-0 iteration) dependent launches of a captured graph.  NASB_PDL=0 launches without the attribute.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("NASB_PDL") ? atoi(getenv("NASB_PDL")) : 1;
+    return v != 0;
+}
+// A kernel launched with the attribute becomes resident while its predecessor drains: its CTAs hold shared memory and
+// register-file space without working, which costs more than the launch gap it hides once the grid is large (the slots are
+// taken from kernels of the concurrent weight-gradient / branch streams, and a capped persistent grid gets packed onto the SMs
+// that happened to free first).  So only grids of at most NASB_PDL_MAX_CTAS CTAs ask for it.
+inline long long pdl_max_ctas() {
+    static long long v = -1;
+    if (v < 0) v = getenv("NASB_PDL_MAX_CTAS") ? atoll(getenv("NASB_PDL_MAX_CTAS")) : 1184;
+    return v;
+}
+template <typename... KA, typename... A>
+inline void launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_enabled() && (long long)grid.x * grid.y * grid.z <= pdl_max_ctas()) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 

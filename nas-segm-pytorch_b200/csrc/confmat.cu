@@ -25,6 +25,7 @@ __device__ __forceinline__ void cm_count(int *hist, long long *cm, int C, bool u
 
 __global__ void __launch_bounds__(256) confmat_labels_kernel(const uint8_t *pred, const uint8_t *gt, long long n, int C,
                                                              long long *cm) {
+    pdl_sync();
     extern __shared__ int hist[];
     const bool use_smem = C <= CM_SMEM_MAXC;
     if (use_smem) {
@@ -63,6 +64,7 @@ constexpr int CM_WARP_MAXC = 32;
 
 __global__ void __launch_bounds__(256) confmat_labels_warp_kernel(const uint8_t *pred, const uint8_t *gt, long long nvec, int C,
                                                                   long long *cm) {
+    pdl_sync();
     extern __shared__ int hist[];  // [8 warps][C*C]
     const int CC = C * C;
     for (int i = threadIdx.x; i < 8 * CC; i += blockDim.x) hist[i] = 0;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) confmat_labels_warp_kernel(const uint8_t 
 template <typename T>
 __global__ void __launch_bounds__(256) confmat_logits_kernel(const T *x, int cs, int N, int h, int w, int C, const uint8_t *gt,
                                                              int H, int W, int n_classes, long long *cm, float rh, float rw) {
+    pdl_sync();
     extern __shared__ int hist[];
     const bool use_smem = n_classes <= CM_SMEM_MAXC;
     if (use_smem) {
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(256) confmat_logits_kernel(const T *x, int cs,
 }
 
 __global__ void ius_accs_kernel(const long long *cm, int C, double *iu, long long *npx, double *accs) {
+    pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C) return;
     unsigned int pi = 0, gi = 0;
@@ -196,7 +200,7 @@ extern "C" int nasb_confmat_labels(const uint8_t *pred, const uint8_t *gt, long 
         long long blocks = (nvec + 1023) / 1024, cap = (long long)NASB_SM_COUNT * 3;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        confmat_labels_warp_kernel<<<(int)blocks, 256, (size_t)8 * n_classes * n_classes * sizeof(int), ST>>>(pred, gt, nvec, n_classes, cm);
+        nasb::launch_pdl((confmat_labels_warp_kernel), dim3((int)blocks), dim3(256), (size_t)8 * n_classes * n_classes * sizeof(int), (cudaStream_t)(ST), pred, gt, nvec, n_classes, cm);
         NASB_CHECK_LAUNCH();
         pred += nvec * 16, gt += nvec * 16, n -= nvec * 16;
         if (n == 0) return 0;
@@ -206,7 +210,7 @@ extern "C" int nasb_confmat_labels(const uint8_t *pred, const uint8_t *gt, long 
     long long cap = (long long)NASB_SM_COUNT * 8;
     if (blocks > cap) blocks = cap;
     size_t smem = n_classes <= CM_SMEM_MAXC ? (size_t)n_classes * n_classes * sizeof(int) : 0;
-    confmat_labels_kernel<<<(int)blocks, 256, smem, ST>>>(pred, gt, n, n_classes, cm);
+    nasb::launch_pdl((confmat_labels_kernel), dim3((int)blocks), dim3(256), smem, (cudaStream_t)(ST), pred, gt, n, n_classes, cm);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -222,10 +226,10 @@ extern "C" int nasb_confmat_logits(const NasbTensor *logits, const uint8_t *gt, 
     size_t smem = n_classes <= CM_SMEM_MAXC ? (size_t)n_classes * n_classes * sizeof(int) : 0;
     float rh = (float)logits->h / (float)H, rw = (float)logits->w / (float)W;
     if (logits->dtype == NASB_BF16)
-        confmat_logits_kernel<bf16><<<(int)blocks, 256, smem, ST>>>((const bf16 *)logits->ptr, logits->cstride, logits->n, logits->h,
+        nasb::launch_pdl((confmat_logits_kernel<bf16>), dim3((int)blocks), dim3(256), smem, (cudaStream_t)(ST), (const bf16 *)logits->ptr, logits->cstride, logits->n, logits->h,
                                                                     logits->w, logits->c, gt, H, W, n_classes, cm, rh, rw);
     else
-        confmat_logits_kernel<float><<<(int)blocks, 256, smem, ST>>>((const float *)logits->ptr, logits->cstride, logits->n,
+        nasb::launch_pdl((confmat_logits_kernel<float>), dim3((int)blocks), dim3(256), smem, (cudaStream_t)(ST), (const float *)logits->ptr, logits->cstride, logits->n,
                                                                      logits->h, logits->w, logits->c, gt, H, W, n_classes, cm, rh,
                                                                      rw);
     NASB_CHECK_LAUNCH();
@@ -234,7 +238,7 @@ extern "C" int nasb_confmat_logits(const NasbTensor *logits, const uint8_t *gt, 
 
 extern "C" int nasb_ius_accs(const long long *cm, int n_classes, double *iu, long long *n_pixels, double *accs, void *stream) {
     if (!cm || n_classes <= 0) return NASB_ERR_BAD_ARG;
-    ius_accs_kernel<<<cdiv(n_classes, 64), 64, 0, ST>>>(cm, n_classes, iu, n_pixels, accs);
+    nasb::launch_pdl((ius_accs_kernel), dim3(cdiv(n_classes, 64)), dim3(64), 0, (cudaStream_t)(ST), cm, n_classes, iu, n_pixels, accs);
     NASB_CHECK_LAUNCH();
     return 0;
 }

@@ -144,6 +144,7 @@ constexpr int BM = 128, BK = 16, NT = 256;
 
 template <int BN>
 __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvP p) {
+    pdl_sync();
     constexpr int TX = BN / 4;      // thread columns
     constexpr int TY = NT / TX;     // thread rows
     constexpr int RM = BM / TY;     // output rows per thread (8 for BN=64, 4 for BN=32)
@@ -303,6 +304,7 @@ struct WgradP {
 };
 
 __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const WgradP q) {
+    pdl_sync();
     const ConvP &p = q.c;
     __shared__ __align__(16) float Zs[WP][WB];
     __shared__ __align__(16) float Xs[WP][WB];
@@ -454,10 +456,10 @@ extern "C" int nasb_conv_fwd(const NasbTensor *x0, const NasbTensor *x1, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (p.Nc <= 32) {
         dim3 grid(cdiv(M, BM), cdiv(p.Nc, 32));
-        conv_gemm_kernel<32><<<grid, NT, 0, st>>>(p);
+        nasb::launch_pdl((conv_gemm_kernel<32>), dim3(grid), dim3(NT), 0, (cudaStream_t)(st), p);
     } else {
         dim3 grid(cdiv(M, BM), cdiv(p.Nc, 64));
-        conv_gemm_kernel<64><<<grid, NT, 0, st>>>(p);
+        nasb::launch_pdl((conv_gemm_kernel<64>), dim3(grid), dim3(NT), 0, (cudaStream_t)(st), p);
     }
     NASB_CHECK_LAUNCH();
     return 0;
@@ -495,10 +497,10 @@ extern "C" int nasb_conv_dgrad(const NasbTensor *dz, const float *weight, int ks
     cudaStream_t st = (cudaStream_t)stream;
     if (p.Nc <= 32) {
         dim3 grid(cdiv(M, BM), cdiv(p.Nc, 32));
-        conv_gemm_kernel<32><<<grid, NT, 0, st>>>(p);
+        nasb::launch_pdl((conv_gemm_kernel<32>), dim3(grid), dim3(NT), 0, (cudaStream_t)(st), p);
     } else {
         dim3 grid(cdiv(M, BM), cdiv(p.Nc, 64));
-        conv_gemm_kernel<64><<<grid, NT, 0, st>>>(p);
+        nasb::launch_pdl((conv_gemm_kernel<64>), dim3(grid), dim3(NT), 0, (cudaStream_t)(st), p);
     }
     NASB_CHECK_LAUNCH();
     return 0;
@@ -543,7 +545,7 @@ extern "C" int nasb_conv_wgrad(const NasbTensor *x0, const NasbTensor *x1, const
     rows = (rows + WP - 1) / WP * WP;
     q.rows_per_cta = rows;
     dim3 grid(tiles, cdiv(M, rows));
-    conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(q);
+    nasb::launch_pdl((conv_wgrad_kernel), dim3(grid), dim3(NT), 0, (cudaStream_t)((cudaStream_t)stream), q);
     NASB_CHECK_LAUNCH();
     return 0;
 }

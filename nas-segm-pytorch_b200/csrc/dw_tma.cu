@@ -96,6 +96,7 @@ __device__ __forceinline__ void ldw8(uint32_t a, float2 (&w)[4]) {
 // All arithmetic is packed fp32 (fma.rn.f32x2), accumulation in fp32.
 template <int K, int S, int STATS>
 __global__ void __launch_bounds__(256, 2) dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const DwT p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
     const size_t tile_bytes = (size_t)p.ITH * p.ITW * p.CC * 2;
@@ -291,6 +292,7 @@ struct DwW {
 template <int K, int S, int KC>
 __global__ void __launch_bounds__(256, 2) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_dz, const DwW p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
     const size_t xt_bytes = (size_t)p.ITH * p.ITW * p.CC * 2, zt_bytes = (size_t)p.TH * p.TW * p.CC * 2;
@@ -416,6 +418,7 @@ __device__ __forceinline__ int floordiv(int a, int b) { return (a >= 0) ? a / b 
 
 template <int K>
 __global__ void __launch_bounds__(256) dw_dgrad_strided_tile_kernel(const __grid_constant__ CUtensorMap map_dz, const DwG p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
     bf16 *zt = reinterpret_cast<bf16 *>(base);  // [ZTH][ZTW][CC]
@@ -497,6 +500,7 @@ constexpr int DQ_QS = 4;  // quads per strip
 
 template <bool GATE>
 __global__ void __launch_bounds__(256, 2) dw_dgrad_s2k3_kernel(const __grid_constant__ CUtensorMap map_dz, const DwQ p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t dsm[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dsm + 127) & ~(uintptr_t)127);
     const size_t tile_bytes = (size_t)p.ZTH * p.ZTW * p.CC * 2;
@@ -826,7 +830,7 @@ static int dw_tile_launch(const NasbTensor *x, const float *weight, int ks, int 
     if (gx < 1) gx = 1;
     if (gx > total) gx = total;
     dim3 grid((unsigned)gx, p.nchunks);
-    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(mx, p);
+    nasb::launch_pdl((kern), dim3(grid), dim3(threads), smem, (cudaStream_t)((cudaStream_t)stream), mx, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -888,7 +892,7 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     if (gx < 1) gx = 1;
     if (gx > total) gx = total;
     dim3 grid((unsigned)gx, p.nchunks);
-    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(mx, mz, p);
+    nasb::launch_pdl((kern), dim3(grid), dim3(threads), smem, (cudaStream_t)((cudaStream_t)stream), mx, mz, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -979,7 +983,7 @@ static int dw_dgrad_strided(const NasbTensor *dz, const float *weight, int ks, i
         long long gx = (long long)NASB_SM_COUNT * per_sm / q.nchunks;
         if (gx < 1) gx = 1;
         if (gx > total) gx = total;
-        kq<<<dim3((unsigned)gx, q.nchunks), threads, smem, (cudaStream_t)stream>>>(mq, q);
+        nasb::launch_pdl((kq), dim3(dim3((unsigned)gx, q.nchunks)), dim3(threads), smem, (cudaStream_t)((cudaStream_t)stream), mq, q);
         NASB_CHECK_LAUNCH();
         return 0;
     }
@@ -1024,7 +1028,7 @@ static int dw_dgrad_strided(const NasbTensor *dz, const float *weight, int ks, i
                 return NASB_ERR_UNSUPPORTED;
             cfg = true;
         }
-        dw_dgrad_strided_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(mz, p);
+        nasb::launch_pdl((dw_dgrad_strided_tile_kernel<3>), dim3(grid), dim3(256), smem, (cudaStream_t)((cudaStream_t)stream), mz, p);
     } else {
         static bool cfg = false;
         if (!cfg) {
@@ -1032,7 +1036,7 @@ static int dw_dgrad_strided(const NasbTensor *dz, const float *weight, int ks, i
                 return NASB_ERR_UNSUPPORTED;
             cfg = true;
         }
-        dw_dgrad_strided_tile_kernel<5><<<grid, 256, smem, (cudaStream_t)stream>>>(mz, p);
+        nasb::launch_pdl((dw_dgrad_strided_tile_kernel<5>), dim3(grid), dim3(256), smem, (cudaStream_t)((cudaStream_t)stream), mz, p);
     }
     NASB_CHECK_LAUNCH();
     return 0;

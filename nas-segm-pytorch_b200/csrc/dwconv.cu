@@ -22,6 +22,7 @@ struct DwP {
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwP p) {
+    pdl_sync();
     extern __shared__ float wsm[];  // [ks*ks][C]
     const int KK = p.ks * p.ks;
     for (int i = threadIdx.x; i < KK * p.C; i += blockDim.x) {
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwP p) {
 template <typename T, int KS>
 __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const DwP p, const void *dz, int dz_cs, float *dw,
                                                            long long rows_per_cta) {
+    pdl_sync();
     constexpr int KK = KS * KS;
     __shared__ float red[256];
     const int CL = blockDim.x, PL = blockDim.y;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const DwP p, const vo
 template <typename T, int KS, int V>
 __global__ void __launch_bounds__(256) dwconv_wgrad_vec_kernel(const DwP p, const void *dz_, int dz_cs, float *dw,
                                                                long long rows_per_cta) {
+    pdl_sync();
     constexpr int KK = KS * KS;
     extern __shared__ float red_sm[];  // [PL][C]
     const T *dz = reinterpret_cast<const T *>(dz_);
@@ -212,7 +215,7 @@ static bool launch_dw_wgrad_vec(const DwP &p, const NasbTensor *x, const NasbTen
     long long want = (long long)NASB_SM_COUNT * 8;
     long long rows = (M + want - 1) / want;
     if (rows < (long long)PL * 48) rows = (long long)PL * 48;  // >= 48 pixels per thread before the per-tap reduction
-    dwconv_wgrad_vec_kernel<T, KS, V><<<cdiv(M, rows), 256, smem, st>>>(p, dz->ptr, dz->cstride, dweight, rows);
+    nasb::launch_pdl((dwconv_wgrad_vec_kernel<T, KS, V>), dim3(cdiv(M, rows)), dim3(256), smem, (cudaStream_t)(st), p, dz->ptr, dz->cstride, dweight, rows);
     return true;
 }
 
@@ -228,10 +231,10 @@ static int launch_dw(const DwP &p, bool vec, long long rows, cudaStream_t st) {
     if (blocks < 1) blocks = 1;
     if (vec) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(dwconv_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dwconv_kernel<T, V><<<blocks, 256, smem, st>>>(p);
+        nasb::launch_pdl((dwconv_kernel<T, V>), dim3(blocks), dim3(256), smem, (cudaStream_t)(st), p);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(dwconv_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dwconv_kernel<T, 1><<<blocks, 256, smem, st>>>(p);
+        nasb::launch_pdl((dwconv_kernel<T, 1>), dim3(blocks), dim3(256), smem, (cudaStream_t)(st), p);
     }
     return 0;
 }
@@ -337,7 +340,7 @@ extern "C" int nasb_dwconv_wgrad(const NasbTensor *x, int in_relu, const NasbTen
     if (rows < 64) rows = 64;
     dim3 grid(cblocks, cdiv(M, rows)), block(CL, PL);
     cudaStream_t st = (cudaStream_t)stream;
-#define NASB_DW_WG(T, KS) dwconv_wgrad_kernel<T, KS><<<grid, block, 0, st>>>(p, dz->ptr, dz->cstride, dweight, rows)
+#define NASB_DW_WG(T, KS) nasb::launch_pdl((dwconv_wgrad_kernel<T, KS>), dim3(grid), dim3(block), 0, (cudaStream_t)(st), p, dz->ptr, dz->cstride, dweight, rows)
     if (x->dtype == NASB_BF16) {
         if (ks == 3) NASB_DW_WG(bf16, 3);
         else if (ks == 5) NASB_DW_WG(bf16, 5);

@@ -9,6 +9,7 @@ namespace nasb {
 template <typename T>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const T *x, int cs, int C, const int64_t *target, int ignore, long long P,
                                                      double *acc2) {
+    pdl_sync();
     __shared__ double sm[256];
     double loss = 0.0, cnt = 0.0;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T *x, int cs, int C, 
 }
 
 __global__ void ce_finalize_kernel(const double *acc2, float *out2) {
+    pdl_sync();
     out2[0] = (float)(acc2[0] / acc2[1]);  // 0/0 -> nan like torch when every pixel is ignored
     out2[1] = (float)acc2[1];
 }
@@ -39,6 +41,7 @@ __global__ void ce_finalize_kernel(const double *acc2, float *out2) {
 template <typename T, typename TG>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const T *x, int cs, int C, const int64_t *target, int ignore, long long P,
                                                      const float *out2, const float *gscale, TG *dx, int dcs) {
+    pdl_sync();
     const float k = (gscale ? gscale[0] : 1.f) / out2[1];
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
         long long t = target[p];
@@ -63,6 +66,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T *x, int cs, int C, 
 // generic strided element walk over an NHWC tensor: element e -> (pixel, channel)
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) mse_fwd_kernel(const TX *x, int xcs, const TY *y, int ycs, int C, long long P, double *acc) {
+    pdl_sync();
     __shared__ double sm[256];
     double a = 0.0;
     const long long total = P * C;
@@ -76,11 +80,13 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const TX *x, int xcs, cons
     if (threadIdx.x == 0) atomicAdd(acc, s);
 }
 
-__global__ void mse_finalize_kernel(const double *acc, double total, float *out1) { out1[0] = (float)(acc[0] / total); }
+__global__ void mse_finalize_kernel(const double *acc, double total, float *out1) {
+    pdl_sync(); out1[0] = (float)(acc[0] / total); }
 
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) mse_bwd_kernel(const TX *x, int xcs, const TY *y, int ycs, int C, long long P,
                                                       const float *gscale, TX *dx, int dcs) {
+    pdl_sync();
     const long long total = P * C;
     const float k = 2.f * (gscale ? gscale[0] : 1.f) / (float)total;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -94,6 +100,7 @@ __global__ void __launch_bounds__(256) mse_bwd_kernel(const TX *x, int xcs, cons
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) berhu_max_kernel(const TX *x, int xcs, const TY *y, int ycs, int C, long long P,
                                                         float vmin, unsigned int *maxbits) {
+    pdl_sync();
     float m = 0.f;
     const long long total = P * C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(256) berhu_max_kernel(const TX *x, int xcs, co
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) berhu_sum_kernel(const TX *x, int xcs, const TY *y, int ycs, int C, long long P, float vmin,
                                                         const unsigned int *maxbits, double *acc2) {
+    pdl_sync();
     __shared__ double sm[256];
     const float cth = 0.2f * __uint_as_float(maxbits[0]);
     double a = 0.0, n = 0.0;
@@ -132,6 +140,7 @@ __global__ void __launch_bounds__(256) berhu_sum_kernel(const TX *x, int xcs, co
 }
 
 __global__ void berhu_finalize_kernel(const double *acc2, const unsigned int *maxbits, float *out3) {
+    pdl_sync();
     out3[0] = (float)(acc2[0] / acc2[1]);
     out3[1] = (float)acc2[1];
     out3[2] = 0.2f * __uint_as_float(maxbits[0]);
@@ -140,6 +149,7 @@ __global__ void berhu_finalize_kernel(const double *acc2, const unsigned int *ma
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) berhu_bwd_kernel(const TX *x, int xcs, const TY *y, int ycs, int C, long long P, float vmin,
                                                         const float *out3, const float *gscale, TX *dx, int dcs) {
+    pdl_sync();
     const float k = (gscale ? gscale[0] : 1.f) / out3[1], cth = out3[2];
     const long long total = P * C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -181,14 +191,14 @@ extern "C" int nasb_ce_fwd(const NasbTensor *logits, const int64_t *target, int 
     if (e != cudaSuccess) return (int)e;
     if (P > 0) {
         if (logits->dtype == NASB_BF16)
-            ce_fwd_kernel<bf16><<<lgrid(P), 256, 0, ST>>>((const bf16 *)logits->ptr, logits->cstride, logits->c, target, ignore_index,
+            nasb::launch_pdl((ce_fwd_kernel<bf16>), dim3(lgrid(P)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)logits->ptr, logits->cstride, logits->c, target, ignore_index,
                                                           P, acc);
         else
-            ce_fwd_kernel<float><<<lgrid(P), 256, 0, ST>>>((const float *)logits->ptr, logits->cstride, logits->c, target,
+            nasb::launch_pdl((ce_fwd_kernel<float>), dim3(lgrid(P)), dim3(256), 0, (cudaStream_t)(ST), (const float *)logits->ptr, logits->cstride, logits->c, target,
                                                            ignore_index, P, acc);
         NASB_CHECK_LAUNCH();
     }
-    ce_finalize_kernel<<<1, 1, 0, ST>>>(acc, out2);
+    nasb::launch_pdl((ce_finalize_kernel), dim3(1), dim3(1), 0, (cudaStream_t)(ST), acc, out2);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -200,7 +210,7 @@ extern "C" int nasb_ce_bwd(const NasbTensor *logits, const int64_t *target, int 
     long long P = npix(*logits);
     if (P == 0) return 0;
 #define CEB(T, TG)                                                                                                          \
-    ce_bwd_kernel<T, TG><<<lgrid(P), 256, 0, ST>>>((const T *)logits->ptr, logits->cstride, logits->c, target, ignore_index, P, \
+    nasb::launch_pdl((ce_bwd_kernel<T, TG>), dim3(lgrid(P)), dim3(256), 0, (cudaStream_t)(ST), (const T *)logits->ptr, logits->cstride, logits->c, target, ignore_index, P, \
                                                    out2, gscale_dev, (TG *)dlogits->ptr, dlogits->cstride)
     if (logits->dtype == NASB_BF16) {
         if (dlogits->dtype == NASB_BF16) CEB(bf16, bf16); else CEB(bf16, float);
@@ -215,11 +225,11 @@ extern "C" int nasb_ce_bwd(const NasbTensor *logits, const int64_t *target, int 
 #define NASB_XY(KERNEL, ...)                                                                       \
     do {                                                                                           \
         if (x->dtype == NASB_BF16) {                                                               \
-            if (y->dtype == NASB_BF16) KERNEL<bf16, bf16><<<lgrid(P * C), 256, 0, ST>>>((const bf16 *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
-            else KERNEL<bf16, float><<<lgrid(P * C), 256, 0, ST>>>((const bf16 *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
+            if (y->dtype == NASB_BF16) nasb::launch_pdl((KERNEL<bf16, bf16>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
+            else nasb::launch_pdl((KERNEL<bf16, float>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
         } else {                                                                                   \
-            if (y->dtype == NASB_BF16) KERNEL<float, bf16><<<lgrid(P * C), 256, 0, ST>>>((const float *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
-            else KERNEL<float, float><<<lgrid(P * C), 256, 0, ST>>>((const float *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
+            if (y->dtype == NASB_BF16) nasb::launch_pdl((KERNEL<float, bf16>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
+            else nasb::launch_pdl((KERNEL<float, float>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, __VA_ARGS__); \
         }                                                                                          \
     } while (0)
 
@@ -234,7 +244,7 @@ extern "C" int nasb_mse_fwd(const NasbTensor *x, const NasbTensor *y, float *out
         NASB_XY(mse_fwd_kernel, acc);
         NASB_CHECK_LAUNCH();
     }
-    mse_finalize_kernel<<<1, 1, 0, ST>>>(acc, (double)P * (double)C, out1);
+    nasb::launch_pdl((mse_finalize_kernel), dim3(1), dim3(1), 0, (cudaStream_t)(ST), acc, (double)P * (double)C, out1);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -249,12 +259,12 @@ extern "C" int nasb_mse_bwd(const NasbTensor *x, const NasbTensor *y, const floa
     if (P == 0) return 0;
     if (x->dtype == NASB_BF16) {
         bf16 *d = (bf16 *)dx->ptr;
-        if (y->dtype == NASB_BF16) mse_bwd_kernel<bf16, bf16><<<lgrid(P * C), 256, 0, ST>>>((const bf16 *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
-        else mse_bwd_kernel<bf16, float><<<lgrid(P * C), 256, 0, ST>>>((const bf16 *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
+        if (y->dtype == NASB_BF16) nasb::launch_pdl((mse_bwd_kernel<bf16, bf16>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
+        else nasb::launch_pdl((mse_bwd_kernel<bf16, float>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
     } else {
         float *d = (float *)dx->ptr;
-        if (y->dtype == NASB_BF16) mse_bwd_kernel<float, bf16><<<lgrid(P * C), 256, 0, ST>>>((const float *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
-        else mse_bwd_kernel<float, float><<<lgrid(P * C), 256, 0, ST>>>((const float *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
+        if (y->dtype == NASB_BF16) nasb::launch_pdl((mse_bwd_kernel<float, bf16>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
+        else nasb::launch_pdl((mse_bwd_kernel<float, float>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, gscale_dev, d, dx->cstride);
     }
     NASB_CHECK_LAUNCH();
     return 0;
@@ -275,7 +285,7 @@ extern "C" int nasb_berhu_fwd(const NasbTensor *x, const NasbTensor *y, float va
         NASB_XY(berhu_sum_kernel, valid_min, mb, acc);
         NASB_CHECK_LAUNCH();
     }
-    berhu_finalize_kernel<<<1, 1, 0, ST>>>(acc, mb, out3);
+    nasb::launch_pdl((berhu_finalize_kernel), dim3(1), dim3(1), 0, (cudaStream_t)(ST), acc, mb, out3);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -290,12 +300,12 @@ extern "C" int nasb_berhu_bwd(const NasbTensor *x, const NasbTensor *y, float va
     if (P == 0) return 0;
     if (x->dtype == NASB_BF16) {
         bf16 *d = (bf16 *)dx->ptr;
-        if (y->dtype == NASB_BF16) berhu_bwd_kernel<bf16, bf16><<<lgrid(P * C), 256, 0, ST>>>((const bf16 *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
-        else berhu_bwd_kernel<bf16, float><<<lgrid(P * C), 256, 0, ST>>>((const bf16 *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
+        if (y->dtype == NASB_BF16) nasb::launch_pdl((berhu_bwd_kernel<bf16, bf16>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
+        else nasb::launch_pdl((berhu_bwd_kernel<bf16, float>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
     } else {
         float *d = (float *)dx->ptr;
-        if (y->dtype == NASB_BF16) berhu_bwd_kernel<float, bf16><<<lgrid(P * C), 256, 0, ST>>>((const float *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
-        else berhu_bwd_kernel<float, float><<<lgrid(P * C), 256, 0, ST>>>((const float *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
+        if (y->dtype == NASB_BF16) nasb::launch_pdl((berhu_bwd_kernel<float, bf16>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, (const bf16 *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
+        else nasb::launch_pdl((berhu_bwd_kernel<float, float>), dim3(lgrid(P * C)), dim3(256), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, (const float *)y->ptr, y->cstride, C, P, valid_min, out3, gscale_dev, d, dx->cstride);
     }
     NASB_CHECK_LAUNCH();
     return 0;

@@ -41,6 +41,7 @@ __device__ __forceinline__ int mt_find(const int *chunk0, int n, int b) {
 }
 
 __global__ void __launch_bounds__(MT_THREADS) mt_sumsq_kernel(const __grid_constant__ MtTable T, double *cells) {
+    pdl_sync();
     __shared__ double sm[MT_THREADS];
     const int t = mt_find(T.chunk0, T.n, blockIdx.x);
     const int chunk = blockIdx.x - T.chunk0[t];
@@ -96,6 +97,7 @@ __device__ __forceinline__ void mt_update(float &p, float &g, float &s1, float &
 
 __global__ void __launch_bounds__(MT_THREADS) mt_step_kernel(const __grid_constant__ MtTable T, const __grid_constant__ MtGroups G,
                                                              const double *cells, float polyak_decay) {
+    pdl_sync();
     const int t = mt_find(T.chunk0, T.n, blockIdx.x);
     const int chunk = blockIdx.x - T.chunk0[t];
     const int n = T.numel[t], lo = chunk * MT_CHUNK, hi = min(n, lo + MT_CHUNK);
@@ -196,6 +198,7 @@ struct PkTable {
 };
 
 __global__ void __launch_bounds__(256) mt_pack_kernel(const __grid_constant__ PkTable T) {
+    pdl_sync();
     const int t = mt_find(T.chunk0, T.n, blockIdx.x);
     const int lo = (blockIdx.x - T.chunk0[t]) * PK_CHUNK;
     const float *w = T.src[t];
@@ -265,7 +268,7 @@ extern "C" int nasb_mt_grad_sumsq(const NasbOptTensor *tensors, int n, double *c
         const int blocks = mt_fill(T, tensors + i0, m);
         if (blocks < 0) return NASB_ERR_BAD_ARG;
         if (blocks == 0) continue;
-        mt_sumsq_kernel<<<blocks, MT_THREADS, 0, (cudaStream_t)stream>>>(T, cells);
+        nasb::launch_pdl((mt_sumsq_kernel), dim3(blocks), dim3(MT_THREADS), 0, (cudaStream_t)((cudaStream_t)stream), T, cells);
         NASB_CHECK_LAUNCH();
     }
     return 0;
@@ -290,7 +293,7 @@ extern "C" int nasb_mt_optim_step(const NasbOptTensor *tensors, int n, const Nas
         for (int i = 0; i < m; ++i)
             if (T.group[i] >= n_groups || T.clip[i] >= n_cells) return NASB_ERR_BAD_ARG;
         if (blocks == 0) continue;
-        mt_step_kernel<<<blocks, MT_THREADS, 0, (cudaStream_t)stream>>>(T, G, cells, polyak_decay);
+        nasb::launch_pdl((mt_step_kernel), dim3(blocks), dim3(MT_THREADS), 0, (cudaStream_t)((cudaStream_t)stream), T, G, cells, polyak_decay);
         NASB_CHECK_LAUNCH();
     }
     return 0;
@@ -318,7 +321,7 @@ extern "C" int nasb_mt_pack_bf16(const NasbPackJob *jobs, int n, void *stream) {
         T.chunk0[m] = c;
         T.n = m;
         if (c == 0) continue;
-        mt_pack_kernel<<<c, 256, 0, (cudaStream_t)stream>>>(T);
+        nasb::launch_pdl((mt_pack_kernel), dim3(c), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), T);
         NASB_CHECK_LAUNCH();
     }
     return 0;
@@ -346,6 +349,7 @@ __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__floa
 
 // per output channel: the constants of dz = s*g + A*z + B, and the BatchNorm parameter gradients
 __global__ void __launch_bounds__(256) pw_bn_coef_kernel(const PwBnP p) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.co) return;
     const double S1 = p.sums[c], S2 = p.sums[p.co + c];
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(256) pw_bn_coef_kernel(const PwBnP p) {
 // blockIdx.y == 0: rows -- dW[c][i] += s gx + A (W_b xx)[c][i] + B sx[i]; pack_g[i][c] = bf16(s W[c][i])
 // blockIdx.y == 1: M[o][i] = sum_c W_b[c][i] A[c] W_b[c][o] -> pack_x[o][Kp(ci)]; bias_row[o] = sum_c B[c] W_b[c][o]
 __global__ void __launch_bounds__(256) pw_bn_mats_kernel(const PwBnP p) {
+    pdl_sync();
     const int Kp = (p.co + 7) / 8 * 8, Kpi = (p.ci + 7) / 8 * 8;
     const float *cs = p.coef, *cA = p.coef + p.co, *cB = p.coef + 2 * p.co;
     if (blockIdx.y == 0) {
@@ -408,11 +413,11 @@ extern "C" int nasb_pw_bn_bwd_prepare(const float *weight, int c_out, int c_in, 
     if (c_in > 256 || c_out > 4096) return NASB_ERR_UNSUPPORTED;
     PwBnP p{weight, c_out, c_in, scale, mean, rstd, sums, 1.0 / (double)P, gx, xx, sx, dweight, dgamma, dbeta,
             (bf16 *)pack_g, (bf16 *)pack_x, bias_row, (float *)scratch};
-    pw_bn_coef_kernel<<<cdiv(c_out, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    nasb::launch_pdl((pw_bn_coef_kernel), dim3(cdiv(c_out, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p);
     NASB_CHECK_LAUNCH();
     const int Kpi = (c_in + 7) / 8 * 8;
     long long work = (long long)c_out * c_in > (long long)c_in * Kpi ? (long long)c_out * c_in : (long long)c_in * Kpi;
-    pw_bn_mats_kernel<<<dim3(cdiv(work, 256), 2), 256, 0, (cudaStream_t)stream>>>(p);
+    nasb::launch_pdl((pw_bn_mats_kernel), dim3(dim3(cdiv(work, 256), 2)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p);
     NASB_CHECK_LAUNCH();
     return 0;
 }

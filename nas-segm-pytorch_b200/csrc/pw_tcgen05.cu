@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const __grid_constant__ CUtensorMap map_o,
                                                            const __grid_constant__ CUtensorMap map_z, const PwParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                    // nkb x [64 x 128 B]
@@ -283,6 +284,7 @@ __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.
 __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const __grid_constant__ CUtensorMap map_o, const PwParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                               // nkb x [64 x 128 B]
@@ -496,6 +498,7 @@ constexpr int WG_STAGE_A = 2 * TILE_M * 128;  // two 64-channel blocks of dz
 
 __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz,
                                                                  const __grid_constant__ CUtensorMap map_x, const WgParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // Co <= 64: only one 64-channel dz block is staged; the descriptor's second block (LBO) then aliases the first x block and
@@ -583,6 +586,7 @@ __device__ __forceinline__ void pack_one(const float *w, int rows, int cols, int
     out[i] = __float2bfloat16_rn(v);
 }
 __global__ void pack_weight_kernel(const float *w, int rows, int cols, int transpose, bf16 *out, int R, int Kp) {
+    pdl_sync();
     pack_one(w, rows, cols, transpose, out, R, Kp, blockIdx.x * blockDim.x + threadIdx.x);
 }
 }  // namespace nasb
@@ -593,7 +597,7 @@ extern "C" int nasb_pack_weight_bf16(const float *w, int rows, int cols, int tra
     if (!w || !out || rows <= 0 || cols <= 0) return NASB_ERR_BAD_ARG;
     int R = transpose ? cols : rows, K = transpose ? rows : cols;
     int Kp = (K + 7) / 8 * 8;
-    pack_weight_kernel<<<cdiv((long long)R * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, transpose, (bf16 *)out, R, Kp);
+    nasb::launch_pdl((pack_weight_kernel), dim3(cdiv((long long)R * Kp, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), w, rows, cols, transpose, (bf16 *)out, R, Kp);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -675,7 +679,7 @@ static int pw_tc_launch(const NasbTensor *x, const void *wpack, int N, const flo
             long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;
             if (grid < p.nnb) grid = p.nnb;
             if (grid > (long long)ntiles * p.nnb) grid = (long long)ntiles * p.nnb;
-            pw_tc_ws_kernel<<<(int)grid, WS_THREADS, smem_ws, (cudaStream_t)stream>>>(ma, mb, mo, p);
+            nasb::launch_pdl((pw_tc_ws_kernel), dim3((int)grid), dim3(WS_THREADS), smem_ws, (cudaStream_t)((cudaStream_t)stream), ma, mb, mo, p);
             NASB_CHECK_LAUNCH();
             return 0;
         }
@@ -694,7 +698,7 @@ static int pw_tc_launch(const NasbTensor *x, const void *wpack, int N, const flo
     long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;  // a multiple of the N blocks
     if (grid < p.nnb) grid = p.nnb;
     if (grid > (long long)ntiles * p.nnb) grid = (long long)ntiles * p.nnb;
-    pw_tc_kernel<<<(int)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, mo, mz, p);
+    nasb::launch_pdl((pw_tc_kernel), dim3((int)grid), dim3(TC_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), ma, mb, mo, mz, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -764,7 +768,7 @@ extern "C" int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float
         if (grid > want) grid = want;
         if (grid > nchunks) grid = nchunks;
         if (grid < 1) grid = 1;
-        pw_wgrad_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mdz, mx, p);
+        nasb::launch_pdl((pw_wgrad_tc_kernel), dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), mdz, mx, p);
         NASB_CHECK_LAUNCH();
     }
     return 0;

@@ -54,6 +54,7 @@ template <int K>
 __global__ void __launch_bounds__(SEP_THREADS) sep_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const __grid_constant__ CUtensorMap map_o, const SepP p) {
+    pdl_sync();
     constexpr int ITH = SEP_TH + K - 1, ITW = SEP_TW + K - 1, KK = K * K;
     constexpr uint32_t XS_BYTES = ((uint32_t)ITH * ITW * 128 + 1023) / 1024 * 1024;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -330,7 +331,7 @@ extern "C" int nasb_sepconv_tc_fwd(const NasbTensor *x, const float *dw_weight, 
     long long total = (long long)p.tiles_x * p.tiles_y * x->n;
     long long grid = (long long)NASB_SM_COUNT * per_sm;
     if (grid > total) grid = total;
-    kern<<<(int)grid, SEP_THREADS, smem, (cudaStream_t)stream>>>(mx, mb, mo, p);
+    nasb::launch_pdl((kern), dim3((int)grid), dim3(SEP_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), mx, mb, mo, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }

@@ -24,6 +24,7 @@ static inline int grid_for(long long total, int threads = 256) {
 template <typename T, int V>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const T *x, int x_cs, T *out, int out_cs, uint8_t *argmax, int N,
                                                        int IH, int IW, int OH, int OW, int C, int stride, int mode) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * OH * OW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const T *x, int x_cs, T *
 template <typename T, int V>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const T *dy, int dy_cs, T *dx, int dx_cs, const uint8_t *argmax,
                                                        int N, int IH, int IW, int OH, int OW, int C, int stride, int mode) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * IH * IW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256) resize_axpby_kernel(const T *x, int x_cs,
                                                            const TY *y, int y_cs, const float *sb, T *out, int out_cs,
                                                            int N, int OH, int OW, int C, float rh, float rw, int identity,
                                                            int relu) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * OH * OW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -193,6 +196,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) resize_bwd_kernel(const T *dz, int dz_cs, int OH, int OW, const float *sa, T *dx,
                                                          int dx_cs, int N, int IH, int IW, int C, float rh, float rw,
                                                          int identity) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * IH * IW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(256) axpby_bwd_params_kernel(const T *dz, int 
                                                                const T *y, int y_cs, float *dsa, float *dsb, int N, int OH,
                                                                int OW, int C, float rh, float rw, int identity,
                                                                long long rows_per_cta) {
+    pdl_sync();
     __shared__ float ra[256], rb[256];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const long long M = (long long)N * OH * OW;
@@ -320,6 +325,7 @@ __global__ void __launch_bounds__(256) axpby_bwd_params_kernel(const T *dz, int 
 template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256) scale_copy_kernel(const TI *x, int x_cs, const float *s, int relu, TO *out,
                                                          int out_cs, long long P, int C) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = P * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(256) scale_copy_kernel(const TI *x, int x_cs, 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) channel_tile_kernel(const T *x, int x_cs, int IH, int IW, T *out, int out_cs, int N,
                                                            int OH, int OW, int C, int R, int stride, float scale) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * OH * OW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -363,6 +370,7 @@ __global__ void __launch_bounds__(256) channel_tile_kernel(const T *x, int x_cs,
 template <typename T, int V>
 __global__ void __launch_bounds__(256) channel_tile_bwd_kernel(const T *dz, int dz_cs, int OH, int OW, T *dx, int dx_cs,
                                                                int N, int IH, int IW, int C, int R, int stride, float scale) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * IH * IW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -394,6 +402,7 @@ __global__ void __launch_bounds__(256) channel_tile_bwd_kernel(const T *dz, int 
 template <typename T>
 __global__ void __launch_bounds__(256) spatial_sum_kernel(const T *x, int x_cs, float *out, int HW, int C, float scale,
                                                           int rows_per_cta) {
+    pdl_sync();
     __shared__ float red[256];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int n = blockIdx.z;
@@ -413,6 +422,7 @@ __global__ void __launch_bounds__(256) spatial_sum_kernel(const T *x, int x_cs, 
 template <typename TV, typename T, int V>
 __global__ void __launch_bounds__(256) spatial_bcast_kernel(const TV *v, int v_cs, float s, T *out, int out_cs, int N, int HW,
                                                             int C) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = (long long)N * HW * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -429,6 +439,7 @@ __global__ void __launch_bounds__(256) spatial_bcast_kernel(const TV *v, int v_c
 template <typename T, int V>
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const T *dy, int dy_cs, const T *y, int y_cs, T *dx, int dx_cs,
                                                        long long P, int C) {
+    pdl_sync();
     const int CV = C / V;
     const long long total = P * CV;
     NASB_GRID_STRIDE(idx, total) {
@@ -444,6 +455,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T *dy, int dy_cs, c
 }
 
 __global__ void sumsq_kernel(const float *x, long long n, float *out) {
+    pdl_sync();
     __shared__ double sm[256];
     double a = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -489,7 +501,7 @@ extern "C" int nasb_pool3x3_fwd(const NasbTensor *x, int mode, int stride, const
     long long rows = npix(*out);
     if (rows == 0) return 0;
     bool ok = vec_ok(*x, vfor(x->dtype)) && vec_ok(*out, vfor(x->dtype));
-    NASB_DISPATCH(x->dtype, ok, (pool_fwd_kernel<T, V><<<grid_for(rows * (x->c / V)), 256, 0, ST>>>(
+    NASB_DISPATCH(x->dtype, ok, (nasb::launch_pdl((pool_fwd_kernel<T, V>), dim3(grid_for(rows * (x->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                     (const T *)x->ptr, x->cstride, (T *)out->ptr, out->cstride, argmax, x->n, x->h, x->w,
                                     out->h, out->w, x->c, stride, mode)));
     NASB_CHECK_LAUNCH();
@@ -503,7 +515,7 @@ extern "C" int nasb_pool3x3_bwd(const NasbTensor *dy, int mode, int stride, cons
     long long rows = npix(*dx);
     if (rows == 0) return 0;
     bool ok = vec_ok(*dy, vfor(dy->dtype)) && vec_ok(*dx, vfor(dy->dtype));
-    NASB_DISPATCH(dy->dtype, ok, (pool_bwd_kernel<T, V><<<grid_for(rows * (dx->c / V)), 256, 0, ST>>>(
+    NASB_DISPATCH(dy->dtype, ok, (nasb::launch_pdl((pool_bwd_kernel<T, V>), dim3(grid_for(rows * (dx->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                      (const T *)dy->ptr, dy->cstride, (T *)dx->ptr, dx->cstride, argmax, dx->n, dx->h, dx->w,
                                      dy->h, dy->w, dx->c, stride, mode)));
     NASB_CHECK_LAUNCH();
@@ -522,15 +534,15 @@ extern "C" int nasb_resize_axpby(const NasbTensor *x, const float *sa, const Nas
     if (y && y->dtype != x->dtype) {
         // mixed operand dtype (fp32 second operand with bf16 activations): scalar path only
         if (x->dtype == NASB_BF16)
-            resize_axpby_kernel<bf16, float, 1><<<grid_for(rows * x->c), 256, 0, ST>>>(
+            nasb::launch_pdl((resize_axpby_kernel<bf16, float, 1>), dim3(grid_for(rows * x->c)), dim3(256), 0, (cudaStream_t)(ST), 
                 (const bf16 *)x->ptr, x->cstride, x->h, x->w, sa, (const float *)y->ptr, y->cstride, sb, (bf16 *)out->ptr,
                 out->cstride, out->n, out->h, out->w, out->c, rh, rw, identity, relu);
         else
-            resize_axpby_kernel<float, bf16, 1><<<grid_for(rows * x->c), 256, 0, ST>>>(
+            nasb::launch_pdl((resize_axpby_kernel<float, bf16, 1>), dim3(grid_for(rows * x->c)), dim3(256), 0, (cudaStream_t)(ST), 
                 (const float *)x->ptr, x->cstride, x->h, x->w, sa, (const bf16 *)y->ptr, y->cstride, sb, (float *)out->ptr,
                 out->cstride, out->n, out->h, out->w, out->c, rh, rw, identity, relu);
     } else {
-        NASB_DISPATCH(x->dtype, ok, (resize_axpby_kernel<T, T, V><<<grid_for(rows * (x->c / V)), 256, 0, ST>>>(
+        NASB_DISPATCH(x->dtype, ok, (nasb::launch_pdl((resize_axpby_kernel<T, T, V>), dim3(grid_for(rows * (x->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                         (const T *)x->ptr, x->cstride, x->h, x->w, sa, y ? (const T *)y->ptr : nullptr,
                                         y ? y->cstride : 0, sb, (T *)out->ptr, out->cstride, out->n, out->h, out->w, out->c,
                                         rh, rw, identity, relu)));
@@ -546,7 +558,7 @@ extern "C" int nasb_resize_bwd(const NasbTensor *dz, const float *sa, const Nasb
     int identity = (dz->h == dx->h && dz->w == dx->w) ? 1 : 0;
     float rh = (float)dx->h / (float)dz->h, rw = (float)dx->w / (float)dz->w;
     bool ok = vec_ok(*dz, vfor(dz->dtype)) && vec_ok(*dx, vfor(dz->dtype));
-    NASB_DISPATCH(dz->dtype, ok, (resize_bwd_kernel<T, V><<<grid_for(rows * (dx->c / V)), 256, 0, ST>>>(
+    NASB_DISPATCH(dz->dtype, ok, (nasb::launch_pdl((resize_bwd_kernel<T, V>), dim3(grid_for(rows * (dx->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                      (const T *)dz->ptr, dz->cstride, dz->h, dz->w, sa, (T *)dx->ptr, dx->cstride, dx->n,
                                      dx->h, dx->w, dx->c, rh, rw, identity)));
     NASB_CHECK_LAUNCH();
@@ -569,11 +581,11 @@ extern "C" int nasb_axpby_bwd_params(const NasbTensor *dz, const NasbTensor *x, 
     if (rows < 64) rows = 64;
     dim3 grid(cblocks, cdiv(M, rows)), block(32, 8);
     if (dz->dtype == NASB_BF16)
-        axpby_bwd_params_kernel<bf16><<<grid, block, 0, ST>>>((const bf16 *)dz->ptr, dz->cstride, (const bf16 *)x->ptr, x->cstride,
+        nasb::launch_pdl((axpby_bwd_params_kernel<bf16>), dim3(grid), dim3(block), 0, (cudaStream_t)(ST), (const bf16 *)dz->ptr, dz->cstride, (const bf16 *)x->ptr, x->cstride,
                                                               x->h, x->w, y ? (const bf16 *)y->ptr : nullptr, y ? y->cstride : 0,
                                                               dsa, dsb, dz->n, dz->h, dz->w, dz->c, rh, rw, identity, rows);
     else
-        axpby_bwd_params_kernel<float><<<grid, block, 0, ST>>>((const float *)dz->ptr, dz->cstride, (const float *)x->ptr,
+        nasb::launch_pdl((axpby_bwd_params_kernel<float>), dim3(grid), dim3(block), 0, (cudaStream_t)(ST), (const float *)dz->ptr, dz->cstride, (const float *)x->ptr,
                                                                x->cstride, x->h, x->w, y ? (const float *)y->ptr : nullptr,
                                                                y ? y->cstride : 0, dsa, dsb, dz->n, dz->h, dz->w, dz->c, rh, rw,
                                                                identity, rows);
@@ -588,7 +600,7 @@ extern "C" int nasb_scale_copy(const NasbTensor *x, const float *s, int relu, co
     int C = x->c;
     bool ok4 = vec_ok(*x, 4) && vec_ok(*out, 4), ok8 = vec_ok(*x, 8) && vec_ok(*out, 8);
 #define SC(TI, TO, V)                                                                                                   \
-    scale_copy_kernel<TI, TO, V><<<grid_for(P * (C / V)), 256, 0, ST>>>((const TI *)x->ptr, x->cstride, s, relu, (TO *)out->ptr, \
+    nasb::launch_pdl((scale_copy_kernel<TI, TO, V>), dim3(grid_for(P * (C / V))), dim3(256), 0, (cudaStream_t)(ST), (const TI *)x->ptr, x->cstride, s, relu, (TO *)out->ptr, \
                                                                           out->cstride, P, C)
     if (x->dtype == NASB_BF16 && out->dtype == NASB_BF16) {
         if (ok8) SC(bf16, bf16, 8); else SC(bf16, bf16, 1);
@@ -613,7 +625,7 @@ extern "C" int nasb_channel_tile(const NasbTensor *x, int stride, float scale, c
     int R = out->c / x->c;
     bool ok = vec_ok(*x, vfor(x->dtype)) && (out->cstride % vfor(x->dtype) == 0) &&
               ((uintptr_t)out->ptr % 16 == 0);
-    NASB_DISPATCH(x->dtype, ok, (channel_tile_kernel<T, V><<<grid_for(rows * (x->c / V)), 256, 0, ST>>>(
+    NASB_DISPATCH(x->dtype, ok, (nasb::launch_pdl((channel_tile_kernel<T, V>), dim3(grid_for(rows * (x->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                     (const T *)x->ptr, x->cstride, x->h, x->w, (T *)out->ptr, out->cstride, out->n, out->h,
                                     out->w, x->c, R, stride, scale)));
     NASB_CHECK_LAUNCH();
@@ -627,7 +639,7 @@ extern "C" int nasb_channel_tile_bwd(const NasbTensor *dz, int stride, float sca
     if (rows == 0) return 0;
     int R = dz->c / dx->c;
     bool ok = vec_ok(*dx, vfor(dx->dtype)) && (dz->cstride % vfor(dx->dtype) == 0) && ((uintptr_t)dz->ptr % 16 == 0);
-    NASB_DISPATCH(dx->dtype, ok, (channel_tile_bwd_kernel<T, V><<<grid_for(rows * (dx->c / V)), 256, 0, ST>>>(
+    NASB_DISPATCH(dx->dtype, ok, (nasb::launch_pdl((channel_tile_bwd_kernel<T, V>), dim3(grid_for(rows * (dx->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                      (const T *)dz->ptr, dz->cstride, dz->h, dz->w, (T *)dx->ptr, dx->cstride, dx->n, dx->h,
                                      dx->w, dx->c, R, stride, scale)));
     NASB_CHECK_LAUNCH();
@@ -647,9 +659,9 @@ static int spatial_reduce(const NasbTensor *x, float *out_nc, float scale, void 
     if (rows < 64) rows = 64;
     dim3 grid(cblocks, cdiv(HW, rows), x->n), block(32, 8);
     if (x->dtype == NASB_BF16)
-        spatial_sum_kernel<bf16><<<grid, block, 0, ST>>>((const bf16 *)x->ptr, x->cstride, out_nc, HW, x->c, scale, rows);
+        nasb::launch_pdl((spatial_sum_kernel<bf16>), dim3(grid), dim3(block), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, out_nc, HW, x->c, scale, rows);
     else
-        spatial_sum_kernel<float><<<grid, block, 0, ST>>>((const float *)x->ptr, x->cstride, out_nc, HW, x->c, scale, rows);
+        nasb::launch_pdl((spatial_sum_kernel<float>), dim3(grid), dim3(block), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, out_nc, HW, x->c, scale, rows);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -669,7 +681,7 @@ extern "C" int nasb_spatial_bcast(const NasbTensor *v, float s, const NasbTensor
     if (rows == 0) return 0;
     int HW = out->h * out->w;
 #define BC(TV, T, V)                                                                                                          \
-    spatial_bcast_kernel<TV, T, V><<<grid_for(rows * (out->c / V)), 256, 0, ST>>>((const TV *)v->ptr, v->cstride, s, (T *)out->ptr, \
+    nasb::launch_pdl((spatial_bcast_kernel<TV, T, V>), dim3(grid_for(rows * (out->c / V))), dim3(256), 0, (cudaStream_t)(ST), (const TV *)v->ptr, v->cstride, s, (T *)out->ptr, \
                                                                                     out->cstride, out->n, HW, out->c)
     if (out->dtype == NASB_BF16) {
         bool ok = vec_ok(*out, 8);
@@ -698,9 +710,9 @@ extern "C" int nasb_channel_sum(const NasbTensor *x, float *out_c, void *workspa
     if (rows < 64) rows = 64;
     dim3 grid(cblocks, cdiv(P, rows), 1), block(32, 8);
     if (x->dtype == NASB_BF16)
-        spatial_sum_kernel<bf16><<<grid, block, 0, ST>>>((const bf16 *)x->ptr, x->cstride, out_c, (int)P, x->c, 1.f, rows);
+        nasb::launch_pdl((spatial_sum_kernel<bf16>), dim3(grid), dim3(block), 0, (cudaStream_t)(ST), (const bf16 *)x->ptr, x->cstride, out_c, (int)P, x->c, 1.f, rows);
     else
-        spatial_sum_kernel<float><<<grid, block, 0, ST>>>((const float *)x->ptr, x->cstride, out_c, (int)P, x->c, 1.f, rows);
+        nasb::launch_pdl((spatial_sum_kernel<float>), dim3(grid), dim3(block), 0, (cudaStream_t)(ST), (const float *)x->ptr, x->cstride, out_c, (int)P, x->c, 1.f, rows);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -712,7 +724,7 @@ extern "C" int nasb_relu_bwd(const NasbTensor *dy, const NasbTensor *y, const Na
     long long P = npix(*dy);
     if (P == 0) return 0;
     bool ok = vec_ok(*dy, vfor(dy->dtype)) && vec_ok(*y, vfor(dy->dtype)) && vec_ok(*dx, vfor(dy->dtype));
-    NASB_DISPATCH(dy->dtype, ok, (relu_bwd_kernel<T, V><<<grid_for(P * (dy->c / V)), 256, 0, ST>>>(
+    NASB_DISPATCH(dy->dtype, ok, (nasb::launch_pdl((relu_bwd_kernel<T, V>), dim3(grid_for(P * (dy->c / V))), dim3(256), 0, (cudaStream_t)(ST), 
                                      (const T *)dy->ptr, dy->cstride, (const T *)y->ptr, y->cstride, (T *)dx->ptr, dx->cstride, P,
                                      dy->c)));
     NASB_CHECK_LAUNCH();
@@ -722,7 +734,7 @@ extern "C" int nasb_relu_bwd(const NasbTensor *dy, const NasbTensor *y, const Na
 extern "C" int nasb_sumsq(const float *x, long long n, float *out1, void *stream) {
     if (!x || !out1) return NASB_ERR_BAD_ARG;
     if (n == 0) return 0;
-    sumsq_kernel<<<grid_for(n), 256, 0, ST>>>(x, n, out1);
+    nasb::launch_pdl((sumsq_kernel), dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)(ST), x, n, out1);
     NASB_CHECK_LAUNCH();
     return 0;
 }

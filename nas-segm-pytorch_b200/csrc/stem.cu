@@ -22,6 +22,7 @@ struct StemP {
 };
 
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemP p) {
+    pdl_sync();
     __shared__ __align__(16) float ws[STEM_K][STEM_CO];
     __shared__ float s_sc[STEM_CO], s_sh[STEM_CO];
     for (int i = threadIdx.x; i < STEM_K * STEM_CO; i += blockDim.x) {
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemP p) {
 // nasb_pw_tc_wgrad on the same matrix.  Thread = output pixel: 27 loads (adjacent threads read adjacent columns),
 // four 16-byte stores.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const StemP p) {
+    pdl_sync();
     const long long total = (long long)p.N * p.OH * p.OW;
     const long long plane = (long long)p.IH * p.IW;
     for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
@@ -130,6 +132,7 @@ constexpr int STEM_WP = 64;  // pixels staged per step of the weight gradient
 
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const StemP p, const T *dz, int dz_cs, float *dw, long long rows_per_cta) {
+    pdl_sync();
     __shared__ float Zs[STEM_WP][STEM_CO];
     __shared__ float Xs[STEM_WP][STEM_K + 1];
     const int tid = threadIdx.x;
@@ -214,7 +217,7 @@ extern "C" int nasb_stem_fwd(const NasbTensor *img, const float *weight, int ks,
     if (total == 0) return 0;
     long long blocks = (total + 127) / 128, cap = (long long)NASB_SM_COUNT * 32;
     if (blocks > cap) blocks = cap;
-    stem_fwd_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(p);
+    nasb::launch_pdl((stem_fwd_kernel), dim3((int)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -240,9 +243,9 @@ extern "C" int nasb_stem_wgrad(const NasbTensor *img, const NasbTensor *dz, int 
     if (rows < STEM_WP * 4) rows = STEM_WP * 4;
     int blocks = cdiv(M, rows);
     if (dz->dtype == NASB_BF16)
-        stem_wgrad_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, (const bf16 *)dz->ptr, dz->cstride, dweight, rows);
+        nasb::launch_pdl((stem_wgrad_kernel<bf16>), dim3(blocks), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, (const bf16 *)dz->ptr, dz->cstride, dweight, rows);
     else
-        stem_wgrad_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, (const float *)dz->ptr, dz->cstride, dweight, rows);
+        nasb::launch_pdl((stem_wgrad_kernel<float>), dim3(blocks), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, (const float *)dz->ptr, dz->cstride, dweight, rows);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -270,7 +273,7 @@ extern "C" int nasb_stem_im2col(const NasbTensor *img, int ks, int stride, int d
     if (total == 0) return 0;
     long long blocks = (total + 255) / 256, cap = (long long)NASB_SM_COUNT * 16;
     if (blocks > cap) blocks = cap;
-    stem_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    nasb::launch_pdl((stem_im2col_kernel), dim3((int)blocks), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p);
     NASB_CHECK_LAUNCH();
     return 0;
 }

@@ -26,6 +26,7 @@ struct UpTable {
 };
 
 __global__ void __launch_bounds__(256) units_prepare_kernel(const __grid_constant__ UpTable T) {
+    pdl_sync();
     int lo = 0, hi = T.n;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -103,7 +104,7 @@ extern "C" int nasb_conv_units_prepare(const NasbConvUnit *const *units, const i
         T.chunk0[m] = c;
         T.n = m;
         if (c == 0) continue;
-        units_prepare_kernel<<<c, 256, 0, (cudaStream_t)stream>>>(T);
+        nasb::launch_pdl((units_prepare_kernel), dim3(c), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), T);
         NASB_CHECK_LAUNCH();
     }
     return 0;

@@ -61,7 +61,7 @@ def test_train_task0_matches_reference_trajectory(golden, graphs):
     finally:
         trainer.logger.info = orig
         nas_segm_b200.config().cuda_graphs = False
-        nas_segm_b200.config().graph_warmup = 3
+        nas_segm_b200.config().graph_warmup = 1
     if graphs:
         assert dec._nasb_task0_graph.graph is not None and dec._nasb_task0_graph.calls == 4
     assert np.allclose(losses, fx["logged_avg_loss"], atol=2e-3), (losses, fx["logged_avg_loss"])
@@ -226,7 +226,7 @@ def test_train_segmenter_matches_reference_trajectory(golden, mode):
             ok, tot = ok + frac * n, tot + n
         assert ok / tot > 0.99, ok / tot
     finally:
-        cfg.cuda_graphs, cfg.graph_warmup, cfg.fused_optim = False, 3, True
+        cfg.cuda_graphs, cfg.graph_warmup, cfg.fused_optim = False, 1, True
 
 
 def test_train_segmenter_graph_is_recaptured_when_what_it_bakes_in_changes():
@@ -278,7 +278,7 @@ def test_train_segmenter_graph_is_recaptured_when_what_it_bakes_in_changes():
         assert g3 is not g2                      # BatchNorm mode changed
         assert not torch.equal(w_before, dec.conv_clf.weight)
     finally:
-        cfg.cuda_graphs, cfg.graph_warmup = False, 3
+        cfg.cuda_graphs, cfg.graph_warmup = False, 1
 
 
 def test_search_round_on_gpu():
@@ -338,5 +338,5 @@ def test_search_round_on_gpu():
             assert tb.shape == (1, 4) and 0.0 <= float(tb[0, 0]) <= 1.0 and float(tb[0, 3]) > 1e4  # reward, #params
         assert all(len(u) == 1 and u[0][0] in built for u in seen)
     finally:
-        cfg.cuda_graphs, cfg.graph_warmup = False, 3
+        cfg.cuda_graphs, cfg.graph_warmup = False, 1
         nas_segm_b200.set_act_dtype(torch.float32)
