@@ -16,9 +16,10 @@
 
 namespace nasb {
 
-constexpr int C3_THREADS = 128;
-constexpr int C3_TILE = 128;  // pixels per patch
-constexpr int C3_NB = 64;     // output channels per CTA
+constexpr int C3_THREADS = 128;   // weight-gradient kernel
+constexpr int C3F_THREADS = 192;  // forward / data-gradient kernel: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int C3_TILE = 128;      // pixels per patch
+constexpr int C3_NB = 64;         // output channels per CTA
 
 struct C3Params {
     int NI, H, W;        // images, height, width (input == output size: stride 1, pad == dil*(3-1)/2 .. general pad below)
@@ -30,31 +31,51 @@ struct C3Params {
     int halo;            // 1: row-halo staging (TH == 1): three (TW + 2*dil)-pixel row boxes per (patch, K block) feed all nine taps
     int rowbuf;          // bytes between the row buffers of one halo stage (multiple of 1024)
     int nr;              // rows per tap in the packed weight (N rounded up to 64)
+    int brows;           // rows per tap kept in shared memory (32 when N <= 32, else 64)
     const float *scale, *shift;
     int act;
-    void *out;           // fp32 output (direct stores) when out_f32, else the TMA map is used
+    void *out;           // fp32 output when out_f32, else the TMA map is used
     int out_cs, out_f32;
+    int so_bufs;         // bf16 output tiles in shared memory (2 when they fit, else 1)
+    int f32_staged;      // fp32 output with out_cs == N: the patch is a contiguous span per image row, written from a staging tile
     double *stats;
 };
 
-__global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant__ CUtensorMap map_x,
-                                                           const __grid_constant__ CUtensorMap map_b,
-                                                           const __grid_constant__ CUtensorMap map_o, const C3Params p) {
+__device__ __forceinline__ void c3_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void c3_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void c3_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// Warp-specialised: the producer streams (patch, tap / row-halo, K block) items through a ring of `stages` shared-memory
+// slots, the MMA issuer accumulates a patch into one of TWO TMEM accumulators, the four epilogue warps drain the other one.
+// Barriers: full[s] (tx bytes, producer -> MMA), done[s] (commit, MMA -> producer), acc_full[a] (commit, MMA -> epilogue),
+// acc_empty[a] (128 arrivals, epilogue -> MMA).  Completion k of each barrier requires the waiter of completion k-1 to have
+// passed (item g+S waits done of item g, committed after the MMA's wait on full of item g; patch i+2 waits acc_empty of
+// patch i, arrived after the epilogue's wait on acc_full of patch i), so a parity wait is never overtaken by two phases.
+__global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_b,
+                                                            const __grid_constant__ CUtensorMap map_o, const C3Params p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nb_items = 9 * p.nkb;
-    uint8_t *sB = smem;                                        // 9*nkb x [64 x 128 B]
-    uint8_t *sA = sB + (size_t)nb_items * C3_NB * 128;         // stages x [128 x 128 B]
+    const size_t b_tile = (size_t)p.brows * 128;
+    uint8_t *sB = smem;                                        // 9*nkb x [brows x 128 B]
+    uint8_t *sA = sB + (size_t)nb_items * b_tile;              // stages x stage_bytes
     const size_t stage_bytes = p.halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
-    uint8_t *sO = sA + (size_t)p.stages * stage_bytes;          // [128 x 128 B]
-    float *s_scale = (float *)(sO + (size_t)C3_TILE * 128);
+    uint8_t *sO = sA + (size_t)p.stages * stage_bytes;          // bf16: so_bufs x [128 x 128 B]; staged fp32: [128 x N] floats
+    const size_t so_bytes = p.out_f32 ? (p.f32_staged ? (((size_t)C3_TILE * p.N * 4 + 1023) & ~(size_t)1023) : 0)
+                                      : (size_t)p.so_bufs * C3_TILE * 128;
+    float *s_scale = (float *)(sO + so_bytes);
     float *s_shift = s_scale + C3_NB;
     float *s_sum = s_shift + C3_NB;
     float *s_sq = s_sum + C3_NB;
     uint64_t *bar_b = (uint64_t *)(s_sq + C3_NB);
-    uint64_t *bar_acc = bar_b + 1;
-    uint64_t *full = bar_acc + 1;      // [stages]
-    uint64_t *done = full + 8;         // [stages]
+    uint64_t *acc_full = bar_b + 1;    // [2]
+    uint64_t *acc_empty = acc_full + 2;  // [2]
+    uint64_t *full = acc_empty + 2;    // [stages <= 8]
+    uint64_t *done = full + 8;         // [stages <= 8]
     uint32_t *s_tmem = (uint32_t *)(done + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -64,30 +85,32 @@ __global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant
     const int tiles_img = p.tiles_x * p.tiles_y, total_patches = tiles_img * p.NI;
     const int patch0 = (int)blockIdx.x / p.nnb, pstride = (int)gridDim.x / p.nnb;
     const int my_patches = patch0 < total_patches ? (total_patches - 1 - patch0) / pstride + 1 : 0;
-    const uint32_t tmem_cols = npb > 32 ? 64u : 32u;
+    const uint32_t acc_cols = npb > 32 ? 64u : 32u;
     const int S = p.stages;
 
     if (tid == 0) {
         mbar_init(bar_b, 1);
-        mbar_init(bar_acc, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
         for (int i = 0; i < S; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&done[i], 1);
         }
         fence_barrier_init();
     }
-    for (int i = tid; i < C3_NB; i += C3_THREADS) {
+    for (int i = tid; i < C3_NB; i += C3F_THREADS) {
         s_scale[i] = (p.scale && i < nblk) ? p.scale[n0 + i] : 1.f;
         s_shift[i] = (p.shift && i < nblk) ? p.shift[n0 + i] : 0.f;
         s_sum[i] = 0.f;
         s_sq[i] = 0.f;
     }
-    if (warp == 0) tmem_alloc(s_tmem, tmem_cols);
+    if (warp == 5) tmem_alloc(s_tmem, 2 * acc_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    const uint32_t idesc = make_idesc_bf16(npb);
 
     // patch index -> (image, y0, x0)
     auto patch_origin = [&](int pi, int &n, int &y0, int &x0) {
@@ -100,140 +123,187 @@ __global__ void __launch_bounds__(C3_THREADS) c3_tc_kernel(const __grid_constant
     };
     // pipeline item: (patch, tap, K block) in tap mode, (patch, K block) in row-halo mode
     const int items_pp = p.halo ? p.nkb : nb_items;
-    const long long total_items = (long long)my_patches * items_pp;
-    long long g_issued = 0;
-    auto issue = [&](long long g) {  // thread 0 only: TMA for pipeline item g
-        const int s = (int)(g % S);
-        if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
-        const int pi = (int)(g / items_pp), j = (int)(g % items_pp);
-        int n, y0, x0;
-        patch_origin(pi, n, y0, x0);
-        if (p.halo) {
-            // rows y0 - pad + {0, dil, 2 dil}, pixels x0 - pad .. x0 - pad + TW + 2 dil - 1: tap (ty, tx) is the 128 consecutive
-            // 128-byte rows of row buffer ty that start at pixel tx*dil (both TMA and UMMA swizzle on absolute address bits)
-            const uint32_t row_bytes = (uint32_t)(p.TW + 2 * p.dil) * 128;
-            mbar_expect_tx(&full[s], 3 * row_bytes);
-            for (int ty = 0; ty < 3; ++ty)
-                tma_load_4d_sw(sA + (size_t)s * stage_bytes + (size_t)ty * p.rowbuf, &map_x, &full[s], j * 64, x0 - p.pad,
-                               y0 - p.pad + ty * p.dil, n);
-        } else {
-            const int tap = j / p.nkb, kb = j - tap * p.nkb;
-            mbar_expect_tx(&full[s], C3_TILE * 128);
-            tma_load_4d_sw(sA + (size_t)s * C3_TILE * 128, &map_x, &full[s], kb * 64, x0 - p.pad + (tap % 3) * p.dil,
-                           y0 - p.pad + (tap / 3) * p.dil, n);
-        }
-    };
-    if (tid == 0 && my_patches > 0) {
-        mbar_expect_tx(bar_b, (uint32_t)(nb_items * C3_NB * 128));
-        for (int j = 0; j < nb_items; ++j) {
-            const int tap = j / p.nkb, kb = j - tap * p.nkb;
-            tma_load_2d(sB + (size_t)j * C3_NB * 128, &map_b, bar_b, kb * 64, tap * p.nr + n0);
-        }
-        while (g_issued < total_items && g_issued < S) issue(g_issued++);
-    }
 
-    for (int pi = 0; pi < my_patches; ++pi) {
-        int n, y0, x0;
-        patch_origin(pi, n, y0, x0);
-        if (tid == 0) {
-            if (pi == 0) mbar_wait(bar_b, 0);
-            for (int j = 0; j < items_pp; ++j) {
-                const long long c = (long long)pi * items_pp + j;
-                if (c >= 1 && g_issued < total_items) issue(g_issued++);  // refill the slot freed one item ago
-                const int s = (int)(c % S);
-                mbar_wait(&full[s], (uint32_t)(c / S) & 1);
-                tc_fence_after();
-                const int kb = p.halo ? j : j % p.nkb;
-                const int krem = p.K - kb * 64;
-                const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
-                if (p.halo) {
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a0 = smem_u32(sA + (size_t)s * stage_bytes + (size_t)(tap / 3) * p.rowbuf) +
-                                            (uint32_t)((tap % 3) * p.dil) * 128;
-                        const uint32_t b0 = smem_u32(sB + (size_t)(tap * p.nkb + kb) * C3_NB * 128);
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            umma_f16(tmem_base, make_desc_sw128(a0 + ks * 32), make_desc_sw128(b0 + ks * 32), idesc,
-                                     (j > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+    if (warp == 4) {
+        if (lane == 0 && my_patches > 0) {  // ---- producer
+            mbar_expect_tx(bar_b, (uint32_t)(nb_items * b_tile));
+            for (int j = 0; j < nb_items; ++j) {
+                const int tap = j / p.nkb, kb = j - tap * p.nkb;
+                tma_load_2d(sB + (size_t)j * b_tile, &map_b, bar_b, kb * 64, tap * p.nr + n0);
+            }
+            int g = 0;
+            for (int pi = 0; pi < my_patches; ++pi) {
+                int n, y0, x0;
+                patch_origin(pi, n, y0, x0);
+                for (int j = 0; j < items_pp; ++j, ++g) {
+                    const int s = g % S;
+                    if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
+                    if (p.halo) {
+                        // rows y0 - pad + {0, dil, 2 dil}, pixels x0 - pad .. x0 - pad + TW + 2 dil - 1: tap (ty, tx) is the 128
+                        // consecutive 128-byte rows of row buffer ty that start at pixel tx*dil (both TMA and UMMA swizzle on
+                        // absolute address bits)
+                        const uint32_t row_bytes = (uint32_t)(p.TW + 2 * p.dil) * 128;
+                        mbar_expect_tx(&full[s], 3 * row_bytes);
+                        for (int ty = 0; ty < 3; ++ty)
+                            tma_load_4d_sw(sA + (size_t)s * stage_bytes + (size_t)ty * p.rowbuf, &map_x, &full[s], j * 64,
+                                           x0 - p.pad, y0 - p.pad + ty * p.dil, n);
+                    } else {
+                        const int tap = j / p.nkb, kb = j - tap * p.nkb;
+                        mbar_expect_tx(&full[s], C3_TILE * 128);
+                        tma_load_4d_sw(sA + (size_t)s * C3_TILE * 128, &map_x, &full[s], kb * 64,
+                                       x0 - p.pad + (tap % 3) * p.dil, y0 - p.pad + (tap / 3) * p.dil, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0 && my_patches > 0) {  // ---- MMA issuer
+            const uint32_t idesc = make_idesc_bf16(npb);
+            mbar_wait(bar_b, 0);
+            int g = 0;
+            for (int pi = 0; pi < my_patches; ++pi) {
+                const int a = pi & 1;
+                const uint32_t acc = tmem_base + (uint32_t)a * acc_cols;
+                if (pi >= 2) mbar_wait(&acc_empty[a], (uint32_t)((pi >> 1) - 1) & 1);
+                for (int j = 0; j < items_pp; ++j, ++g) {
+                    const int s = g % S;
+                    mbar_wait(&full[s], (uint32_t)(g / S) & 1);
+                    tc_fence_after();
+                    const int kb = p.halo ? j : j % p.nkb;
+                    const int krem = p.K - kb * 64;
+                    const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+                    if (p.halo) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t a0 = smem_u32(sA + (size_t)s * stage_bytes + (size_t)(tap / 3) * p.rowbuf) +
+                                                (uint32_t)((tap % 3) * p.dil) * 128;
+                            const uint32_t b0 = smem_u32(sB + (size_t)(tap * p.nkb + kb) * b_tile);
+                            for (int ks = 0; ks < ksteps; ++ks)
+                                umma_f16(acc, make_desc_sw128(a0 + ks * 32), make_desc_sw128(b0 + ks * 32), idesc,
+                                         (j > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    } else {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)s * C3_TILE * 128) + ks * 32);
+                            uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)j * b_tile) + ks * 32);
+                            umma_f16(acc, ad, bd, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&done[s]);  // the slot may be refilled once these MMAs have read it
+                }
+                umma_commit(&acc_full[a]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 0..3 (128 threads): thread = TMEM lane = pixel of the patch
+        const int row = warp * 32 + lane;
+        float *sF = reinterpret_cast<float *>(sO);
+        for (int pi = 0; pi < my_patches; ++pi) {
+            const int a = pi & 1;
+            int n, y0, x0;
+            patch_origin(pi, n, y0, x0);
+            uint8_t *sOt = sO + (size_t)(p.so_bufs == 2 ? a : 0) * C3_TILE * 128;
+            mbar_wait(&acc_full[a], (uint32_t)(pi >> 1) & 1);
+            tc_fence_after();
+            if (!p.out_f32) {
+                if (tid == 0) {  // the bulk store that last read this tile (patch pi - so_bufs) has finished reading it
+                    if (p.so_bufs == 2) {
+                        if (pi >= 2) c3_store_wait_read1();
+                    } else if (pi >= 1) {
+                        tma_store_wait_read();
+                    }
+                }
+                c3_epi_barrier();
+            } else if (p.f32_staged) {
+                c3_epi_barrier();  // the copy-out of the previous patch is complete
+            }
+            const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+            const bool row_ok = py < p.H && px < p.W;
+#pragma unroll 1
+            for (int c0 = 0; c0 < npb; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+                if (p.stats) {
+                    float q[16], q2[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        q[j] = row_ok ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
+                        q2[j] = q[j] * q[j];
+                    }
+                    int col;
+                    float t1 = warp_colsum16(q, lane, col), t2 = warp_colsum16(q2, lane, col);
+                    if (!(lane & 1) && c0 + col < nblk) {
+                        atomicAdd(&s_sum[c0 + col], t1);
+                        atomicAdd(&s_sq[c0 + col], t2);
+                    }
+                }
+                if (p.out_f32) {
+                    if (p.f32_staged) {
+                        float *o = sF + (size_t)row * nblk + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < nblk) o[j] = v[j];
+                    } else if (row_ok) {
+                        float *o = reinterpret_cast<float *>(p.out) + (((size_t)n * p.H + py) * p.W + px) * p.out_cs + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < nblk) o[j] = v[j];
                     }
                 } else {
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)s * C3_TILE * 128) + ks * 32);
-                        uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)j * C3_NB * 128) + ks * 32);
-                        umma_f16(tmem_base, ad, bd, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                    const int ch = c0 >> 3;
+                    uint8_t *orow = sOt + (size_t)row * 128;
+                    uint4 q0, q1;
+                    bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        e0[j] = __float2bfloat16_rn(v[j]);
+                        e1[j] = __float2bfloat16_rn(v[8 + j]);
+                    }
+                    *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
+                    *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
+                }
+            }
+            tc_fence_before();
+            c3_arrive(&acc_empty[a]);  // this thread is done with accumulator a
+            if (!p.out_f32) {
+                fence_proxy_async();
+                c3_epi_barrier();  // patch complete in shared memory
+                if (tid == 0) {
+                    tma_store_4d(&map_o, sOt, n0, x0, y0, n);
+                    tma_store_commit();
+                }
+            } else if (p.f32_staged) {
+                c3_epi_barrier();
+                // out_cs == N: each image row of the patch is ONE contiguous span of (valid pixels x N) floats
+                const int vw = p.W - x0 < p.TW ? p.W - x0 : p.TW;
+                for (int ty = 0; ty < p.TH && y0 + ty < p.H; ++ty) {
+                    const float *src = sF + (size_t)ty * p.TW * nblk;
+                    float *dst = reinterpret_cast<float *>(p.out) + (((size_t)n * p.H + y0 + ty) * p.W + x0) * nblk;
+                    const int cnt = vw * nblk;
+                    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+                        const int c4 = cnt >> 2;
+                        for (int e = tid; e < c4; e += 128)
+                            reinterpret_cast<float4 *>(dst)[e] = reinterpret_cast<const float4 *>(src)[e];
+                        for (int e = (c4 << 2) + tid; e < cnt; e += 128) dst[e] = src[e];
+                    } else {
+                        for (int e = tid; e < cnt; e += 128) dst[e] = src[e];
                     }
                 }
-                umma_commit(&done[s]);
-            }
-            umma_commit(bar_acc);
-        }
-        mbar_wait(bar_acc, (uint32_t)pi & 1);
-        tc_fence_after();
-
-        const int row = warp * 32 + lane;
-        const int py = y0 + row / p.TW, px = x0 + row % p.TW;
-        const bool row_ok = py < p.H && px < p.W;
-#pragma unroll 1
-        for (int c0 = 0; c0 < npb; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
-            if (p.stats) {
-                float q[16], q2[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    q[j] = row_ok ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
-                    q2[j] = q[j] * q[j];
-                }
-                int col;
-                float t1 = warp_colsum16(q, lane, col), t2 = warp_colsum16(q2, lane, col);
-                if (!(lane & 1) && c0 + col < nblk) {
-                    atomicAdd(&s_sum[c0 + col], t1);
-                    atomicAdd(&s_sq[c0 + col], t2);
-                }
-            }
-            if (p.out_f32) {
-                if (row_ok) {
-                    float *o = reinterpret_cast<float *>(p.out) + (((size_t)n * p.H + py) * p.W + px) * p.out_cs + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < nblk) o[j] = v[j];
-                }
-            } else {
-                const int ch = c0 >> 3;
-                uint8_t *orow = sO + (size_t)row * 128;
-                uint4 q0, q1;
-                bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    e0[j] = __float2bfloat16_rn(v[j]);
-                    e1[j] = __float2bfloat16_rn(v[8 + j]);
-                }
-                *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
-                *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
             }
         }
-        if (!p.out_f32) fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (!p.out_f32 && tid == 0) {
-            tma_store_4d(&map_o, sO, n0, x0, y0, n);
-            tma_store_commit();
-            tma_store_wait_read();
-        }
-        __syncthreads();
-    }
-    if (tid == 0) tma_store_wait_all();
-    if (p.stats) {
-        __syncthreads();
-        for (int c = tid; c < nblk; c += C3_THREADS) {
-            atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
-            atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
+        if (tid == 0) tma_store_wait_all();
+        if (p.stats) {
+            c3_epi_barrier();
+            for (int c = tid; c < nblk; c += 128) {
+                atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
+                atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 5) tmem_dealloc(tmem_base, 2 * acc_cols);
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -250,6 +320,7 @@ struct C3WParams {
 
 __global__ void __launch_bounds__(C3_THREADS) c3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                  const __grid_constant__ CUtensorMap map_dz, const C3WParams p) {
+    pdl_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int S = 2, PAIRS = 5;
@@ -344,6 +415,7 @@ __global__ void __launch_bounds__(C3_THREADS) c3_wgrad_tc_kernel(const __grid_co
 //   mode 0 (forward)      : row n = co, col k = ci, tap unchanged
 //   mode 1 (data gradient): row n = ci, col k = co, tap flipped (8 - tap)
 __global__ void pack_conv3_kernel(const float *w, int Co, int Ci, int mode, bf16 *out, int Nr, int Kp) {
+    pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 9 * Nr * Kp) return;
     int k = i % Kp, t = i / Kp, n = t % Nr, tap = t / Nr;
@@ -364,8 +436,10 @@ static void pick_patch(int H, int W, int &TH, int &TW) {
     (void)H;
 }
 
-static size_t c3_smem(int nkb, int stages, size_t stage_bytes = (size_t)C3_TILE * 128) {
-    return (size_t)9 * nkb * C3_NB * 128 + (size_t)stages * stage_bytes + (size_t)C3_TILE * 128 + 4 * C3_NB * 4 + 256 + 1024;
+// shared memory of the forward kernel: weight taps + ring + output staging + constants/barriers + alignment slack
+static size_t c3_smem(int nkb, int stages, size_t stage_bytes = (size_t)C3_TILE * 128, int brows = C3_NB,
+                      size_t so_bytes = (size_t)2 * C3_TILE * 128) {
+    return (size_t)9 * nkb * brows * 128 + (size_t)stages * stage_bytes + so_bytes + 4 * C3_NB * 4 + 256 + 1024;
 }
 
 }  // namespace nasb
@@ -381,7 +455,7 @@ extern "C" int nasb_pack_conv3_bf16(const float *w, int Co, int Ci, int mode, vo
     if (!w || !out || Co <= 0 || Ci <= 0) return NASB_ERR_BAD_ARG;
     int N = mode == 0 ? Co : Ci, K = mode == 0 ? Ci : Co;
     int Nr = (N + 63) / 64 * 64, Kp = (K + 7) / 8 * 8;
-    pack_conv3_kernel<<<cdiv(9LL * Nr * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, Co, Ci, mode, (bf16 *)out, Nr, Kp);
+    nasb::launch_pdl((pack_conv3_kernel), dim3(cdiv(9LL * Nr * Kp, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), w, Co, Ci, mode, (bf16 *)out, Nr, Kp);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -390,7 +464,7 @@ extern "C" int nasb_pack_conv3_bf16(const float *w, int Co, int Ci, int mode, vo
 extern "C" int nasb_conv3_tc_supported(int K, int N) {
     if (K < 1 || N < 1 || N > 4096) return 0;
     int nkb = (K + 63) / 64;
-    return c3_smem(nkb, 2) <= 200 * 1024 ? 1 : 0;
+    return c3_smem(nkb, 2, (size_t)C3_TILE * 128, C3_NB, (size_t)C3_TILE * 128) <= 200 * 1024 ? 1 : 0;
 }
 
 extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, int dil, int pad, const float *scale,
@@ -421,33 +495,43 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     if (halo_on < 0) halo_on = getenv("NASB_C3_HALO") ? atoi(getenv("NASB_C3_HALO")) : 1;
     p.halo = (halo_on && p.TH == 1 && p.TW + 2 * dil <= 256) ? 1 : 0;
     p.rowbuf = (int)((((size_t)(p.TW + 2 * dil) * 128) + 1023) / 1024 * 1024);
-    size_t stage_bytes = p.halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
-    p.stages = p.halo ? 3 : 8;
-    while (p.stages > 2 && c3_smem(p.nkb, p.stages, stage_bytes) > 216 * 1024) --p.stages;
-    if (c3_smem(p.nkb, p.stages, stage_bytes) > 216 * 1024) {  // row buffers do not fit: tap-per-box pipeline
-        p.halo = 0;
-        stage_bytes = (size_t)C3_TILE * 128;
-        p.stages = 8;
-        while (p.stages > 2 && c3_smem(p.nkb, p.stages, stage_bytes) > 216 * 1024) --p.stages;
+    p.out_f32 = out->dtype == NASB_F32 ? 1 : 0;
+    p.f32_staged = (p.out_f32 && out->cstride == N && N <= C3_NB) ? 1 : 0;
+    p.brows = N <= 32 ? 32 : C3_NB;
+    // preference order: row-halo ring before tap ring, two output tiles before one; each needs >= 2 ring stages to fit
+    const size_t f32_so = p.f32_staged ? (((size_t)C3_TILE * N * 4 + 1023) & ~(size_t)1023) : 0;
+    size_t stage_bytes = 0, so_bytes = 0;
+    bool placed = false;
+    for (int use_halo = p.halo; use_halo >= 0 && !placed; --use_halo) {
+        for (int bufs = 2; bufs >= 1 && !placed; --bufs) {
+            stage_bytes = use_halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
+            so_bytes = p.out_f32 ? f32_so : (size_t)bufs * C3_TILE * 128;
+            if (c3_smem(p.nkb, 2, stage_bytes, p.brows, so_bytes) > 216 * 1024) continue;
+            p.halo = use_halo;
+            p.so_bufs = bufs;
+            p.stages = use_halo ? 3 : 8;
+            while (p.stages > 2 && c3_smem(p.nkb, p.stages, stage_bytes, p.brows, so_bytes) > 216 * 1024) --p.stages;
+            placed = true;
+        }
     }
+    if (!placed) return NASB_ERR_UNSUPPORTED;
     p.nr = (N + 63) / 64 * 64;
     p.scale = scale;
     p.shift = shift;
     p.act = act;
     p.out = out->ptr;
     p.out_cs = out->cstride;
-    p.out_f32 = out->dtype == NASB_F32 ? 1 : 0;
     p.stats = stats;
     int Kp = (p.K + 7) / 8 * 8;
     CUtensorMap mx, mb, mo;
     if (!tc_make_map4(&mx, x, p.halo ? p.TW + 2 * dil : p.TW, p.TH)) return NASB_ERR_UNSUPPORTED;
-    if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)9 * p.nr, (uint64_t)Kp, C3_NB)) return NASB_ERR_UNSUPPORTED;
+    if (!tc_make_map2(&mb, wpack, (uint64_t)Kp, (uint64_t)9 * p.nr, (uint64_t)Kp, (uint32_t)p.brows)) return NASB_ERR_UNSUPPORTED;
     if (p.out_f32) {
         mo = mx;  // unused
     } else if (!tc_make_map4(&mo, out, p.TW, p.TH)) {
         return NASB_ERR_UNSUPPORTED;
     }
-    size_t smem = c3_smem(p.nkb, p.stages, stage_bytes);
+    size_t smem = c3_smem(p.nkb, p.stages, stage_bytes, p.brows, so_bytes);
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(c3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
@@ -461,7 +545,7 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     long long grid = (long long)NASB_SM_COUNT * per_sm / p.nnb * p.nnb;
     if (grid < p.nnb) grid = p.nnb;
     if (grid > total * p.nnb) grid = total * p.nnb;
-    c3_tc_kernel<<<(int)grid, C3_THREADS, smem, (cudaStream_t)stream>>>(mx, mb, mo, p);
+    nasb::launch_pdl((c3_tc_kernel), dim3((int)grid), dim3(C3F_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), mx, mb, mo, p);
     NASB_CHECK_LAUNCH();
     return 0;
 }
@@ -514,7 +598,7 @@ extern "C" int nasb_conv3_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, in
             if (per_sm > 2) per_sm = 2;
             long long grid = (long long)NASB_SM_COUNT * per_sm;
             if (grid > total) grid = total;
-            c3_wgrad_tc_kernel<<<(int)grid, C3_THREADS, smem, (cudaStream_t)stream>>>(mx, mz, p);
+            nasb::launch_pdl((c3_wgrad_tc_kernel), dim3((int)grid), dim3(C3_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), mx, mz, p);
             NASB_CHECK_LAUNCH();
         }
     }
