@@ -667,6 +667,7 @@ def search_numbers(a, dev, rank, world, rounds, warm_rounds, n_task0, task1_iter
             "rewards": [[round(float(t[s, 0]), 5) for s in range(world)] for t in hist],
             "phase_seconds_per_candidate_rank0": {k: round(v / max(rounds, 1), 3) for k, v in phases.items()},
             "populate_task0_s_per_image": t_populate_per_image, "n_task0": n_task0, "task1_iterations": task1_iters,
+            "max_memory_reserved_gb": round(torch.cuda.max_memory_reserved() / 2 ** 30, 2),
             "val_images": len(val) * 64, "errors": errors[:3],
             "recipe": "task0: 5 epochs x %d it (batch 64, 64x64 feats, KD+aux, Adam, clip, Polyak) + validate; TaskPerformer; "
                       "task1: %d it of train_segmenter (batch 32 @350x350, host batches) + validate; fresh model + CUDA-graph "

@@ -17,7 +17,7 @@
 namespace nasb {
 
 constexpr int C3_THREADS = 128;   // weight-gradient kernel
-constexpr int C3F_THREADS = 192;  // forward / data-gradient kernel: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int C3F_THREADS = 320;  // forward / data-gradient kernel: warps 0-7 epilogue (two groups), warp 8 TMA producer, warp 9 MMA issuer
 constexpr int C3_TILE = 128;      // pixels per patch
 constexpr int C3_NB = 64;         // output channels per CTA
 
@@ -36,7 +36,6 @@ struct C3Params {
     int act;
     void *out;           // fp32 output when out_f32, else the TMA map is used
     int out_cs, out_f32;
-    int so_bufs;         // bf16 output tiles in shared memory (2 when they fit, else 1)
     int f32_staged;      // fp32 output with out_cs == N: the patch is a contiguous span per image row, written from a staging tile
     double *stats;
 };
@@ -44,11 +43,17 @@ struct C3Params {
 __device__ __forceinline__ void c3_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void c3_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void c3_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void c3_epi_barrier(int group) {
+    if (group == 0)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 // Warp-specialised: the producer streams (patch, tap / row-halo, K block) items through a ring of `stages` shared-memory
-// slots, the MMA issuer accumulates a patch into one of TWO TMEM accumulators, the four epilogue warps drain the other one.
+// slots, the MMA issuer accumulates patch i into TMEM accumulator i & 1, and epilogue group i & 1 (four warps each, its own
+// accumulator, output tile and named barrier) drains it.  Two groups because ONE warp per SM sub-partition cannot hide its own
+// ALU latency: ncu showed the single-group epilogue 69 % busy at ~0.25 instructions per clock, the MMA warp waiting on it.
 // Barriers: full[s] (tx bytes, producer -> MMA), done[s] (commit, MMA -> producer), acc_full[a] (commit, MMA -> epilogue),
 // acc_empty[a] (128 arrivals, epilogue -> MMA).  Completion k of each barrier requires the waiter of completion k-1 to have
 // passed (item g+S waits done of item g, committed after the MMA's wait on full of item g; patch i+2 waits acc_empty of
@@ -64,10 +69,10 @@ __global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constan
     uint8_t *sB = smem;                                        // 9*nkb x [brows x 128 B]
     uint8_t *sA = sB + (size_t)nb_items * b_tile;              // stages x stage_bytes
     const size_t stage_bytes = p.halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
-    uint8_t *sO = sA + (size_t)p.stages * stage_bytes;          // bf16: so_bufs x [128 x 128 B]; staged fp32: [128 x N] floats
-    const size_t so_bytes = p.out_f32 ? (p.f32_staged ? (((size_t)C3_TILE * p.N * 4 + 1023) & ~(size_t)1023) : 0)
-                                      : (size_t)p.so_bufs * C3_TILE * 128;
-    float *s_scale = (float *)(sO + so_bytes);
+    uint8_t *sO = sA + (size_t)p.stages * stage_bytes;          // per epilogue group: bf16 [128 x 128 B] or staged fp32 [128 x N]
+    const size_t so_tile = p.out_f32 ? (p.f32_staged ? (((size_t)C3_TILE * p.N * 4 + 1023) & ~(size_t)1023) : 0)
+                                     : (size_t)C3_TILE * 128;
+    float *s_scale = (float *)(sO + 2 * so_tile);
     float *s_shift = s_scale + C3_NB;
     float *s_sum = s_shift + C3_NB;
     float *s_sq = s_sum + C3_NB;
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constan
         s_sum[i] = 0.f;
         s_sq[i] = 0.f;
     }
-    if (warp == 5) tmem_alloc(s_tmem, 2 * acc_cols);
+    if (warp == 9) tmem_alloc(s_tmem, 2 * acc_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -124,20 +129,20 @@ __global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constan
     // pipeline item: (patch, tap, K block) in tap mode, (patch, K block) in row-halo mode
     const int items_pp = p.halo ? p.nkb : nb_items;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0 && my_patches > 0) {  // ---- producer
             mbar_expect_tx(bar_b, (uint32_t)(nb_items * b_tile));
             for (int j = 0; j < nb_items; ++j) {
                 const int tap = j / p.nkb, kb = j - tap * p.nkb;
                 tma_load_2d(sB + (size_t)j * b_tile, &map_b, bar_b, kb * 64, tap * p.nr + n0);
             }
-            int g = 0;
+            int g = 0, s = 0;
+            uint32_t done_par = 0;  // parity the producer waits for on done[s]: completion (pass - 1) of the slot, pass >= 1
             for (int pi = 0; pi < my_patches; ++pi) {
                 int n, y0, x0;
                 patch_origin(pi, n, y0, x0);
                 for (int j = 0; j < items_pp; ++j, ++g) {
-                    const int s = g % S;
-                    if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
+                    if (g >= S) mbar_wait(&done[s], done_par);
                     if (p.halo) {
                         // rows y0 - pad + {0, dil, 2 dil}, pixels x0 - pad .. x0 - pad + TW + 2 dil - 1: tap (ty, tx) is the 128
                         // consecutive 128-byte rows of row buffer ty that start at pixel tx*dil (both TMA and UMMA swizzle on
@@ -153,77 +158,109 @@ __global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constan
                         tma_load_4d_sw(sA + (size_t)s * C3_TILE * 128, &map_x, &full[s], kb * 64,
                                        x0 - p.pad + (tap % 3) * p.dil, y0 - p.pad + (tap / 3) * p.dil, n);
                     }
+                    if (++s == S) {
+                        s = 0;
+                        if (g >= S) done_par ^= 1;
+                    }
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (lane == 0 && my_patches > 0) {  // ---- MMA issuer
+            // Descriptors are built ONCE: a SWIZZLE_128B K-major descriptor differs between operand tiles only in its 14-bit
+            // start-address field (bytes >> 4), so every MMA's descriptors are `base + constant` (the first version rebuilt
+            // both descriptors from byte addresses for each of the 36 MMAs of a patch: ~110 dependent uniform-datapath
+            // instructions per tap, 3 us per patch -- ncu showed this single thread as the kernel's critical path).
             const uint32_t idesc = make_idesc_bf16(npb);
+            const uint64_t a_desc0 = make_desc_sw128(smem_u32(sA)), b_desc0 = make_desc_sw128(smem_u32(sB));
+            const uint32_t stage16 = (uint32_t)(stage_bytes >> 4), btile16 = (uint32_t)(b_tile >> 4);
+            const uint32_t row16 = (uint32_t)p.rowbuf >> 4, col16 = (uint32_t)p.dil * 8;  // halo: row buffer / tap column step
             mbar_wait(bar_b, 0);
-            int g = 0;
+            int g = 0, s = 0;
+            uint32_t full_par = 0;  // parity of full[s] for the current pass over the ring
             for (int pi = 0; pi < my_patches; ++pi) {
                 const int a = pi & 1;
                 const uint32_t acc = tmem_base + (uint32_t)a * acc_cols;
                 if (pi >= 2) mbar_wait(&acc_empty[a], (uint32_t)((pi >> 1) - 1) & 1);
                 for (int j = 0; j < items_pp; ++j, ++g) {
-                    const int s = g % S;
-                    mbar_wait(&full[s], (uint32_t)(g / S) & 1);
+                    mbar_wait(&full[s], full_par);
                     tc_fence_after();
                     const int kb = p.halo ? j : j % p.nkb;
                     const int krem = p.K - kb * 64;
                     const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+                    const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)s * stage16);
                     if (p.halo) {
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t a0 = smem_u32(sA + (size_t)s * stage_bytes + (size_t)(tap / 3) * p.rowbuf) +
-                                                (uint32_t)((tap % 3) * p.dil) * 128;
-                            const uint32_t b0 = smem_u32(sB + (size_t)(tap * p.nkb + kb) * b_tile);
-                            for (int ks = 0; ks < ksteps; ++ks)
-                                umma_f16(acc, make_desc_sw128(a0 + ks * 32), make_desc_sw128(b0 + ks * 32), idesc,
-                                         (j > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                        const uint64_t b_kb = b_desc0 + (uint64_t)((uint32_t)kb * btile16);
+                        const uint32_t b_tap = (uint32_t)p.nkb * btile16;
+                        if (ksteps == 4) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t ad = a_st + (uint64_t)((uint32_t)(tap / 3) * row16 + (uint32_t)(tap % 3) * col16);
+                                const uint64_t bd = b_kb + (uint64_t)((uint32_t)tap * b_tap);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_f16(acc, ad + 2 * ks, bd + 2 * ks, idesc, (j > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t ad = a_st + (uint64_t)((uint32_t)(tap / 3) * row16 + (uint32_t)(tap % 3) * col16);
+                                const uint64_t bd = b_kb + (uint64_t)((uint32_t)tap * b_tap);
+                                for (int ks = 0; ks < ksteps; ++ks)
+                                    umma_f16(acc, ad + 2 * ks, bd + 2 * ks, idesc, (j > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                            }
                         }
                     } else {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)s * C3_TILE * 128) + ks * 32);
-                            uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)j * b_tile) + ks * 32);
-                            umma_f16(acc, ad, bd, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-                        }
+                        const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)j * btile16);
+                        for (int ks = 0; ks < ksteps; ++ks) umma_f16(acc, a_st + 2 * ks, bd + 2 * ks, idesc, (j > 0 || ks > 0) ? 1u : 0u);
                     }
                     umma_commit(&done[s]);  // the slot may be refilled once these MMAs have read it
+                    if (++s == S) {
+                        s = 0;
+                        full_par ^= 1;
+                    }
                 }
                 umma_commit(&acc_full[a]);
             }
         }
     } else {
-        // ---- epilogue warps 0..3 (128 threads): thread = TMEM lane = pixel of the patch
-        const int row = warp * 32 + lane;
-        float *sF = reinterpret_cast<float *>(sO);
-        for (int pi = 0; pi < my_patches; ++pi) {
-            const int a = pi & 1;
+        // ---- epilogue group g = warps 4g..4g+3 (128 threads): patches i = g, g+2, ...; thread = TMEM lane = pixel of the patch
+        const int grp = warp >> 2, gt = tid & 127;
+        const int row = (warp & 3) * 32 + lane;
+        uint8_t *sOt = sO + (size_t)grp * so_tile;
+        float *sF = reinterpret_cast<float *>(sOt);
+        const float hi = p.act == NASB_ACT_RELU6 ? 6.f : INFINITY;
+        const uint32_t acc = tmem_base + (((uint32_t)(warp & 3) * 32) << 16) + (uint32_t)grp * acc_cols;
+        for (int pi = grp; pi < my_patches; pi += 2) {
             int n, y0, x0;
             patch_origin(pi, n, y0, x0);
-            uint8_t *sOt = sO + (size_t)(p.so_bufs == 2 ? a : 0) * C3_TILE * 128;
-            mbar_wait(&acc_full[a], (uint32_t)(pi >> 1) & 1);
+            mbar_wait(&acc_full[grp], (uint32_t)(pi >> 1) & 1);
             tc_fence_after();
             if (!p.out_f32) {
-                if (tid == 0) {  // the bulk store that last read this tile (patch pi - so_bufs) has finished reading it
-                    if (p.so_bufs == 2) {
-                        if (pi >= 2) c3_store_wait_read1();
-                    } else if (pi >= 1) {
-                        tma_store_wait_read();
-                    }
-                }
-                c3_epi_barrier();
+                if (gt == 0 && pi >= 2) tma_store_wait_read();  // this group's previous bulk store has finished reading the tile
+                c3_epi_barrier(grp);
             } else if (p.f32_staged) {
-                c3_epi_barrier();  // the copy-out of the previous patch is complete
+                c3_epi_barrier(grp);  // the copy-out of this group's previous patch is complete
             }
             const int py = y0 + row / p.TW, px = x0 + row % p.TW;
             const bool row_ok = py < p.H && px < p.W;
 #pragma unroll 1
             for (int c0 = 0; c0 < npb; c0 += 16) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * acc_cols + (uint32_t)c0, v);
+                tmem_ld16(acc + (uint32_t)c0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] * s_scale[c0 + j] + s_shift[c0 + j], p.act);
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c0 + j);
+                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c0 + j);
+                    v[j] = fmaf(v[j], sc.x, sh.x);
+                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                }
+                if (p.act != NASB_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], 0.f), hi);
+                }
                 if (p.stats) {
                     float q[16], q2[16];
 #pragma unroll
@@ -254,27 +291,29 @@ __global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constan
                     const int ch = c0 >> 3;
                     uint8_t *orow = sOt + (size_t)row * 128;
                     uint4 q0, q1;
-                    bf16 *e0 = reinterpret_cast<bf16 *>(&q0), *e1 = reinterpret_cast<bf16 *>(&q1);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        e0[j] = __float2bfloat16_rn(v[j]);
-                        e1[j] = __float2bfloat16_rn(v[8 + j]);
-                    }
+                    q0.x = pack_bf16x2(v[0], v[1]);
+                    q0.y = pack_bf16x2(v[2], v[3]);
+                    q0.z = pack_bf16x2(v[4], v[5]);
+                    q0.w = pack_bf16x2(v[6], v[7]);
+                    q1.x = pack_bf16x2(v[8], v[9]);
+                    q1.y = pack_bf16x2(v[10], v[11]);
+                    q1.z = pack_bf16x2(v[12], v[13]);
+                    q1.w = pack_bf16x2(v[14], v[15]);
                     *reinterpret_cast<uint4 *>(orow + (((ch) ^ (row & 7)) << 4)) = q0;
                     *reinterpret_cast<uint4 *>(orow + (((ch + 1) ^ (row & 7)) << 4)) = q1;
                 }
             }
             tc_fence_before();
-            c3_arrive(&acc_empty[a]);  // this thread is done with accumulator a
+            c3_arrive(&acc_empty[grp]);  // this thread is done with the accumulator
             if (!p.out_f32) {
                 fence_proxy_async();
-                c3_epi_barrier();  // patch complete in shared memory
-                if (tid == 0) {
+                c3_epi_barrier(grp);  // patch complete in shared memory
+                if (gt == 0) {
                     tma_store_4d(&map_o, sOt, n0, x0, y0, n);
                     tma_store_commit();
                 }
             } else if (p.f32_staged) {
-                c3_epi_barrier();
+                c3_epi_barrier(grp);
                 // out_cs == N: each image row of the patch is ONE contiguous span of (valid pixels x N) floats
                 const int vw = p.W - x0 < p.TW ? p.W - x0 : p.TW;
                 for (int ty = 0; ty < p.TH && y0 + ty < p.H; ++ty) {
@@ -283,27 +322,27 @@ __global__ void __launch_bounds__(C3F_THREADS) c3_tc_kernel(const __grid_constan
                     const int cnt = vw * nblk;
                     if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
                         const int c4 = cnt >> 2;
-                        for (int e = tid; e < c4; e += 128)
+                        for (int e = gt; e < c4; e += 128)
                             reinterpret_cast<float4 *>(dst)[e] = reinterpret_cast<const float4 *>(src)[e];
-                        for (int e = (c4 << 2) + tid; e < cnt; e += 128) dst[e] = src[e];
+                        for (int e = (c4 << 2) + gt; e < cnt; e += 128) dst[e] = src[e];
                     } else {
-                        for (int e = tid; e < cnt; e += 128) dst[e] = src[e];
+                        for (int e = gt; e < cnt; e += 128) dst[e] = src[e];
                     }
                 }
             }
         }
-        if (tid == 0) tma_store_wait_all();
-        if (p.stats) {
-            c3_epi_barrier();
-            for (int c = tid; c < nblk; c += 128) {
-                atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
-                atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
-            }
+        if (gt == 0) tma_store_wait_all();
+    }
+    if (p.stats) {  // shared-memory partials of both groups -> global fp64 sums
+        __syncthreads();
+        for (int c = tid; c < nblk; c += C3F_THREADS) {
+            atomicAdd(&p.stats[n0 + c], (double)s_sum[c]);
+            atomicAdd(&p.stats[p.N + n0 + c], (double)s_sq[c]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 2 * acc_cols);
+    if (warp == 9) tmem_dealloc(tmem_base, 2 * acc_cols);
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -350,39 +389,64 @@ __global__ void __launch_bounds__(C3_THREADS) c3_wgrad_tc_kernel(const __grid_co
 
     if (tid == 0 && my_patches > 0) {
         const uint32_t idesc = make_idesc_bf16(p.npb) | (1u << 15) | (1u << 16);  // A, B MN-major
-        const long long total_items = (long long)my_patches * PAIRS;
-        auto issue = [&](long long g) {
-            const int s = (int)(g % S);
-            if (g >= S) mbar_wait(&done[s], (uint32_t)((g / S) - 1) & 1);
-            const int pi = (int)(g / PAIRS), j = (int)(g % PAIRS);
+        const int total_items = my_patches * PAIRS;
+        // producer and consumer cursors of the ONE thread that drives both (item = (patch, tap pair)); plain counters instead
+        // of 64-bit divisions, descriptors as base + constant (start-address field in 16-byte units)
+        int g = 0, g_s = 0, g_pi = 0, g_j = 0;
+        uint32_t g_par = 0;  // parity the producer waits for on done[g_s] (passes >= 1)
+        int gn = 0, gy0 = 0, gx0 = 0;
+        auto origin = [&](int pi, int &n, int &y0, int &x0) {
             const int t = (int)blockIdx.x + pi * (int)gridDim.x;
-            const int n = t / tiles_img, r = t - n * tiles_img, ty = r / p.tiles_x;
-            const int y0 = ty * p.TH, x0 = (r - ty * p.tiles_x) * p.TW;
-            const int ntaps = j == PAIRS - 1 ? 1 : 2;
-            mbar_expect_tx(&full[s], (uint32_t)((ntaps + (j == 0 ? 1 : 0)) * C3_TILE * 128));
-            for (int q = 0; q < ntaps; ++q) {
-                const int tap = 2 * j + q;
-                tma_load_4d_sw(sX + ((size_t)s * 2 + q) * C3_TILE * 128, &map_x, &full[s], 0, x0 - p.pad + (tap % 3) * p.dil,
-                               y0 - p.pad + (tap / 3) * p.dil, n);
-            }
-            if (j == 0) tma_load_4d_sw(sZ + (size_t)(pi & 1) * C3_TILE * 128, &map_dz, &full[s], 0, x0, y0, n);
+            n = t / tiles_img;
+            const int r = t - n * tiles_img, ty = r / p.tiles_x;
+            y0 = ty * p.TH;
+            x0 = (r - ty * p.tiles_x) * p.TW;
         };
-        long long g_issued = 0;
-        while (g_issued < total_items && g_issued < S) issue(g_issued++);
-        for (long long c = 0; c < total_items; ++c) {
-            if (c >= 1 && g_issued < total_items) issue(g_issued++);
-            const int s = (int)(c % S), pi = (int)(c / PAIRS), j = (int)(c % PAIRS);
-            mbar_wait(&full[s], (uint32_t)(c / S) & 1);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sX + (size_t)s * 2 * C3_TILE * 128);
-            const uint32_t b0 = smem_u32(sZ + (size_t)(pi & 1) * C3_TILE * 128);
-#pragma unroll
-            for (int ks = 0; ks < C3_TILE / 16; ++ks) {
-                uint64_t ad = make_desc_mn_sw128(a0 + ks * 2048, C3_TILE * 128);
-                uint64_t bd = make_desc_mn_sw128(b0 + ks * 2048, C3_TILE * 128);
-                umma_f16(tmem_base + (uint32_t)(j * p.npb), ad, bd, idesc, (pi > 0 || ks > 0) ? 1u : 0u);
+        origin(0, gn, gy0, gx0);
+        auto issue = [&]() {
+            if (g >= S) mbar_wait(&done[g_s], g_par);
+            const int ntaps = g_j == PAIRS - 1 ? 1 : 2;
+            mbar_expect_tx(&full[g_s], (uint32_t)((ntaps + (g_j == 0 ? 1 : 0)) * C3_TILE * 128));
+            for (int q = 0; q < ntaps; ++q) {
+                const int tap = 2 * g_j + q;
+                tma_load_4d_sw(sX + ((size_t)g_s * 2 + q) * C3_TILE * 128, &map_x, &full[g_s], 0, gx0 - p.pad + (tap % 3) * p.dil,
+                               gy0 - p.pad + (tap / 3) * p.dil, gn);
             }
+            if (g_j == 0) tma_load_4d_sw(sZ + (size_t)(g_pi & 1) * C3_TILE * 128, &map_dz, &full[g_s], 0, gx0, gy0, gn);
+            ++g;
+            if (++g_s == S) {
+                g_s = 0;
+                if (g > S) g_par ^= 1;
+            }
+            if (++g_j == PAIRS) {
+                g_j = 0;
+                ++g_pi;
+                if (g_pi < my_patches) origin(g_pi, gn, gy0, gx0);
+            }
+        };
+        while (g < total_items && g < S) issue();
+        const uint64_t xd0 = make_desc_mn_sw128(smem_u32(sX), C3_TILE * 128), zd0 = make_desc_mn_sw128(smem_u32(sZ), C3_TILE * 128);
+        constexpr uint32_t SLOT16 = (2 * C3_TILE * 128) >> 4, ZBUF16 = (C3_TILE * 128) >> 4, KS16 = 2048 >> 4;
+        int s = 0, pi = 0, j = 0;
+        uint32_t par = 0;
+        for (int c = 0; c < total_items; ++c) {
+            if (c >= 1 && g < total_items) issue();
+            mbar_wait(&full[s], par);
+            tc_fence_after();
+            const uint64_t ad0 = xd0 + (uint64_t)((uint32_t)s * SLOT16), bd0 = zd0 + (uint64_t)((uint32_t)(pi & 1) * ZBUF16);
+            const uint32_t acc = tmem_base + (uint32_t)(j * p.npb);
+#pragma unroll
+            for (int ks = 0; ks < C3_TILE / 16; ++ks)
+                umma_f16(acc, ad0 + (uint64_t)(ks * KS16), bd0 + (uint64_t)(ks * KS16), idesc, (pi > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&done[s]);
+            if (++s == S) {
+                s = 0;
+                par ^= 1;
+            }
+            if (++j == PAIRS) {
+                j = 0;
+                ++pi;
+            }
         }
         umma_commit(final_bar);  // completes exactly once, after every MMA of this CTA
     }
@@ -464,7 +528,7 @@ extern "C" int nasb_pack_conv3_bf16(const float *w, int Co, int Ci, int mode, vo
 extern "C" int nasb_conv3_tc_supported(int K, int N) {
     if (K < 1 || N < 1 || N > 4096) return 0;
     int nkb = (K + 63) / 64;
-    return c3_smem(nkb, 2, (size_t)C3_TILE * 128, C3_NB, (size_t)C3_TILE * 128) <= 200 * 1024 ? 1 : 0;
+    return c3_smem(nkb, 2) <= 216 * 1024 ? 1 : 0;
 }
 
 extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, int dil, int pad, const float *scale,
@@ -498,17 +562,18 @@ extern "C" int nasb_conv3_tc_fwd(const NasbTensor *x, const void *wpack, int N, 
     p.out_f32 = out->dtype == NASB_F32 ? 1 : 0;
     p.f32_staged = (p.out_f32 && out->cstride == N && N <= C3_NB) ? 1 : 0;
     p.brows = N <= 32 ? 32 : C3_NB;
-    // preference order: row-halo ring before tap ring, two output tiles before one; each needs >= 2 ring stages to fit
-    const size_t f32_so = p.f32_staged ? (((size_t)C3_TILE * N * 4 + 1023) & ~(size_t)1023) : 0;
+    // two output tiles (one per epilogue group); preference: staged fp32 output before direct stores, row-halo ring before
+    // tap ring; each combination needs >= 2 ring stages to fit
     size_t stage_bytes = 0, so_bytes = 0;
     bool placed = false;
-    for (int use_halo = p.halo; use_halo >= 0 && !placed; --use_halo) {
-        for (int bufs = 2; bufs >= 1 && !placed; --bufs) {
+    const int want_halo = p.halo;
+    for (int staged = p.f32_staged; staged >= 0 && !placed; --staged) {
+        so_bytes = p.out_f32 ? (staged ? 2 * (((size_t)C3_TILE * N * 4 + 1023) & ~(size_t)1023) : 0) : (size_t)2 * C3_TILE * 128;
+        for (int use_halo = want_halo; use_halo >= 0 && !placed; --use_halo) {
             stage_bytes = use_halo ? (size_t)3 * p.rowbuf : (size_t)C3_TILE * 128;
-            so_bytes = p.out_f32 ? f32_so : (size_t)bufs * C3_TILE * 128;
             if (c3_smem(p.nkb, 2, stage_bytes, p.brows, so_bytes) > 216 * 1024) continue;
             p.halo = use_halo;
-            p.so_bufs = bufs;
+            p.f32_staged = staged;
             p.stages = use_halo ? 3 : 8;
             while (p.stages > 2 && c3_smem(p.nkb, p.stages, stage_bytes, p.brows, so_bytes) > 216 * 1024) --p.stages;
             placed = true;

@@ -124,11 +124,12 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
             mbar_wait(bar_a, parity);
             tc_fence_after();
             const int ksteps = (p.K + 15) / 16;
+            // descriptors differ only in the start-address field (16-byte units): base + constant per K step
+            const uint64_t ad0 = make_desc_sw128(smem_u32(sA)), bd0 = make_desc_sw128(smem_u32(sB));
             for (int ks = 0; ks < ksteps; ++ks) {
-                const int kb = ks >> 2, kin = ks & 3;  // 4 K-steps of 16 elements (32 B) per 128-byte swizzle row
-                uint64_t ad = make_desc_sw128(smem_u32(sA + (size_t)kb * TILE_M * 128) + kin * 32);
-                uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * TILE_N * 128) + kin * 32);
-                umma_f16(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                const uint32_t kb = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3;  // 4 K-steps of 16 elements (32 B) per swizzle row
+                umma_f16(tmem_base, ad0 + (uint64_t)(kb * (TILE_M * 128 / 16) + kin * 2),
+                         bd0 + (uint64_t)(kb * (TILE_N * 128 / 16) + kin * 2), idesc, ks > 0 ? 1u : 0u);
             }
             umma_commit(bar_mma);
         }
@@ -349,17 +350,20 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
         if (lane == 0 && my_n > 0) {  // ---- MMA issuer
             const uint32_t idesc = make_idesc_bf16(npb);
             const int ksteps = (p.K + 15) / 16;
+            // descriptors differ only in the start-address field (16-byte units): base + constant per stage / K step
+            const uint64_t a_desc0 = make_desc_sw128(smem_u32(sA)), b_desc0 = make_desc_sw128(smem_u32(sB));
             mbar_wait(b_full, 0);
             for (int i = 0; i < my_n; ++i) {
                 const int s = i % WS_SA, a = i & 1;
                 if (i >= 2) mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) - 1) & 1);
                 mbar_wait(&a_full[s], (uint32_t)(i / WS_SA) & 1);
                 tc_fence_after();
+                const uint64_t ad0 = a_desc0 + (uint64_t)((uint32_t)(s * p.nkb) * (TILE_M * 128 / 16));
+                const uint32_t acc = tmem_base + (uint32_t)a * 64;
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    const int kb = ks >> 2, kin = ks & 3;
-                    uint64_t ad = make_desc_sw128(smem_u32(sA + ((size_t)s * p.nkb + kb) * TILE_M * 128) + kin * 32);
-                    uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * TILE_N * 128) + kin * 32);
-                    umma_f16(tmem_base + (uint32_t)a * 64, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                    const uint32_t kb = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3;
+                    umma_f16(acc, ad0 + (uint64_t)(kb * (TILE_M * 128 / 16) + kin * 2),
+                             b_desc0 + (uint64_t)(kb * (TILE_N * 128 / 16) + kin * 2), idesc, ks > 0 ? 1u : 0u);
                 }
                 umma_commit(&a_empty[s]);   // the A stage may be refilled once these MMAs have read it
                 umma_commit(&acc_full[a]);  // ... and the accumulator is complete
@@ -523,6 +527,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
 
     if (tid == 0 && my_n > 0) {
         uint32_t idesc = make_idesc_bf16(p.npad) | (1u << 15) | (1u << 16);  // A and B MN-major
+        const uint64_t wg_desc0 = make_desc_mn_sw128(smem_u32(smem), TILE_M * 128);  // stage / K-step descriptors = base + constant
         auto load = [&](int i) {
             const int s = i & 1;
             uint8_t *st = smem + (size_t)s * stage_bytes;
@@ -541,13 +546,11 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
             }
             mbar_wait(&bars[s], (uint32_t)(i >> 1) & 1);
             tc_fence_after();
-            const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + a_bytes;
+            const uint64_t ad0 = wg_desc0 + (uint64_t)((uint32_t)(s * stage_bytes) >> 4), bd0 = ad0 + (uint64_t)((uint32_t)a_bytes >> 4);
 #pragma unroll
-            for (int ks = 0; ks < TILE_M / 16; ++ks) {
-                uint64_t ad = make_desc_mn_sw128(a0 + ks * 2048, TILE_M * 128);
-                uint64_t bd = make_desc_mn_sw128(b0 + ks * 2048, TILE_M * 128);
-                umma_f16(tmem_base, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-            }
+            for (int ks = 0; ks < TILE_M / 16; ++ks)
+                umma_f16(tmem_base, ad0 + (uint64_t)(ks * (2048 / 16)), bd0 + (uint64_t)(ks * (2048 / 16)), idesc,
+                         (i > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&bars[2 + s]);
         }
         umma_commit(&bars[4]);  // completes exactly once, after every MMA of this CTA

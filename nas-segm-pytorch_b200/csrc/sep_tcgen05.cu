@@ -194,12 +194,10 @@ __global__ void __launch_bounds__(SEP_THREADS) sep_tc_kernel(const __grid_consta
             if (tid == 0) {
                 if (g == 0) mbar_wait(bar_b, 0);
                 tc_fence_after();
+                const uint64_t ad0 = make_desc_sw128(sA_a[stage]), bd0 = make_desc_sw128(smem_u32(sB + (size_t)kb * 64 * 128));
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = make_desc_sw128(sA_a[stage] + ks * 32);
-                    const uint64_t bd = make_desc_sw128(smem_u32(sB + (size_t)kb * 64 * 128) + ks * 32);
-                    umma_f16(tmem_base, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                }
+                for (int ks = 0; ks < 4; ++ks)  // K steps of 32 bytes = 2 units of the descriptor's start-address field
+                    umma_f16(tmem_base, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
                 umma_commit(&bar_m[stage]);
             }
         }

@@ -17,6 +17,7 @@ the datasets, the checkpoint saver.  They enter through plain callables:
 ``evaluate_candidate`` is the per-candidate recipe of main_search.py:551-656 on top of this package's engine functions
 (``train_task0`` / ``train_segmenter`` / ``validate`` replay CUDA graphs when ``config().cuda_graphs`` is on).
 """
+import gc
 import queue
 import threading
 import time
@@ -207,6 +208,10 @@ def search_rounds(n_rounds, sample_fn, build_fn, evaluate_fn, update_fn=None, lo
         n_params = compute_params(segmenter)[1] if hasattr(segmenter, "named_parameters") else 0
         out = evaluate_fn(segmenter, samples[rank][0])
         del segmenter
+        # a candidate's captured graphs hang off its modules and their closures point back at the modules: collect the cycle
+        # now, so the graphs' memory returns to the shared capture pool before the next candidate captures (graphs.capture
+        # skips the gc.collect() + empty_cache() torch's own context manager would do at every capture)
+        gc.collect()
         n_epochs = 1
         if isinstance(out, (tuple, list)) and len(out) == 2:  # (reward, epochs run) from evaluate_candidate
             out, n_epochs = float(out[0]), max(int(out[1]), 1)

@@ -4,13 +4,58 @@ At inference sizes the network is launch-bound on the host (~300 C-ABI calls per
 replayed graph is what a latency-sensitive user runs.  The kernels take explicit stream arguments and allocate nothing,
 tensor maps are passed by value, so the whole forward is capturable; torch's allocator serves the activations from the
 graph's private pool."""
+import contextlib
+
 import torch
+
+_pools = {}  # device index -> (pool handle, keep-alive graph)
+
+
+def shared_pool(device=None):
+    """ONE allocator pool for every capture of the process (per device).  torch gives each captured graph a private pool
+    that starts empty, so every activation of a capture is a fresh cudaMalloc (measured in the search loop, where each
+    candidate captures four graphs: 12.8 k torch.empty calls cost 1.07 s of a 10 s candidate), and returns the memory to
+    the driver when the graph dies.  A shared pool kept alive by a one-node graph hands the blocks of the previous
+    candidate's graphs to the next capture.  Sharing is safe here because graphs are replayed one at a time on one stream
+    and nothing but their static inputs / outputs (alive, hence never reused) is read across a replay boundary."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev not in _pools:
+        handle = torch.cuda.graph_pool_handle()
+        g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            g.capture_begin(pool=handle)
+            try:
+                keep = torch.zeros(8, device="cuda:%d" % dev)
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        _pools[dev] = (handle, g, keep)
+    return _pools[dev][0]
+
+
+@contextlib.contextmanager
+def capture(graph, stream=None):
+    """`with capture(g):` -- like `torch.cuda.graph(g)`, but into the shared pool and without the gc.collect() /
+    empty_cache() of torch's context manager (which hands every cached block back to the driver, so the eager iterations
+    of the next candidate start with cudaMalloc again)."""
+    torch.cuda.synchronize()
+    pool = shared_pool()
+    stream = torch.cuda.Stream() if stream is None else stream
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        graph.capture_begin(pool=pool)
+        try:
+            yield
+        finally:
+            graph.capture_end()
+    torch.cuda.current_stream().wait_stream(stream)
 
 
 class GraphedForward:
     """``g = GraphedForward(model, example_input); out = g(x)`` -- x must have example_input's shape / dtype."""
 
-    def __init__(self, model, example, warmup=3):
+    def __init__(self, model, example, warmup=1):
         assert example.is_cuda
         self.model = model
         self.static_in = example.clone()
@@ -28,7 +73,7 @@ class GraphedForward:
         # The captured forward starts with ONE launch that folds BatchNorm and packs the tensor-core operand of every unit
         # (packs.scope -> nasb_conv_units_prepare), so a replay always sees the current weights without the two small
         # per-unit launches (200 of ~360 for arch0).
-        with torch.no_grad(), torch.cuda.graph(self.graph), packs.scope(model):
+        with torch.no_grad(), capture(self.graph, s), packs.scope(model):
             self.static_out = model(self.static_in)
         model.train(was_training)
 
@@ -91,7 +136,7 @@ class StepGraph:
         torch.cuda.synchronize()
         l0 = lib.launches
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with capture(self.graph, self.side):
             self.static_loss = self.fn(*self.static_inputs).detach()
         self.launches_per_replay = lib.launches - l0
         lib.launches = l0  # capture launched nothing

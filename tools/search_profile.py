@@ -1,6 +1,7 @@
 """Per-call CUDA-event table of the search loop's two training functions at their own geometry (task 0: decoder only on
 cached 64x64 features, batch 64; task 1: end to end, batch 32 @350x350), eager, one stream, a few iterations of one
-candidate.  Usage: python tools/search_profile.py OUT.txt"""
+candidate.  Usage: python tools/search_profile.py OUT.txt   (or --graphs: the same candidate with
+CUDA graphs and no instrumentation, to be run under ncu; tools/summarize_search_launches.py reads the launch list)"""
 import os
 import sys
 import types
@@ -35,11 +36,15 @@ def main():
                 iters[name] += n_it
         return w
 
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    if out_path == "--graphs":  # plain run with CUDA graphs for an `ncu --metrics gpu__time_duration.sum` launch list
+        res = bench.search_numbers(types.SimpleNamespace(), dev, 0, 1, 1, 0, 256, 4, 64)
+        print(res["per_candidate_s"], res["errors"])
+        return
     n_task0, task1_iters = 128, 3
     trainer.train_task0 = wrap("train_task0", trainer.train_task0, n_task0 // 64)
     trainer.train_segmenter = wrap("train_segmenter", trainer.train_segmenter, task1_iters)
-    dev = torch.device("cuda:0")
-    torch.cuda.set_device(dev)
     res = bench.search_numbers(types.SimpleNamespace(), dev, 0, 1, 1, 0, n_task0, task1_iters, 64)
     with open(out_path, "w") as f:
         f.write("# errors: %s\n" % res["errors"])
