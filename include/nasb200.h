@@ -114,7 +114,9 @@ int nasb_stem_im2col(const NasbTensor *img, int ks, int stride, int dil, int pad
  * operands, tcgen05.mma (kind::f16, M=128) with the fp32 accumulator in TMEM, fused epilogue, TMA store.
  * nasb_pack_weight_bf16 : fp32 [rows][cols] -> bf16 [R][Kp] (K padded to 8): transpose=0 for the forward
  *                         (R=C_out, K=C_in), transpose=1 for the data gradient (R=C_in, K=C_out).
- * nasb_pw_tc_supported  : 1 if a (K=C_in, N=C_out) pair fits the kernel (8-aligned, N <= 256, smem budget).
+ * nasb_pw_tc_supported  : 1 if a (K=C_in, N=C_out) pair fits the kernel (8-aligned, K and N <= 4096; up to 448 input
+ *                         channels the weights stay resident in shared memory, beyond that K blocks of A and B
+ *                         stream through a ring -- MobileNet-v2's 960-channel layers).
  * nasb_pw_tc_fwd        : out = act(scale*x.W^T + shift) (+res); x/out/res bf16.  stats (optional) -> fp64
  *                         [2][N] sum / sum-of-squares of the stored output, ACCUMULATED (training-mode BN fused
  *                         into the epilogue; finish with nasb_bn_finalize).  The data gradient is the same call

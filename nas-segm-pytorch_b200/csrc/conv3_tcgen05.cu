@@ -492,12 +492,19 @@ __global__ void pack_conv3_kernel(const float *w, int Co, int Ci, int mode, bf16
     out[i] = __float2bfloat16_rn(v);
 }
 
+// 128-pixel patch TH x TW: the shape that wastes the fewest pixels on the image edges (W = 88: 4 x 32 covers 96 columns,
+// 2 x 64 would cover 128); ties go to the wider patch (TH == 1 enables the row-halo ring)
 static void pick_patch(int H, int W, int &TH, int &TW) {
-    if (W >= 96) { TH = 1; TW = 128; }
-    else if (W >= 48) { TH = 2; TW = 64; }
-    else if (W >= 24) { TH = 4; TW = 32; }
-    else { TH = 8; TW = 16; }
-    (void)H;
+    long long best = -1;
+    for (int tw = 128; tw >= 16; tw >>= 1) {
+        const int th = C3_TILE / tw;
+        const long long area = (long long)cdiv(W, tw) * tw * ((long long)cdiv(H, th) * th);
+        if (best < 0 || area < best) {
+            best = area;
+            TH = th;
+            TW = tw;
+        }
+    }
 }
 
 // shared memory of the forward kernel: weight taps + ring + output staging + constants/barriers + alignment slack

@@ -24,6 +24,7 @@ namespace nasb {
 struct PwParams {
     int M, K, N;     // pixels, C_in, C_out
     int nkb, nnb;    // K blocks of 64, N blocks of 64 (one N block per CTA)
+    int kring;       // > 0: warp-specialised kernel streams (A, B) K blocks through a ring of `kring` stages (large C_in)
     const float *scale, *shift;
     int act;
     const bf16 *res;
@@ -275,6 +276,8 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 // acc_full of item i), so a parity wait can never be overtaken by two phases.
 constexpr int WS_THREADS = 192;
 constexpr int WS_SA = 2;
+constexpr int WS_RING_MAX = 8;                                    // K-ring mode: at most 8 stages
+constexpr int WS_RING_STAGE = TILE_M * 128 + TILE_N * 128;       // one A K-block + one B K-block (24 KB)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -290,7 +293,9 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sB = smem;                                               // nkb x [64 x 128 B]
     uint8_t *sA = sB + (size_t)p.nkb * TILE_N * 128;                  // WS_SA x nkb x [128 x 128 B]
-    uint8_t *sO = sA + (size_t)WS_SA * p.nkb * TILE_M * 128;          // 2 x [128 x 128 B]
+    // K-ring mode (C_in too large for resident weights + whole A tiles: MobileNet-v2's 960-channel layers): the same shared
+    // memory holds `kring` stages of [A K-block 128 x 128 B | B K-block 64 x 128 B]; weights are re-read per tile out of L2
+    uint8_t *sO = p.kring ? smem + (size_t)p.kring * WS_RING_STAGE : sA + (size_t)WS_SA * p.nkb * TILE_M * 128;  // 2 x [128 x 128 B]
     float *s_scale = (float *)(sO + (size_t)2 * TILE_M * 128);
     float *s_shift = s_scale + TILE_N;
     float *s_sum = s_shift + TILE_N;
@@ -300,7 +305,9 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
     uint64_t *a_empty = a_full + WS_SA;     // [WS_SA]
     uint64_t *acc_full = a_empty + WS_SA;   // [2]
     uint64_t *acc_empty = acc_full + 2;     // [2]
-    uint32_t *s_tmem = (uint32_t *)(acc_empty + 2);
+    uint64_t *r_full = acc_empty + 2;       // [WS_RING_MAX] K-ring mode
+    uint64_t *r_empty = r_full + WS_RING_MAX;
+    uint32_t *s_tmem = (uint32_t *)(r_empty + WS_RING_MAX);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.M + TILE_M - 1) / TILE_M;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
     const int npb = (nblk + 15) / 16 * 16;
     const int tile0 = (int)blockIdx.x / p.nnb, tstride = (int)gridDim.x / p.nnb;
     const int my_n = tile0 < ntiles ? (ntiles - 1 - tile0) / tstride + 1 : 0;
+    const int RS = p.kring;
 
     if (tid == 0) {
         mbar_init(b_full, 1);
@@ -319,6 +327,10 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 128);
+        }
+        for (int i = 0; i < WS_RING_MAX; ++i) {
+            mbar_init(&r_full[i], 1);
+            mbar_init(&r_empty[i], 1);
         }
         fence_barrier_init();
     }
@@ -335,7 +347,25 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 4) {
-        if (lane == 0 && my_n > 0) {  // ---- producer
+        if (lane == 0 && my_n > 0 && RS > 0) {  // ---- producer, K-ring mode: one (A, B) K block per ring stage
+            int g = 0, s = 0;
+            uint32_t par = 0;  // parity the producer waits for on r_empty[s] (passes >= 1 over the ring)
+            for (int i = 0; i < my_n; ++i) {
+                const int tile = tile0 + i * tstride;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    if (g >= RS) mbar_wait(&r_empty[s], par);
+                    uint8_t *st = smem + (size_t)s * WS_RING_STAGE;
+                    mbar_expect_tx(&r_full[s], (uint32_t)WS_RING_STAGE);
+                    tma_load_2d(st, &map_a, &r_full[s], kb * 64, tile * TILE_M);
+                    tma_load_2d(st + TILE_M * 128, &map_b, &r_full[s], kb * 64, n0);
+                    ++g;
+                    if (++s == RS) {
+                        s = 0;
+                        if (g > RS) par ^= 1;
+                    }
+                }
+            }
+        } else if (lane == 0 && my_n > 0) {  // ---- producer
             mbar_expect_tx(b_full, (uint32_t)(p.nkb * TILE_N * 128));
             for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sB + (size_t)kb * TILE_N * 128, &map_b, b_full, kb * 64, n0);
             for (int i = 0; i < my_n; ++i) {
@@ -347,7 +377,33 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
             }
         }
     } else if (warp == 5) {
-        if (lane == 0 && my_n > 0) {  // ---- MMA issuer
+        if (lane == 0 && my_n > 0 && RS > 0) {  // ---- MMA issuer, K-ring mode
+            const uint32_t idesc = make_idesc_bf16(npb);
+            const uint64_t ring_desc0 = make_desc_sw128(smem_u32(smem));
+            int s = 0;
+            uint32_t par = 0;
+            for (int i = 0; i < my_n; ++i) {
+                const int a = i & 1;
+                const uint32_t acc = tmem_base + (uint32_t)a * 64;
+                if (i >= 2) mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) - 1) & 1);
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&r_full[s], par);
+                    tc_fence_after();
+                    const int krem = p.K - kb * 64;
+                    const int ksteps = krem >= 64 ? 4 : (krem + 15) / 16;
+                    const uint64_t ad0 = ring_desc0 + (uint64_t)((uint32_t)s * (WS_RING_STAGE / 16));
+                    const uint64_t bd0 = ad0 + (uint64_t)(TILE_M * 128 / 16);
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma_f16(acc, ad0 + (uint64_t)(2 * ks), bd0 + (uint64_t)(2 * ks), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(&r_empty[s]);  // the stage may be refilled once these MMAs have read it
+                    if (++s == RS) {
+                        s = 0;
+                        par ^= 1;
+                    }
+                }
+                umma_commit(&acc_full[a]);
+            }
+        } else if (lane == 0 && my_n > 0) {  // ---- MMA issuer
             const uint32_t idesc = make_idesc_bf16(npb);
             const int ksteps = (p.K + 15) / 16;
             // descriptors differ only in the start-address field (16-byte units): base + constant per stage / K step
@@ -491,11 +547,10 @@ __global__ void __launch_bounds__(WS_THREADS) pw_tc_ws_kernel(const __grid_const
 // 8-pixel groups, 16 pixels (2 groups) per instruction.  A CTA accumulates its pixel chunks in TMEM (two-stage TMA ring),
 // then adds its 128 x C_in fp32 tile to dW with atomics.
 struct WgParams {
-    int M, Co, Ci;   // pixels, channels of this dz block (<= 128), channels of x (<= 256)
-    int npad, nbb;   // C_in rounded to 16, C_in blocks of 64
-    int tmem_cols;
-    float *dw;       // + co0 * ldw already applied
-    int ldw;         // row pitch of dW in floats (= total C_in)
+    int M, Co, Ci;   // pixels, total channels of dz and of x
+    int nco;         // 128-channel blocks of dz; blockIdx.y = (x block of 256 channels) * nco + (dz block)
+    int tmem_cols;   // accumulator columns of the widest x block
+    float *dw;       // [Co][Ci] fp32
 };
 
 constexpr int WG_STAGE_A = 2 * TILE_M * 128;  // two 64-channel blocks of dz
@@ -507,8 +562,14 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     // Co <= 64: only one 64-channel dz block is staged; the descriptor's second block (LBO) then aliases the first x block and
     // produces accumulator rows 64..127 that the epilogue never reads
-    const int a_bytes = p.Co > 64 ? WG_STAGE_A : TILE_M * 128;
-    const int stage_bytes = a_bytes + p.nbb * TILE_M * 128;
+    // this CTA's block of the weight gradient: 128 output channels x 256 input channels (one launch covers all blocks, so the
+    // 960-channel layers of MobileNet-v2 do not become eight serial latency-bound launches)
+    const int co0 = ((int)blockIdx.y % p.nco) * 128, ci0 = ((int)blockIdx.y / p.nco) * 256;
+    const int Co = p.Co - co0 < 128 ? p.Co - co0 : 128, Ci = p.Ci - ci0 < 256 ? p.Ci - ci0 : 256;
+    const int npad = (Ci + 15) / 16 * 16, nbb = (Ci + 63) / 64;
+    float *dw = p.dw + (size_t)co0 * p.Ci + ci0;
+    const int a_bytes = Co > 64 ? WG_STAGE_A : TILE_M * 128;
+    const int stage_bytes = a_bytes + nbb * TILE_M * 128;
     uint64_t *bars = (uint64_t *)(smem + 2 * (size_t)stage_bytes);  // full[2], done[2], final
     uint32_t *s_tmem = (uint32_t *)(bars + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -526,16 +587,16 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
     const uint32_t tmem_base = *s_tmem;
 
     if (tid == 0 && my_n > 0) {
-        uint32_t idesc = make_idesc_bf16(p.npad) | (1u << 15) | (1u << 16);  // A and B MN-major
+        uint32_t idesc = make_idesc_bf16(npad) | (1u << 15) | (1u << 16);  // A and B MN-major
         const uint64_t wg_desc0 = make_desc_mn_sw128(smem_u32(smem), TILE_M * 128);  // stage / K-step descriptors = base + constant
         auto load = [&](int i) {
             const int s = i & 1;
             uint8_t *st = smem + (size_t)s * stage_bytes;
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TILE_M;
             mbar_expect_tx(&bars[s], (uint32_t)stage_bytes);
-            tma_load_2d(st, &map_dz, &bars[s], 0, m0);
-            if (p.Co > 64) tma_load_2d(st + TILE_M * 128, &map_dz, &bars[s], 64, m0);
-            for (int b = 0; b < p.nbb; ++b) tma_load_2d(st + a_bytes + (size_t)b * TILE_M * 128, &map_x, &bars[s], b * 64, m0);
+            tma_load_2d(st, &map_dz, &bars[s], co0, m0);
+            if (Co > 64) tma_load_2d(st + TILE_M * 128, &map_dz, &bars[s], co0 + 64, m0);
+            for (int b = 0; b < nbb; ++b) tma_load_2d(st + a_bytes + (size_t)b * TILE_M * 128, &map_x, &bars[s], ci0 + b * 64, m0);
         };
         load(0);
         for (int i = 0; i < my_n; ++i) {
@@ -561,13 +622,13 @@ __global__ void __launch_bounds__(TC_THREADS) pw_wgrad_tc_kernel(const __grid_co
         tc_fence_after();
         const int co = warp * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+        for (int c0 = 0; c0 < npad; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            if (co < p.Co) {
+            if (co < Co) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < p.Ci) atomicAdd(&p.dw[(size_t)co * p.ldw + c0 + j], v[j]);
+                    if (c0 + j < Ci) atomicAdd(&dw[(size_t)co * p.Ci + c0 + j], v[j]);
             }
         }
     }
@@ -614,7 +675,8 @@ static size_t pw_smem_bytes(int nkb) {
 extern "C" int nasb_pw_tc_supported(int K, int N) {
     if (K < 8 || N < 8 || (K % 8) || (N % 8) || N > 4096) return 0;
     int nkb = (K + 63) / 64;
-    return pw_smem_bytes(nkb) <= 200 * 1024 ? 1 : 0;
+    // beyond 7 K blocks the weights + an A tile no longer fit: the warp-specialised kernel streams K blocks through a ring
+    return (pw_smem_bytes(nkb) <= 200 * 1024 || K <= 4096) ? 1 : 0;
 }
 
 static int pw_tc_launch(const NasbTensor *x, const void *wpack, int N, const float *scale, const float *shift, int act,
@@ -666,9 +728,15 @@ static int pw_tc_launch(const NasbTensor *x, const void *wpack, int N, const flo
     static int ws_mode = -1;
     if (ws_mode < 0) ws_mode = getenv("NASB_PW_WS") ? atoi(getenv("NASB_PW_WS")) : 2;
     int ntiles = (int)((M + TILE_M - 1) / TILE_M);
-    if (!gate && (ws_mode == 1 || (ws_mode == 2 && M <= (1LL << 20)))) {  // warp-specialised schedule (see pw_tc_ws_kernel)
-        const size_t smem_ws = (size_t)p.nkb * TILE_N * 128 + (size_t)WS_SA * p.nkb * TILE_M * 128 + (size_t)2 * TILE_M * 128 +
-                               4 * TILE_N * 4 + 128 + 1024;
+    const bool big_k = pw_smem_bytes(p.nkb) > 200 * 1024;  // K-ring mode of the warp-specialised kernel
+    if (big_k && gate) return NASB_ERR_UNSUPPORTED;
+    if (!gate && (big_k || ws_mode == 1 || (ws_mode == 2 && M <= (1LL << 20)))) {  // warp-specialised schedule (see pw_tc_ws_kernel)
+        size_t smem_ws = (size_t)p.nkb * TILE_N * 128 + (size_t)WS_SA * p.nkb * TILE_M * 128 + (size_t)2 * TILE_M * 128 +
+                         4 * TILE_N * 4 + 256 + 1024;
+        if (big_k || smem_ws > 200 * 1024) {
+            p.kring = p.nkb > 7 ? 6 : 0;
+            if (p.kring) smem_ws = (size_t)p.kring * WS_RING_STAGE + (size_t)2 * TILE_M * 128 + 4 * TILE_N * 4 + 256 + 1024;
+        }
         if (smem_ws <= 200 * 1024) {
             static bool configured_ws = false;
             if (!configured_ws) {
@@ -720,10 +788,9 @@ extern "C" int nasb_pw_tc_dgrad_gated(const NasbTensor *dz, const void *wpack_t,
 }
 
 extern "C" int nasb_pw_tc_wgrad_supported(int Co, int Ci) {
-    if (Co < 8 || Ci < 8 || (Co % 8) || (Ci % 8) || Ci > 256) return 0;
-    int nbb = (Ci + 63) / 64;
-    size_t smem = 2 * ((size_t)WG_STAGE_A + (size_t)nbb * TILE_M * 128) + 64 + 1024;
-    return smem <= 200 * 1024 ? 1 : 0;
+    // any multiple of 8 up to 4096: the launcher walks 128-channel blocks of dz and 256-channel blocks of x
+    if (Co < 8 || Ci < 8 || (Co % 8) || (Ci % 8) || Ci > 4096 || Co > 4096) return 0;
+    return 1;
 }
 
 // dweight[co][ci] += sum over pixels dz[.,co] * x[.,ci]   (1x1 convolution, fp32 [C_out][C_in] layout)
@@ -735,17 +802,6 @@ extern "C" int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float
     if (M == 0) return 0;
     if (M > 0x7fffffffLL) return NASB_ERR_UNSUPPORTED;
     const int Ci = x->c, Co = dz->c;
-    WgParams p{};
-    p.M = (int)M;
-    p.Ci = Ci;
-    p.npad = (Ci + 15) / 16 * 16;
-    p.nbb = (Ci + 63) / 64;
-    int cols = 32;
-    while (cols < p.npad) cols <<= 1;
-    p.tmem_cols = cols;
-    p.ldw = Ci;
-    CUtensorMap mx;
-    if (!tc_make_map2(&mx, x->ptr, (uint64_t)Ci, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 2048));
@@ -753,26 +809,34 @@ extern "C" int nasb_pw_tc_wgrad(const NasbTensor *x, const NasbTensor *dz, float
         configured = true;
     }
     int nchunks = (int)((M + TILE_M - 1) / TILE_M);
-    for (int co0 = 0; co0 < Co; co0 += 128) {
-        CUtensorMap mdz;
-        const int cb = Co - co0 < 128 ? Co - co0 : 128;
-        if (!tc_make_map2(&mdz, (const bf16 *)dz->ptr + co0, (uint64_t)cb, (uint64_t)M, (uint64_t)dz->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
-        p.Co = cb;
-        p.dw = dweight + (size_t)co0 * Ci;
-        const size_t smem = 2 * ((size_t)(cb > 64 ? WG_STAGE_A : TILE_M * 128) + (size_t)p.nbb * TILE_M * 128) + 64 + 1024;
-        int per_sm = (int)((220 * 1024) / smem);
-        if (per_sm > 4) per_sm = 4;
-        if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
-        if (per_sm < 1) per_sm = 1;
-        int grid = NASB_SM_COUNT * per_sm;
-        // every CTA ends with Co x Ci atomics onto the same addresses: at least 16 pixel chunks per CTA (but >= 32 CTAs) --
-        // measured on B200: 2048 chunks 49 -> 27 us, 128 chunks 24 -> 14 us, large M unchanged
-        int want = nchunks / 16 < 32 ? 32 : nchunks / 16;
-        if (grid > want) grid = want;
-        if (grid > nchunks) grid = nchunks;
-        if (grid < 1) grid = 1;
-        nasb::launch_pdl((pw_wgrad_tc_kernel), dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), mdz, mx, p);
-        NASB_CHECK_LAUNCH();
-    }
+    WgParams p{};
+    p.M = (int)M;
+    p.Co = Co;
+    p.Ci = Ci;
+    p.nco = (Co + 127) / 128;
+    const int nci = (Ci + 255) / 256, nblocks = p.nco * nci;
+    const int ci_max = Ci < 256 ? Ci : 256, co_max = Co < 128 ? Co : 128;
+    int cols = 32;
+    while (cols < (ci_max + 15) / 16 * 16) cols <<= 1;
+    p.tmem_cols = cols;
+    p.dw = dweight;
+    CUtensorMap mx, mdz;
+    if (!tc_make_map2(&mx, x->ptr, (uint64_t)Ci, (uint64_t)M, (uint64_t)x->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    if (!tc_make_map2(&mdz, dz->ptr, (uint64_t)Co, (uint64_t)M, (uint64_t)dz->cstride, TILE_M)) return NASB_ERR_UNSUPPORTED;
+    const size_t smem = 2 * ((size_t)(co_max > 64 ? WG_STAGE_A : TILE_M * 128) + (size_t)((ci_max + 63) / 64) * TILE_M * 128) + 64 + 1024;
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
+    if (per_sm < 1) per_sm = 1;
+    // every CTA ends with (its block of) Co x Ci atomics onto the same addresses: at least 16 pixel chunks per CTA, but >= 32
+    // CTAs per launch -- measured on B200: 2048 chunks 49 -> 27 us, 128 chunks 24 -> 14 us, large M unchanged.  The CTAs are
+    // shared out over the channel blocks.
+    int want = nchunks / 16 < 32 ? 32 : nchunks / 16;
+    if (want > NASB_SM_COUNT * per_sm) want = NASB_SM_COUNT * per_sm;
+    int gx = want / nblocks;
+    if (gx > nchunks) gx = nchunks;
+    if (gx < 1) gx = 1;
+    nasb::launch_pdl((pw_wgrad_tc_kernel), dim3(gx, nblocks), dim3(TC_THREADS), smem, (cudaStream_t)((cudaStream_t)stream), mdz, mx, p);
+    NASB_CHECK_LAUNCH();
     return 0;
 }

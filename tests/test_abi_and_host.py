@@ -194,9 +194,9 @@ def test_abi_host_side_contracts_without_a_gpu():
     h = lib.load()
     BAD, UNS = 10002, 10001
     # shape envelopes of the tensor-core paths (include/nasb200.h)
-    assert h.nasb_pw_tc_supported(32, 32) == 1 and h.nasb_pw_tc_supported(448, 320) == 1 and h.nasb_pw_tc_supported(960, 320) == 0
-    assert h.nasb_pw_tc_supported(7, 32) == 0 and h.nasb_pw_tc_supported(32, 12) == 0 and h.nasb_pw_tc_supported(32, 8192) == 0
-    assert h.nasb_pw_tc_wgrad_supported(192, 32) == 1 and h.nasb_pw_tc_wgrad_supported(32, 264) == 0
+    assert h.nasb_pw_tc_supported(32, 32) == 1 and h.nasb_pw_tc_supported(448, 320) == 1 and h.nasb_pw_tc_supported(960, 320) == 1
+    assert h.nasb_pw_tc_supported(7, 32) == 0 and h.nasb_pw_tc_supported(32, 12) == 0 and h.nasb_pw_tc_supported(32, 8192) == 0 and h.nasb_pw_tc_supported(4104, 32) == 0
+    assert h.nasb_pw_tc_wgrad_supported(192, 32) == 1 and h.nasb_pw_tc_wgrad_supported(32, 960) == 1 and h.nasb_pw_tc_wgrad_supported(32, 260) == 0
     assert h.nasb_conv3_tc_supported(64, 19) == 1
     assert h.nasb_pack_conv3_elems(19, 64, 0) > 0
     assert h.nasb_bn_stats_workspace(64) == 64 * (2 * 8 + 2 * 4) and h.nasb_loss_workspace() > 0

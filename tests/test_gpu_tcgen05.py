@@ -43,7 +43,9 @@ def test_tc_gemm_shapes_and_tails():
     bad = []
     for K, N in [(16, 96), (96, 24), (24, 144), (144, 24), (144, 32), (32, 192), (192, 32), (24, 48), (32, 64), (64, 64),
                  (128, 64), (224, 64), (8, 8), (48, 48), (64, 16), (16, 256), (256, 16), (200, 72), (96, 576), (448, 40),
-                 (64, 136)]:
+                 (64, 136),
+                 # K-ring mode of the warp-specialised kernel (more than 7 K blocks): MobileNet-v2's 960-channel layers
+                 (960, 160), (960, 320), (576, 96), (520, 24), (1280, 40)]:
         assert lib.load().nasb_pw_tc_supported(K, N) == 1, (K, N)
         for M in (1, 100, 128, 129, 4099):
             x = torch.randn(1, 1, M, K, generator=g, device="cuda").to(torch.bfloat16)
@@ -85,6 +87,28 @@ def test_tc_epilogues_slices_and_stats():
     assert torch.allclose(st[N:], (yd * yd).sum(0), rtol=1e-4, atol=1e-2)
 
 
+def test_tc_k_ring_epilogues_stats_and_many_tiles():
+    """Large C_in (K-ring mode): every epilogue variant, the fused statistics, and enough tiles per CTA for the ring and the
+    accumulator barriers to cycle through many phases."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    K, N = 960, 160
+    for M in (128 * 700 + 5, 3872):
+        x = torch.randn(1, 1, M, K, generator=g, device="cuda").to(torch.bfloat16)
+        wt = torch.randn(N, K, generator=g, device="cuda") / K ** 0.5
+        scale = torch.rand(N, generator=g, device="cuda") + 0.5
+        shift = torch.randn(N, generator=g, device="cuda")
+        res = torch.randn(1, 1, M, N, generator=g, device="cuda").to(torch.bfloat16)
+        for act, r in ((lib.ACT_NONE, None), (lib.ACT_RELU6, res), (lib.ACT_RELU, None)):
+            y, _ = _run_tc(x, wt, scale, shift, act, r)
+            ref = _ref(x, wt, scale, shift, act, r)
+            err = float((y.float().reshape(-1, N) - ref).abs().max() / ref.abs().max())
+            assert err < 1e-2, (M, act, r is not None, err)
+        y, st = _run_tc(x, wt, None, None, lib.ACT_NONE, None, stats=True)
+        yd = y.float().reshape(-1, N).double()
+        assert torch.allclose(st[:N], yd.sum(0), rtol=1e-4, atol=5e-2)
+        assert torch.allclose(st[N:], (yd * yd).sum(0), rtol=1e-4, atol=5e-2)
+
+
 def test_conv_unit_tc_vs_cuda_core_path():
     """The fused conv unit (train-mode BN, backward) on the tensor-core path vs the CUDA-core path, same bf16 inputs."""
     from nas_segm_b200.nn.layer_factory import conv_bn_relu
@@ -121,6 +145,16 @@ def test_tc_dgrad_is_the_same_kernel_with_transposed_pack():
     ref = dz.float().reshape(M, cout) @ w.reshape(cout, cin).to(torch.bfloat16).float()
     got = dx.permute(0, 2, 3, 1).float().reshape(M, cin)
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-2
+    # expand convolution of an inverted-residual block with 960 hidden channels: the data gradient has K = 960
+    cout, cin, M = 960, 160, 3872
+    dz = torch.randn(1, 1, M, cout, generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn(cout, cin, 1, 1, generator=g, device="cuda") / 30
+    dx = lib.new_act(1, cin, 1, M, torch.bfloat16, "cuda")
+    lib.call("nasb_pw_tc_fwd", lib.ref(lib.desc(dz.permute(0, 3, 1, 2))), lib.ptr(Fn._pack_weight(w, True)), cin, None, None,
+             lib.ACT_NONE, None, lib.ref(lib.desc(dx)), None)
+    ref = dz.float().reshape(M, cout) @ w.reshape(cout, cin).to(torch.bfloat16).float()
+    got = dx.permute(0, 2, 3, 1).float().reshape(M, cin)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-2
 
 
 def test_tc_wgrad_mn_major():
@@ -128,7 +162,7 @@ def test_tc_wgrad_mn_major():
     g = torch.Generator(device="cuda").manual_seed(3)
     bad = []
     for Co, Ci in [(64, 64), (96, 16), (24, 96), (144, 24), (32, 144), (64, 128), (64, 224), (192, 32), (48, 24), (8, 8),
-                   (256, 64), (16, 256)]:
+                   (256, 64), (16, 256), (960, 160), (160, 960), (320, 960), (40, 520)]:  # > 256 input channels: x channel blocks
         assert lib.load().nasb_pw_tc_wgrad_supported(Co, Ci) == 1, (Co, Ci)
         for M in (1, 127, 128, 300, 20011):
             dz = torch.randn(1, 1, M, Co, generator=g, device="cuda").to(torch.bfloat16)

@@ -278,7 +278,9 @@ def _():
 # (n, h, w, cin, cout, stats)
 PW_SHAPES = [(8, 512, 1024, 16, 96, 1), (8, 256, 512, 24, 144, 1), (8, 256, 512, 144, 24, 1), (8, 512, 1024, 32, 32, 1),
              (8, 512, 1024, 96, 16, 0), (8, 256, 512, 224, 64, 1), (8, 128, 256, 32, 192, 1), (8, 128, 256, 192, 32, 1),
-             (8, 128, 256, 32, 32, 1), (8, 128, 256, 32, 64, 1), (8, 32, 64, 64, 64, 1), (8, 256, 512, 24, 24, 1)]
+             (8, 128, 256, 32, 32, 1), (8, 128, 256, 32, 64, 1), (8, 32, 64, 64, 64, 1), (8, 256, 512, 24, 24, 1),
+             # MobileNet-v2's last stage at the search loop's task-1 geometry (batch 32 @350x350 -> 11x11): K-ring mode
+             (32, 11, 11, 960, 160, 1), (32, 11, 11, 160, 960, 1), (32, 11, 11, 960, 320, 1)]
 
 
 @case("pw_tc_fwd")
