@@ -492,11 +492,17 @@ __global__ void pack_conv3_kernel(const float *w, int Co, int Ci, int mode, bf16
     out[i] = __float2bfloat16_rn(v);
 }
 
-// 128-pixel patch TH x TW: the shape that wastes the fewest pixels on the image edges (W = 88: 4 x 32 covers 96 columns,
-// 2 x 64 would cover 128); ties go to the wider patch (TH == 1 enables the row-halo ring)
+// 128-pixel patch TH x TW.  Rows of at least 64 pixels use one image row per patch (TH == 1): that enables the row-halo ring,
+// which stages 3 row boxes per patch instead of 9 tap boxes -- worth more than the edge pixels a 128-wide patch wastes on
+// e.g. W = 88.  Narrower images take the shape that wastes the fewest edge pixels (W = 44: 8 x 16), ties to the wider patch.
 static void pick_patch(int H, int W, int &TH, int &TW) {
+    if (W >= 64) {
+        TH = 1;
+        TW = 128;
+        return;
+    }
     long long best = -1;
-    for (int tw = 128; tw >= 16; tw >>= 1) {
+    for (int tw = 64; tw >= 16; tw >>= 1) {
         const int th = C3_TILE / tw;
         const long long area = (long long)cdiv(W, tw) * tw * ((long long)cdiv(H, th) * th);
         if (best < 0 || area < best) {

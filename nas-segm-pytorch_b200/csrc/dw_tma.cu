@@ -711,6 +711,32 @@ struct TilePlan {
     size_t smem;
 };
 
+// Dilated kernels (sep_conv_3x3_dil3, sep_conv_5x5_dil6 of the search space): the halo is 2*dil*(k-1)/2 pixels per side, so the
+// 8 x 32 patch of the dense path re-reads the input 7 times through TMA (k = 5, dil = 6: 32 x 56 input pixels for 256 outputs,
+// 8 channels per box).  Here the patch may be up to 32 rows and use one CTA's whole shared memory (two buffers of <= 104 KB):
+// the plan minimises input pixels per output pixel, counting boxes narrower than a 32-byte sector as 1.5 times as expensive.
+static bool plan_tiles_dilated(int C, int ks, int dil, size_t extra_per_cc, TilePlan &pl) {
+    const size_t budget = 104 * 1024;
+    const int tw = 32;
+    double best = 0.0;
+    bool found = false;
+    for (int cci = 64; cci >= 8; cci -= 8) {
+        if (C % cci) continue;
+        for (int th = 32; th >= 4; th >>= 1) {
+            const int ith = th - 1 + (ks - 1) * dil + 1, itw = tw - 1 + (ks - 1) * dil + 1;
+            const size_t bytes = (size_t)ith * itw * cci * 2 + extra_per_cc * cci + 1024;
+            if (bytes > budget || ith > 256 || itw > 256) continue;
+            const double cost = (double)ith * itw / ((double)th * tw) * (cci >= 16 ? 1.0 : 1.5);
+            if (!found || cost < best - 1e-9) {
+                best = cost;
+                pl = {cci, th, tw, ith, itw, bytes};
+                found = true;
+            }
+        }
+    }
+    return found;
+}
+
 static bool plan_tiles(int C, int ks, int stride, int dil, size_t extra_per_cc, size_t budget, TilePlan &pl) {
     int cc = pick_cc(C);
     if (!cc) return false;
@@ -760,7 +786,10 @@ static int dw_tile_launch(const NasbTensor *x, const float *weight, int ks, int 
         if (eh != out->h || ew != out->w) return NASB_ERR_BAD_ARG;
     }
     TilePlan pl;
-    if (!plan_tiles(x->c, ks, stride, dil, (size_t)ks * ks * 4, 48 * 1024, pl)) return NASB_ERR_UNSUPPORTED;  // x2 buffers
+    const bool big_halo = dil > 1 && stride == 1;
+    if (big_halo ? !plan_tiles_dilated(x->c, ks, dil, (size_t)ks * ks * 4, pl)
+                 : !plan_tiles(x->c, ks, stride, dil, (size_t)ks * ks * 4, 48 * 1024, pl))
+        return NASB_ERR_UNSUPPORTED;  // x2 buffers
     if (npix(*out) == 0) return 0;
     DwT p{};
     p.N = x->n;
@@ -802,7 +831,7 @@ static int dw_tile_launch(const NasbTensor *x, const float *weight, int ks, int 
     const size_t tile_b = ((size_t)pl.ITH * pl.ITW * pl.CC * 2 + 127) & ~(size_t)127;
     size_t smem = 2 * tile_b + (size_t)ks * ks * pl.CC * 4 + (size_t)2 * pl.CC * 4 + 16 + 256;
     const int CVn = pl.CC / 8, nstrips = (pl.TH / DW_P) * pl.TW;
-    int L = 64;
+    int L = big_halo ? 128 : 64;  // one CTA per SM with the large dilated patches: more lanes instead of more CTAs
     while (L * CVn > 256 || L > nstrips) L >>= 1;
     const int threads = L * CVn;
     typedef void (*Kern)(const CUtensorMap, const DwT);
@@ -818,7 +847,7 @@ static int dw_tile_launch(const NasbTensor *x, const float *weight, int ks, int 
     const int ki = ks == 3 ? 0 : 1, si = (dil == 1 && stride <= 2) ? stride : 0, ti = gate ? 2 : (stats ? 1 : 0);
     Kern kern = kerns[ki][si][ti];
     if (!cfg[ki][si][ti]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, si == 0 ? 216 * 1024 : 100 * 1024) != cudaSuccess)
             return NASB_ERR_UNSUPPORTED;
         cfg[ki][si][ti] = true;
     }
@@ -842,6 +871,8 @@ extern "C" int nasb_dwconv_wgrad_tile(const NasbTensor *x, const NasbTensor *dz,
     if ((ks != 3 && ks != 5) || !vec_ok(*x, 8) || !vec_ok(*dz, 8)) return NASB_ERR_UNSUPPORTED;
     TilePlan pl;
     // extra per channel: the dz patch (TH*TW <= 8*32 pixels) * 2 bytes
+    // (the large dilated patches of the forward kernel are not used here: with K column groups per channel vector the CTA has
+    // 160 threads, and one such CTA per SM hides less latency than the three small ones)
     if (!plan_tiles(x->c, ks, stride, dil, (size_t)8 * 32 * 2, 48 * 1024, pl)) return NASB_ERR_UNSUPPORTED;  // x2 buffers
     if (npix(*dz) == 0) return 0;
     DwW p{};

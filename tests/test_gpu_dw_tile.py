@@ -14,6 +14,8 @@ CASES = [  # C, k, stride, dil, pad, H, W
     (192, 3, 1, 1, 1, 16, 32), (24, 5, 1, 1, 2, 40, 72), (32, 5, 1, 1, 2, 19, 23), (64, 5, 1, 1, 2, 8, 9),
     (48, 5, 2, 1, 2, 37, 53), (32, 5, 1, 6, 12, 33, 47), (64, 3, 1, 3, 3, 21, 34), (16, 3, 1, 1, 1, 5, 7),
     (64, 3, 2, 1, 1, 1, 1),
+    # the search space's dilated separable ops at the search loop's map sizes (large patches of the dilated plan)
+    (48, 5, 1, 6, 12, 64, 64), (48, 5, 1, 6, 12, 88, 88), (48, 3, 1, 3, 3, 88, 50), (64, 5, 1, 6, 12, 11, 11), (40, 3, 1, 3, 3, 9, 70),
 ]
 
 

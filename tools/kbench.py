@@ -156,7 +156,9 @@ def _():
 DW_SHAPES = [(8, 144, 256, 512, 3, 1, 1, 1), (8, 32, 512, 1024, 3, 1, 1, 1), (8, 24, 256, 512, 5, 1, 1, 2),
              (8, 32, 128, 256, 5, 1, 1, 2), (8, 32, 128, 256, 5, 1, 6, 12), (8, 192, 128, 256, 3, 1, 1, 1),
              (8, 96, 512, 1024, 3, 2, 1, 1), (8, 144, 256, 512, 3, 2, 1, 1), (8, 64, 128, 256, 5, 1, 1, 2),
-             (8, 32, 256, 512, 3, 1, 1, 1), (8, 64, 32, 64, 5, 1, 1, 2)]
+             (8, 32, 256, 512, 3, 1, 1, 1), (8, 64, 32, 64, 5, 1, 1, 2),
+             # dilated separable ops of the search space at the search loop's geometry
+             (64, 48, 64, 64, 5, 1, 6, 12), (32, 48, 88, 88, 5, 1, 6, 12), (64, 48, 64, 64, 3, 1, 3, 3)]
 
 
 def _ohw(h, w, ks, s, d, p):
@@ -326,8 +328,7 @@ def _():
 
 @case("conv3_tc")
 def _():
-    n, h, w = 8, 256, 512
-    for ci, co, odt in [(64, 19, torch.float32), (24, 64, BF)]:
+    for n, h, w, ci, co, odt in [(8, 256, 512, 64, 19, torch.float32), (8, 256, 512, 24, 64, BF), (32, 88, 88, 48, 48, BF), (64, 64, 64, 48, 21, torch.float32)]:
         cip = (ci + 7) // 8 * 8
         xb = torch.randn(n, h, w, cip, device=DEV).to(BF)
         x = xb[..., :ci].permute(0, 3, 1, 2)

@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out/c25; mkdir -p $O
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file $O/search_launches.csv python tools/search_profile.py --graphs > $O/search_launches.log 2>&1; echo "ncu launches rc=$?" >> $O/rc.txt
+gzip -f $O/search_launches.csv
+timeout -k 10 400 python tools/search_cprofile.py $O/search_cprofile.txt > $O/search_cprofile.log 2>&1; echo "cprofile rc=$?" >> $O/rc.txt
+cat $O/rc.txt
