@@ -1,0 +1,4 @@
+#!/bin/bash
+O=gpurun_out/c28; mkdir -p $O
+timeout -k 10 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo "bench n2 rc=$?" >> $O/rc.txt
+cat $O/rc.txt
