@@ -282,6 +282,20 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
             ev.record(copy_stream)
         return im, tg, ev
 
+    # The running loss is read back with ONE iteration of lag: iteration i's value is copied into pinned memory behind its
+    # kernels and logged after iteration i+1 has been launched, so the host never drains the GPU to print a line (the
+    # reference's `.item()` right after the step leaves the device idle for the host's launch latency every print_every
+    # iterations; with print_every = 1 that was 1.2 ms of a 23 ms iteration).  Same values, same lines, one launch later.
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    pending = []
+
+    def flush_log():
+        while pending:
+            pi, pn, buf, ev = pending.pop(0)
+            ev.synchronize()
+            logger.info(" Train epoch: {} [{}/{}]\tAvg. Loss: {:.3f}\tAvg. Time: {:.3f}".format(
+                epoch, pi, len(train_loader), float(buf[0]) / pn, (time.time() - start) / pn))
+
     ahead, i = upload(), -1
     while ahead is not None:
         image, target, ready = ahead
@@ -311,6 +325,11 @@ def train_segmenter(segmenter, train_loader, optim_enc, optim_dec, epoch, segm_c
         # (clone: a replayed graph returns the SAME static loss tensor every iteration -- an alias would be overwritten)
         loss_sum = loss.detach().clone() if loss_sum is None else loss_sum + loss.detach()
         n_it += 1
+        flush_log()  # the line of the previous print iteration: its loss arrived while this iteration was being launched
         if i % print_every == 0:
-            logger.info(" Train epoch: {} [{}/{}]\tAvg. Loss: {:.3f}\tAvg. Time: {:.3f}".format(
-                epoch, i, len(train_loader), float(loss_sum.item()) / n_it, (time.time() - start) / n_it))
+            buf = host_loss  # free again: flush_log() above has consumed the previous line
+            buf.copy_(loss_sum.reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((i, n_it, buf, ev))
+    flush_log()
