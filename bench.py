@@ -61,6 +61,7 @@ def args_():
     ap.add_argument("--profile-out", default=None, help="write the per-call CUDA-event table of one instrumented step")
     ap.add_argument("--depth-head-only", action="store_true", help="(internal) print the BASELINE config-5 timings as JSON and exit")
     ap.add_argument("--metric-only", action="store_true", help="(internal) print the confusion-matrix timings as JSON and exit")
+    ap.add_argument("--augment-only", action="store_true", help="(internal) print the batch-augmentation timings as JSON and exit")
     ap.add_argument("--n-task0", type=int, default=4000, help="search workload: cached task0 crops per candidate")
     ap.add_argument("--task1-iters", type=int, default=297, help="search workload: train_segmenter iterations of task 1 "
                     "(297 = one epoch of batch 32 over the reference's 90 %% meta-train split of VOC train+)")
@@ -414,6 +415,62 @@ def run_torch_b200(a):
     print(json.dumps({"impl": "torch_b200", "metric": METRIC, "value": best, "unit": "images/s", "n_gpus": 1, "steps": a.steps,
                       "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "bf16", "data": "synthetic", "config": workload_config(a), "details": res}))
+
+
+# ------------------------------------------------------------------------------------------------- augmentation (row f3)
+def augment_numbers(dev):
+    """The training transform chain of src/data/loaders.py:43-56 for a batch of 32 VOC-sized images (375x500 -> ResizeScale(400,
+    0.7-1.4) -> mirror -> 350x350 crop -> normalise) through nas_segm_b200.data (one kernel launch): from pinned-able host
+    uint8 arrays (raw bytes uploaded inside the timed region) and from device-resident raw images; beside it the same chain
+    with cv2 / numpy calls on ONE host core (what one loader worker of the reference does per image)."""
+    from nas_segm_b200.data import GpuTrainTransform
+    rs = np.random.RandomState(0)
+    norm = (1.0 / 255, np.array([0.485, 0.456, 0.406]).reshape((1, 1, 3)), np.array([0.229, 0.224, 0.225]).reshape((1, 1, 3)))
+    host = [{"image": rs.randint(0, 256, (375, 500, 3)).astype(np.uint8), "mask": rs.randint(0, 21, (375, 500)).astype(np.uint8)}
+            for _ in range(32)]
+    resident = [{"image": torch.from_numpy(h["image"]).to(dev), "mask": torch.from_numpy(h["mask"]).to(dev)} for h in host]
+    t = GpuTrainTransform(400, 0.7, 1.4, False, 350, norm, device=dev)
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, batch in (("host_uint8", host), ("device_uint8", resident)):
+        np.random.seed(1)
+        for _ in range(3):
+            t(batch)
+        torch.cuda.synchronize()
+        w0 = time.time()
+        e0.record()
+        for _ in range(10):
+            o = t(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        out["augment_b32_375x500_to_350_%s_ms" % name] = e0.elapsed_time(e1) / 10
+        out["augment_b32_%s_images_per_s_wall" % name] = 320.0 / (time.time() - w0)
+    out["h2d_bytes_per_image_raw_uint8"] = 375 * 500 * 4
+    out["h2d_bytes_per_image_reference_float32_crop"] = 350 * 350 * 3 * 4 + 350 * 350
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        np.random.seed(1)
+        w0, n = time.time(), 0
+        while time.time() - w0 < 3.0:
+            s = host[n % 32]
+            sc = np.random.uniform(0.7, 1.4)
+            sc = max(sc, 400.0 / 375)
+            im = cv2.resize(s["image"], None, fx=sc, fy=sc, interpolation=cv2.INTER_CUBIC)
+            mk = cv2.resize(s["mask"], None, fx=sc, fy=sc, interpolation=cv2.INTER_NEAREST)
+            if np.random.randint(2):
+                im, mk = cv2.flip(im, 1), cv2.flip(mk, 1)
+            top, left = np.random.randint(0, im.shape[0] - 350 + 1), np.random.randint(0, im.shape[1] - 350 + 1)
+            im, mk = im[top:top + 350, left:left + 350], mk[top:top + 350, left:left + 350]
+            im = ((norm[0] * im - norm[1]) / norm[2]).transpose(2, 0, 1)
+            torch.from_numpy(np.ascontiguousarray(im)).float()
+            n += 1
+        out["cv2_chain_images_per_s_1core"] = n / (time.time() - w0)
+        out["cv2_version"] = cv2.__version__
+    except Exception as e:  # noqa: BLE001
+        out["cv2_chain_error"] = repr(e)[:200]
+    out["check"] = "bit-exact vs the reference's transform classes: tests/test_gpu_augment.py (fixture tests/golden/augment.npz)"
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------ metric (fast_cm)
@@ -781,6 +838,10 @@ def main():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         print(json.dumps(metric_numbers(torch.device("cuda", torch.cuda.current_device()))))
         return
+    if a.augment_only:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        print(json.dumps(augment_numbers(torch.device("cuda", torch.cuda.current_device()))))
+        return
     if a.workload == "search":
         return run_search(a)
     if a.depth_head_only:
@@ -972,6 +1033,8 @@ def main():
             extras["torch_b200"] = tb.get("details", tb)
             # confusion-matrix kernels vs HBM roofline, Cython fast_cm beside them
             extras["metric"] = child(["--metric-only"], 180)
+            # row f3: the loaders' transform chain as one kernel over raw uint8 batches, one cv2 worker beside it
+            extras["augment"] = child(["--augment-only"], 120)
             # BASELINE config 4 through engine.search (task0 + task1, TaskPerformer, per-candidate rebuild + capture)
             sb = child(["--workload", "search", "--steps", "3", "--warmup", "1"], 480)
             sb.pop("config", None)

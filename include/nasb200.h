@@ -418,6 +418,26 @@ int nasb_sep_unit_infer(const NasbTensor *x, const NasbConvUnit *udw, void *scra
                         const NasbConvUnit *upw, void *scratch_pw, long long scratch_pw_bytes, const NasbTensor *res,
                         const NasbTensor *out, int flags, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Row f3: the per-sample transform chain of the data loaders as ONE kernel over a batch of raw uint8 images
+ * (reference: src/data/datasets.py:135-165 ResizeScale, :168-189 RandomMirror, :91-116 RandomCrop, :64-88 CentralCrop,
+ * :192-208 Normalise, :211-220 ToTensor; composed in src/data/loaders.py:43-64).  The HOST draws the random parameters in
+ * the reference's order and fills one NasbAugSample per image; the device computes cv2.resize(INTER_CUBIC) of the image /
+ * cv2.resize(INTER_NEAREST) of the mask at factor `scale`, the optional horizontal flip, the crop window
+ * [top, top+out_h) x [left, left+out_w) and (norm_scale * v - mean) / std in float64 rounded to float32 -- bit-exact with
+ * OpenCV's own 8-bit resize (what cv2 computes with cv2.ipp.setUseIPP(False); oracle/augment_oracle.py).
+ * image: device uint8 [h][w][3]; mask: device uint8 [h][w]; rh, rw = round(h*scale), round(w*scale) (half to even).
+ * samples is a HOST array; out_image [n][3][out_h][out_w] float32 and out_mask [n][out_h][out_w] uint8 are device buffers. */
+typedef struct NasbAugSample {
+    const uint8_t *image;
+    const uint8_t *mask;
+    int32_t h, w, rh, rw;
+    double scale;
+    int32_t top, left, mirror, reserved;
+} NasbAugSample;
+int nasb_augment_batch(const NasbAugSample *samples, int n, int out_h, int out_w, double norm_scale, const double *mean,
+                       const double *stdv, float *out_image, uint8_t *out_mask, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,12 @@ class NasbConvUnit(C.Structure):
                 ("act", C.c_int32)]
 
 
+class NasbAugSample(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("mask", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("rh", C.c_int32),
+                ("rw", C.c_int32), ("scale", C.c_double), ("top", C.c_int32), ("left", C.c_int32), ("mirror", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 _TP = C.POINTER(NasbTensor)
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -105,6 +111,7 @@ _SIG = {
     "nasb_sepconv_tc_supported": [_I, _I, _I, _I, _I, _I],
     "nasb_sepconv_tc_fwd": [_TP, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _TP, _TP, _P],
     "nasb_sep_unit_infer": [_TP, _P, _P, _L, _P, _P, _L, _TP, _TP, _I, _P],
+    "nasb_augment_batch": [C.POINTER(NasbAugSample), _I, _I, _I, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, _P],
     "nasb_version": [],
 }
 _RET = {"nasb_version": C.c_char_p, "nasb_bn_stats_workspace": _L, "nasb_loss_workspace": _L, "nasb_pack_conv3_elems": _L,
