@@ -1,2 +1,2 @@
 """Device-side counterpart of the reference's data transforms (src/data/datasets.py): SURVEY 8(f) row f3."""
-from .augment import GpuTrainTransform, GpuValTransform, make_even, resized_size  # noqa: F401
+from .augment import AugmentedLoader, GpuTrainTransform, GpuValTransform, make_even, resized_size  # noqa: F401

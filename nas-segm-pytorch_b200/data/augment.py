@@ -135,3 +135,24 @@ class GpuValTransform(_GpuTransform):
             raise ValueError("CentralCrop(%d) of a %dx%d image: the reference's negative margins (python slicing from the end) "
                              "are not reproduced" % (self.crop_size, rh, rw))
         return float(scale), 0, top, left, self.crop_size, self.crop_size, rh, rw
+
+
+class AugmentedLoader(object):
+    """`AugmentedLoader(loader, transform)`: iterates a loader that yields lists of RAW samples (dataset without transform,
+    `collate_fn=lambda batch: batch`) and hands the engine device-side batches -- `engine.trainer.train_segmenter`,
+    `populate_task0` and `engine.inference.validate` consume it like the reference's own loaders (their
+    `sample["image"].float().cuda()` is then a no-op).  Attributes the engine looks up on a loader (`dataset.set_stage`,
+    `batch_sampler.batch_size`) are forwarded."""
+
+    def __init__(self, loader, transform):
+        self.loader, self.transform = loader, transform
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for raw in self.loader:
+            yield self.transform(raw)
+
+    def __getattr__(self, name):
+        return getattr(self.loader, name)

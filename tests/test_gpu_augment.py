@@ -103,3 +103,73 @@ def test_dataset_sized_batch_against_the_oracle():
         want_i, want_m = A.apply(s["image"], s["mask"], p, *ONORM)
         assert np.array_equal(out["image"][i].cpu().numpy(), want_i), i
         assert np.array_equal(out["mask"][i].cpu().numpy(), want_m), i
+
+
+@pytest.mark.gpu
+def test_train_segmenter_from_raw_batches_equals_training_on_the_reference_tensors():
+    """The augmentation inside the engine loop: `train_segmenter` fed by an AugmentedLoader over raw uint8 samples ends, weight for weight, where the run fed with the tensors the reference's transform chain (oracle) produces ends."""
+    import types
+
+    import torch.nn as nn
+
+    from nas_segm_b200.data import AugmentedLoader, GpuTrainTransform
+    from nas_segm_b200.engine import trainer
+    from nas_segm_b200.nn.encoders import mbv2
+    from nas_segm_b200.nn.micro_decoders import MicroDecoder
+
+    class Seg(nn.Module):
+        def __init__(self, enc, dec):
+            super().__init__()
+            self.encoder, self.decoder = enc, dec
+
+        def forward(self, x):
+            return self.decoder(self.encoder(x))
+
+    class Wrap(nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+        def forward(self, x):
+            return self.module(x)
+
+    class Loader(list):
+        class _DS:
+            def set_stage(self, s):
+                pass
+        dataset = _DS()
+        batch_sampler = types.SimpleNamespace(batch_size=4)
+
+    rs = np.random.RandomState(21)
+    raw = Loader([{"image": rs.randint(0, 256, (70 + 3 * j, 90 - 2 * j, 3)).astype(np.uint8),
+                   "mask": rs.randint(0, 5, (70 + 3 * j, 90 - 2 * j)).astype(np.uint8)} for j in range(4)] for _ in range(3))
+    cfg = (80, 0.8, 1.3, False, 64)
+    np.random.seed(17)
+    ref_batches = Loader()
+    for batch in raw:
+        ims, mks = [], []
+        for s in batch:
+            p = A.draw_train_params(s["image"].shape[0], s["image"].shape[1], *cfg)
+            a, b = A.apply(s["image"], s["mask"], p, *ONORM)
+            ims.append(torch.from_numpy(a))
+            mks.append(torch.from_numpy(b))
+        ref_batches.append({"image": torch.stack(ims), "mask": torch.stack(mks)})
+
+    def run(loader):
+        torch.manual_seed(0)
+        enc = mbv2()
+        c0 = [[8, [0, 0, 5, 2], [0, 2, 8, 8], [0, 5, 1, 4]], [[3, 3], [3, 2], [3, 0]]]
+        seg = Wrap(Seg(enc, MicroDecoder(list(enc.out_sizes), 5, c0, agg_size=16, aux_cell=True, repeats=1)).cuda())
+        oe = torch.optim.SGD(seg.module.encoder.parameters(), lr=1e-3, momentum=0.9)
+        od = torch.optim.SGD(seg.module.decoder.parameters(), lr=3e-3, momentum=0.9)
+        r = trainer.train_segmenter(seg, loader, oe, od, 0, nn.NLLLoss(ignore_index=255), True, 3.0, 3.0, False, print_every=1,
+                                    aux_weight=0.15)
+        assert r is None
+        torch.cuda.synchronize()
+        return [q.detach().clone() for q in seg.parameters()]
+
+    np.random.seed(17)
+    got = run(AugmentedLoader(raw, GpuTrainTransform(*cfg, NORM)))
+    want = run(ref_batches)
+    for a, b in zip(got, want):  # identical inputs; the atomically-reduced weight gradients may differ in the last bits
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), float((a - b).abs().max())
