@@ -5,6 +5,7 @@ replayed graph is what a latency-sensitive user runs.  The kernels take explicit
 tensor maps are passed by value, so the whole forward is capturable; torch's allocator serves the activations from the
 graph's private pool."""
 import contextlib
+import gc
 
 import torch
 
@@ -38,17 +39,28 @@ def shared_pool(device=None):
 def capture(graph, stream=None):
     """`with capture(g):` -- like `torch.cuda.graph(g)`, but into the shared pool and without the gc.collect() /
     empty_cache() of torch's context manager (which hands every cached block back to the driver, so the eager iterations
-    of the next candidate start with cudaMalloc again)."""
+    of the next candidate start with cudaMalloc again).  The cyclic collector is suspended for the duration instead."""
     torch.cuda.synchronize()
     pool = shared_pool()
     stream = torch.cuda.Stream() if stream is None else stream
     stream.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(stream):
-        graph.capture_begin(pool=pool)
-        try:
-            yield
-        finally:
-            graph.capture_end()
+    # The cyclic collector must not run while the stream is capturing: an unreachable graph of an earlier capture (modules and
+    # graph closures reference each other) would be destroyed from inside the capture, and cudaGraphExecDestroy / the pool
+    # release it triggers invalidate a global-mode capture ("operation failed due to a previous error during capture"; seen
+    # once the test suite's allocation pattern moved a generation-2 collection into a re-capture).  torch.cuda.graph avoids
+    # this with a full gc.collect() before every capture; suspending the collector costs nothing.
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.stream(stream):
+            graph.capture_begin(pool=pool)
+            try:
+                yield
+            finally:
+                graph.capture_end()
+    finally:
+        if gc_was_enabled:
+            gc.enable()
     torch.cuda.current_stream().wait_stream(stream)
 
 
