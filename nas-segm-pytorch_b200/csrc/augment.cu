@@ -33,6 +33,8 @@ struct AugParams {
     uint8_t *out_mask;     // [n][out_h][out_w]
 };
 
+// [host-replica: helpers begin]  (tests/test_augment_oracle.py compiles the text between these markers with g++, the
+// round-to-nearest intrinsics mapped to plain IEEE operations under -ffp-contract=off, and checks it against the fixture)
 // OpenCV interpolateCubic() + saturate_cast<short>(c * 2048), float32, no contraction
 __device__ __forceinline__ void cubic_coeffs(float x, int (&ic)[4]) {
     const float A = -0.75f;
@@ -59,10 +61,13 @@ __device__ __forceinline__ int cubic_taps(int d, double inv, int (&ic)[4]) {
     return (int)fl - 1;
 }
 
+// [host-replica: helpers end]
+
 __global__ void __launch_bounds__(256) augment_kernel(const __grid_constant__ AugTable tab, const AugParams p) {
     pdl_sync();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, si = blockIdx.z;
     if (x >= p.out_w) return;
+    // [host-replica: pixel begin]
     const NasbAugSample &s = tab.s[si];
     const int ry = s.top + y;
     int rx = s.left + x;
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(256) augment_kernel(const __grid_constant__ Au
         p.out_image[((size_t)si * 3 + c) * plane + o] = (float)v;
     }
     p.out_mask[(size_t)si * plane + o] = (uint8_t)m;
+    // [host-replica: pixel end]
 }
 
 }  // namespace nasb
